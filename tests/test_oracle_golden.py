@@ -114,7 +114,8 @@ def test_logdet_against_autograd_jacobian():
         jac = torch.autograd.functional.jacobian(f, y[r])
         sign, logabs = torch.linalg.slogdet(jac)
         _, ld = fo.stack_forward(lt, y[r:r + 1], h[r:r + 1])
-        assert abs(float(logabs) - float(ld[0])) < 1e-9
+        # Q from an fp32 QR has |det| = 1 only to ~1e-7, and the flow counts it as exactly 0
+        assert abs(float(logabs) - float(ld[0])) < 1e-5
 
 
 def test_macs_per_row_match_survey():
