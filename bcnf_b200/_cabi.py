@@ -1,0 +1,118 @@
+"""ctypes binding of include/bcnf_b200.h (the C-ABI shared library ``libbcnf_b200.so``).
+
+There is no fallback: if the library is missing or does not load, importing this module's
+``lib()`` raises, and every compute entry point of the package raises with it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+LIB_PATH = os.path.join(HERE, "libbcnf_b200.so")
+SOURCES = [os.path.join(HERE, "csrc", "bcnf_abi.cu")]
+HEADERS = [os.path.join(HERE, "csrc", n) for n in
+           ("common.cuh", "cond_project.cuh", "flow_rowthread.cuh", "flow_tiled.cuh")] + \
+          [os.path.join(REPO, "include", "bcnf_b200.h")]
+
+MAX_HIDDEN_LAYERS = 8
+OP_ACTNORM, OP_COUPLING, OP_ORTHO = 0, 1, 2
+PREC_FP32, PREC_BF16X3, PREC_BF16 = 0, 1, 2
+KERNEL_NAMES = {0: "rowthread", 1: "tiled", 2: "tcgen05"}
+
+EXPORTS = ["bcnf_abi_version", "bcnf_last_error", "bcnf_flow_create", "bcnf_flow_destroy",
+           "bcnf_flow_info", "bcnf_flow_set_params", "bcnf_cond_project", "bcnf_flow_forward",
+           "bcnf_flow_inverse"]
+
+
+class FlowDesc(C.Structure):
+    _fields_ = [("size", C.c_int32), ("n_conditions", C.c_int32), ("n_hidden", C.c_int32),
+                ("hidden", C.c_int32 * MAX_HIDDEN_LAYERS), ("two_way", C.c_int32), ("n_ops", C.c_int32),
+                ("precision", C.c_int32), ("device", C.c_int32)]
+
+
+FloatPP = C.POINTER(C.c_void_p)
+
+
+class OpParams(C.Structure):
+    _fields_ = [("type", C.c_int32), ("reserved", C.c_int32), ("scale", C.c_void_p), ("bias", C.c_void_p),
+                ("q", C.c_void_p), ("w_a", FloatPP), ("b_a", FloatPP), ("w_b", FloatPP), ("b_b", FloatPP)]
+
+
+class FlowInfo(C.Structure):
+    _fields_ = [("kernel", C.c_int32), ("proj_width", C.c_int32), ("n_half_couplings", C.c_int32),
+                ("rows_per_cta", C.c_int32), ("packed_bytes", C.c_int64), ("macs_per_row", C.c_int64),
+                ("macs_per_instance", C.c_int64)]
+
+
+def nvcc_command(out_path: str = LIB_PATH) -> list[str]:
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+            "-shared", "-Xcompiler", "-fPIC", "-o", out_path] + SOURCES
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(p) > t for p in SOURCES + HEADERS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA sources for sm_100a into ``libbcnf_b200.so`` (in-tree)."""
+    if force or needs_build():
+        cmd = nvcc_command()
+        if verbose:
+            print(" ".join(cmd), file=sys.stderr)
+        subprocess.run(cmd, check=True)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the shared library (once).  Raises if it is absent -- there is no CPU path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"bcnf_b200: {LIB_PATH} is not built. Run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU or PyTorch fallback for the coupling stack.")
+    L = C.CDLL(LIB_PATH)
+    L.bcnf_abi_version.restype = C.c_int
+    L.bcnf_last_error.restype = C.c_char_p
+    L.bcnf_flow_create.argtypes = [C.POINTER(FlowDesc), C.POINTER(C.c_int32), C.POINTER(C.c_void_p)]
+    L.bcnf_flow_destroy.argtypes = [C.c_void_p]
+    L.bcnf_flow_info.argtypes = [C.c_void_p, C.POINTER(FlowInfo)]
+    L.bcnf_flow_set_params.argtypes = [C.c_void_p, C.POINTER(OpParams), C.c_void_p]
+    L.bcnf_cond_project.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    flow_args = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
+                 C.c_void_p, C.c_void_p]
+    L.bcnf_flow_forward.argtypes = flow_args
+    L.bcnf_flow_inverse.argtypes = flow_args
+    for name in EXPORTS:
+        if name not in ("bcnf_last_error",):
+            getattr(L, name).restype = C.c_int if name != "bcnf_last_error" else C.c_char_p
+    L.bcnf_last_error.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+class BcnfError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().bcnf_last_error()
+        msg = msg.decode() if msg else ""
+        if rc == -2:
+            raise NotImplementedError(f"{what}: {msg}")
+        if rc == -1:
+            raise ValueError(f"{what}: {msg}")
+        raise BcnfError(f"{what} failed with code {rc}: {msg}")

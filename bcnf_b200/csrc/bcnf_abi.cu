@@ -1,0 +1,524 @@
+// C ABI of bcnf_b200 (include/bcnf_b200.h): handle management, parameter packing, dispatch.
+#include "../../include/bcnf_b200.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "cond_project.cuh"
+#include "flow_rowthread.cuh"
+#include "flow_tiled.cuh"
+
+using namespace bcnf;
+
+// ----------------------------------------------------------------------------------------------
+// error reporting
+// ----------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CUDA_TRY(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t e__ = (expr);                                                               \
+    if (e__ != cudaSuccess) return fail((int)e__, "%s: %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+
+// ----------------------------------------------------------------------------------------------
+// parameter packing: one table-driven kernel per set_params call
+// ----------------------------------------------------------------------------------------------
+struct PackDesc {
+  const float* src;
+  float* dst;
+  int src_pitch, rows, cols, dst_pitch;
+  int mode;  // 0 copy: dst[r*dp + c] = src[r*sp + c]; 1 transpose: dst[c*dp + r] = src[r*sp + c];
+             // 2 actnorm log-det: dst[0] = sum_r log|src[r]|
+  int pad;
+};
+
+__global__ void pack_kernel(const PackDesc* __restrict__ descs) {
+  const PackDesc d = descs[blockIdx.x];
+  if (d.mode == 2) {
+    if (blockIdx.y == 0 && threadIdx.x == 0) {
+      float s = 0.f;   // torch.sum(torch.log(torch.abs(scale))), cnf.py:350
+      for (int r = 0; r < d.rows; ++r) s += logf(fabsf(d.src[r]));
+      d.dst[0] = s;
+    }
+    return;
+  }
+  const long long n = (long long)d.rows * d.cols;
+  for (long long e = (long long)blockIdx.y * blockDim.x + threadIdx.x; e < n;
+       e += (long long)gridDim.y * blockDim.x) {
+    const int r = (int)(e / d.cols), c = (int)(e - (long long)r * d.cols);
+    const float v = d.src[(size_t)r * d.src_pitch + c];
+    if (d.mode == 0) d.dst[(size_t)r * d.dst_pitch + c] = v;
+    else             d.dst[(size_t)c * d.dst_pitch + r] = v;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// handle
+// ----------------------------------------------------------------------------------------------
+struct Program {
+  std::vector<DevOp> ops;
+  std::vector<Chunk> chunks;
+  DevOp* d_ops = nullptr;
+  Chunk* d_chunks = nullptr;
+  float* d_blob = nullptr;
+  long long blob_floats = 0;
+  int max_chunk_bytes = 0;
+};
+
+struct bcnf_flow {
+  bcnf_flow_desc_t desc;
+  std::vector<int> op_types;
+  StackDims sd;
+  int n_half = 0;
+  Program prog[2];  // 0 forward, 1 inverse
+  float* d_wproj = nullptr;  // (C, PW)
+  float* d_bproj = nullptr;  // (PW)
+  PackDesc* d_pack = nullptr;
+  PackDesc* h_pack = nullptr;  // pinned
+  int pack_cap = 0;
+  int kernel = BCNF_KERNEL_TILED;
+  int rows_per_cta = 0;
+  int num_sms = 148;
+  int max_smem_optin = 0;
+  bool params_set = false;
+  long long packed_bytes = 0;
+  long long macs_row = 0, macs_inst = 0;
+  // tiled launch configuration
+  TiledSmem tiled_lay;
+  int tiled_R = 32;
+};
+
+static const int kRowThreadChunkCap = 20 * 1024;  // bytes per streamed parameter chunk
+
+static void build_half_layout(HalfLayout& hl, int din, int dout, int L, const int* hidden) {
+  memset(&hl, 0, sizeof(hl));
+  hl.din = din; hl.dinp = round_up(din, 4);
+  hl.dout = dout; hl.dop = round_up(dout, 4);
+  hl.L = L;
+  int off = 0;
+  for (int l = 0; l < L; ++l) { hl.h[l] = hidden[l]; hl.hp[l] = round_up(hidden[l], 16); }
+  hl.off_w[0] = off; off += hl.dinp * hl.hp[0];
+  for (int l = 1; l < L; ++l) {
+    hl.off_w[l] = off; off += hl.hp[l - 1] * hl.hp[l];
+    hl.off_b[l] = off; off += hl.hp[l];
+  }
+  hl.off_wout = off; off += hl.hp[L - 1] * 2 * hl.dop;
+  hl.off_bout = off; off += 2 * hl.dop;
+  hl.total = round_up(off, 4);
+}
+
+static int op_param_floats(const bcnf_flow& f, const DevOp& op) {
+  switch (op.type) {
+    case DOP_ACTNORM_FWD:
+    case DOP_ACTNORM_INV: return 2 * f.sd.DP + 4;
+    case DOP_MIX: return f.sd.D * f.sd.DP;
+    default: return f.sd.half[op.src].total;
+  }
+}
+
+// Compile the layer list into the device program of one direction.
+static void build_program(bcnf_flow& f, int dir) {
+  Program& p = f.prog[dir];
+  p.ops.clear();
+  const int n = (int)f.op_types.size();
+  // projection slice of each conditioner network, in forward layer order
+  std::vector<int> proj_a(n, -1), proj_b(n, -1);
+  int pw = 0;
+  for (int i = 0; i < n; ++i)
+    if (f.op_types[i] == BCNF_OP_COUPLING) {
+      proj_a[i] = pw; pw += f.sd.half[0].hp[0];
+      if (f.desc.two_way) { proj_b[i] = pw; pw += f.sd.half[1].hp[0]; }
+    }
+  f.sd.PW = pw;
+  for (int s = 0; s < n; ++s) {
+    const int i = dir == 0 ? s : n - 1 - s;   // inverse walks reversed(self.layers), cnf.py:500
+    DevOp op{};
+    switch (f.op_types[i]) {
+      case BCNF_OP_ACTNORM:
+        op.type = dir == 0 ? DOP_ACTNORM_FWD : DOP_ACTNORM_INV;
+        p.ops.push_back(op);
+        break;
+      case BCNF_OP_ORTHO:
+        op.type = DOP_MIX;
+        p.ops.push_back(op);
+        break;
+      default:
+        // forward: nn_a then nn_b (cnf.py:178-184); the reference's inverse ALSO runs nn_a
+        // first, on z_a, and then nn_b on the recovered y_b (cnf.py:203-208) -- reproduced.
+        op.type = DOP_HALF; op.inverse = dir; op.src = 0; op.proj_off = proj_a[i];
+        p.ops.push_back(op);
+        if (f.desc.two_way) { op.src = 1; op.proj_off = proj_b[i]; p.ops.push_back(op); }
+        break;
+    }
+  }
+  long long off = 0;
+  for (auto& op : p.ops) { op.off = off; off += op_param_floats(f, op); }
+  p.blob_floats = off;
+  // chunks for the streaming kernel: greedy runs of ops up to the byte cap
+  p.chunks.clear();
+  p.max_chunk_bytes = 0;
+  Chunk cur{0, 0, 0, 0, 0};
+  for (int i = 0; i < (int)p.ops.size(); ++i) {
+    const int bytes = op_param_floats(f, p.ops[i]) * 4;
+    if (cur.n_ops > 0 && cur.bytes + bytes > kRowThreadChunkCap) {
+      p.chunks.push_back(cur);
+      cur = Chunk{p.ops[i].off, 0, i, 0, 0};
+    }
+    cur.bytes += bytes;
+    cur.n_ops += 1;
+    if (cur.bytes > p.max_chunk_bytes) p.max_chunk_bytes = cur.bytes;
+  }
+  if (cur.n_ops > 0) p.chunks.push_back(cur);
+}
+
+static void free_program(Program& p) {
+  if (p.d_ops) cudaFree(p.d_ops);
+  if (p.d_chunks) cudaFree(p.d_chunks);
+  if (p.d_blob) cudaFree(p.d_blob);
+  p.d_ops = nullptr; p.d_chunks = nullptr; p.d_blob = nullptr;
+}
+
+extern "C" int bcnf_abi_version(void) { return BCNF_ABI_VERSION; }
+extern "C" const char* bcnf_last_error(void) { return g_err; }
+
+extern "C" int bcnf_flow_destroy(bcnf_flow_t* f) {
+  if (!f) return BCNF_OK;
+  cudaSetDevice(f->desc.device);
+  free_program(f->prog[0]);
+  free_program(f->prog[1]);
+  if (f->d_wproj) cudaFree(f->d_wproj);
+  if (f->d_bproj) cudaFree(f->d_bproj);
+  if (f->d_pack) cudaFree(f->d_pack);
+  if (f->h_pack) cudaFreeHost(f->h_pack);
+  delete f;
+  return BCNF_OK;
+}
+
+template <typename K>
+static int opt_in_smem(K kernel, size_t bytes) {
+  CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+
+extern "C" int bcnf_flow_create(const bcnf_flow_desc_t* desc, const int32_t* op_types, bcnf_flow_t** out) {
+  if (!desc || !op_types || !out) return fail(BCNF_E_ARG, "bcnf_flow_create: null argument");
+  *out = nullptr;
+  if (desc->size < 2 || desc->size > BCNF_MAX_SIZE)
+    return fail(BCNF_E_UNSUPPORTED, "size=%d outside [2, %d]", desc->size, BCNF_MAX_SIZE);
+  if (desc->n_conditions < 1)
+    return fail(BCNF_E_UNSUPPORTED, "n_conditions=%d: the reference's unconditional path is broken "
+                                    "(cnf.py:480-485) and is not provided", desc->n_conditions);
+  if (desc->n_hidden < 1 || desc->n_hidden > BCNF_MAX_HIDDEN_LAYERS)
+    return fail(BCNF_E_UNSUPPORTED, "len(nested_sizes)=%d outside [1, %d]", desc->n_hidden, BCNF_MAX_HIDDEN_LAYERS);
+  for (int l = 0; l < desc->n_hidden; ++l)
+    if (desc->hidden[l] < 1 || desc->hidden[l] > BCNF_MAX_HIDDEN)
+      return fail(BCNF_E_UNSUPPORTED, "nested_sizes[%d]=%d outside [1, %d]", l, desc->hidden[l], BCNF_MAX_HIDDEN);
+  if (desc->n_ops < 1) return fail(BCNF_E_ARG, "empty layer list");
+  if (desc->precision != BCNF_PREC_FP32)
+    return fail(BCNF_E_UNSUPPORTED, "precision %d not built in this version", desc->precision);
+  for (int i = 0; i < desc->n_ops; ++i)
+    if (op_types[i] < 0 || op_types[i] > 2)
+      return fail(BCNF_E_ARG, "layer %d has unknown type %d", i, op_types[i]);   // cnf.py:485
+
+  CUDA_TRY(cudaSetDevice(desc->device));
+  bcnf_flow* f = new (std::nothrow) bcnf_flow();
+  if (!f) return fail(BCNF_E_NOMEM, "out of host memory");
+  f->desc = *desc;
+  f->op_types.assign(op_types, op_types + desc->n_ops);
+  StackDims& sd = f->sd;
+  memset(&sd, 0, sizeof(sd));
+  sd.D = desc->size; sd.DP = round_up(sd.D, 4);
+  sd.Da = (sd.D + 1) / 2; sd.Db = sd.D / 2;
+  sd.C = desc->n_conditions;
+  build_half_layout(sd.half[0], sd.Da, sd.Db, desc->n_hidden, desc->hidden);   // nn_a, cnf.py:136
+  build_half_layout(sd.half[1], sd.Db, sd.Da, desc->n_hidden, desc->hidden);   // nn_b, cnf.py:150
+  build_program(*f, 0);
+  build_program(*f, 1);
+  f->n_half = 0;
+  for (auto& op : f->prog[0].ops) f->n_half += op.type == DOP_HALF;
+
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, desc->device));
+  f->num_sms = prop.multiProcessorCount;
+  f->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+
+  // algorithmic work
+  {
+    long long per_half[2];
+    for (int s = 0; s < 2; ++s) {
+      const HalfLayout& hl = sd.half[s];
+      long long m = (long long)hl.din * hl.h[0];
+      for (int l = 1; l < hl.L; ++l) m += (long long)hl.h[l - 1] * hl.h[l];
+      m += (long long)hl.h[hl.L - 1] * 2 * hl.dout;
+      per_half[s] = m;
+    }
+    f->macs_row = 0; f->macs_inst = 0;
+    for (auto& op : f->prog[0].ops) {
+      if (op.type == DOP_HALF) { f->macs_row += per_half[op.src]; f->macs_inst += (long long)sd.C * sd.half[op.src].h[0]; }
+      else if (op.type == DOP_MIX) f->macs_row += (long long)sd.D * sd.D;
+      else f->macs_row += sd.D;
+    }
+  }
+
+  // kernel selection
+  bool uniform = true;
+  for (int l = 1; l < desc->n_hidden; ++l) uniform &= desc->hidden[l] == desc->hidden[0];
+  const int hp0 = sd.half[0].hp[0];
+  const char* force = getenv("BCNF_FORCE_KERNEL");   // "tiled": exercise the generic path on narrow stacks
+  const bool allow_rowthread = !(force && strcmp(force, "tiled") == 0);
+  const bool rowthread_ok = allow_rowthread && uniform && (hp0 == 16 || hp0 == 32) && (sd.D == 19 || sd.D == 21) &&
+                            std::max(f->prog[0].max_chunk_bytes, f->prog[1].max_chunk_bytes) <= kRowThreadChunkCap;
+  if (rowthread_ok) {
+    f->kernel = BCNF_KERNEL_ROWTHREAD;
+    f->rows_per_cta = kRowThreadBlock;
+  } else {
+    f->kernel = BCNF_KERNEL_TILED;
+    int hpmax = 0;
+    for (int l = 0; l < desc->n_hidden; ++l) hpmax = std::max(hpmax, sd.half[0].hp[l]);
+    TiledSmem lay;
+    lay.YP = round_up(sd.D, 4);
+    lay.XP = std::max(sd.half[0].dinp, sd.half[1].dinp);
+    lay.TP = 2 * std::max(sd.half[0].dop, sd.half[1].dop);
+    lay.AP = hpmax + 4;
+    f->tiled_lay = lay;
+    f->tiled_R = lay.bytes(32) <= (size_t)f->max_smem_optin ? 32 : 16;
+    if (lay.bytes(f->tiled_R) > (size_t)f->max_smem_optin) {
+      delete f;
+      return fail(BCNF_E_UNSUPPORTED, "row tile needs %zu bytes of shared memory", lay.bytes(16));
+    }
+    f->rows_per_cta = f->tiled_R;
+  }
+
+  // device storage
+  long long bytes = 0;
+  for (int d = 0; d < 2; ++d) {
+    Program& p = f->prog[d];
+    if (cudaMalloc(&p.d_blob, p.blob_floats * 4) != cudaSuccess ||
+        cudaMalloc(&p.d_ops, p.ops.size() * sizeof(DevOp)) != cudaSuccess ||
+        cudaMalloc(&p.d_chunks, p.chunks.size() * sizeof(Chunk)) != cudaSuccess) {
+      cudaGetLastError();
+      bcnf_flow_destroy(f);
+      return fail(BCNF_E_NOMEM, "device allocation of %lld bytes failed", p.blob_floats * 4);
+    }
+    cudaMemcpy(p.d_ops, p.ops.data(), p.ops.size() * sizeof(DevOp), cudaMemcpyHostToDevice);
+    cudaMemcpy(p.d_chunks, p.chunks.data(), p.chunks.size() * sizeof(Chunk), cudaMemcpyHostToDevice);
+    bytes += p.blob_floats * 4;
+  }
+  const size_t wproj_bytes = (size_t)sd.C * sd.PW * 4;
+  if (cudaMalloc(&f->d_wproj, wproj_bytes) != cudaSuccess || cudaMalloc(&f->d_bproj, (size_t)sd.PW * 4) != cudaSuccess) {
+    cudaGetLastError();
+    bcnf_flow_destroy(f);
+    return fail(BCNF_E_NOMEM, "device allocation of %zu bytes failed", wproj_bytes);
+  }
+  bytes += wproj_bytes + (size_t)sd.PW * 4;
+  // pack table: per direction, per op at most 2*(L+1)+2 descriptors; projection 2 per half
+  f->pack_cap = 2 * (int)f->prog[0].ops.size() * (2 * desc->n_hidden + 6) + 4 * f->n_half + 16;
+  if (cudaMalloc(&f->d_pack, f->pack_cap * sizeof(PackDesc)) != cudaSuccess ||
+      cudaMallocHost(&f->h_pack, f->pack_cap * sizeof(PackDesc)) != cudaSuccess) {
+    cudaGetLastError();
+    bcnf_flow_destroy(f);
+    return fail(BCNF_E_NOMEM, "pack table allocation failed");
+  }
+  f->packed_bytes = bytes;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { bcnf_flow_destroy(f); return fail((int)e, "create: %s", cudaGetErrorString(e)); }
+  *out = f;
+  return BCNF_OK;
+}
+
+extern "C" int bcnf_flow_info(const bcnf_flow_t* f, bcnf_flow_info_t* info) {
+  if (!f || !info) return fail(BCNF_E_ARG, "bcnf_flow_info: null argument");
+  info->kernel = f->kernel;
+  info->proj_width = f->sd.PW;
+  info->n_half_couplings = f->n_half;
+  info->rows_per_cta = f->rows_per_cta;
+  info->packed_bytes = f->packed_bytes;
+  info->macs_per_row = f->macs_row;
+  info->macs_per_instance = f->macs_inst;
+  return BCNF_OK;
+}
+
+// Emit the pack descriptors of one conditioner network into `v`.
+static int emit_half(const bcnf_flow& f, const HalfLayout& hl, float* dst, const float* const* w,
+                     const float* const* b, int proj_off, bool with_proj, std::vector<PackDesc>& v) {
+  const int L = hl.L, C = f.sd.C;
+  for (int j = 0; j <= L; ++j)
+    if (!w || !b || !w[j] || !b[j]) return fail(BCNF_E_ARG, "coupling layer is missing Linear %d parameters", j);
+  const int in_total = hl.din + C;   // sizes[0] += n_conditions, cnf.py:72
+  // first Linear, own-half columns -> W1a (k-major)
+  v.push_back({w[0], dst + hl.off_w[0], in_total, hl.h[0], hl.din, hl.hp[0], 1, 0});
+  if (with_proj) {
+    // first Linear, feature columns -> projection matrix; bias -> projection bias
+    v.push_back({w[0] + hl.din, f.d_wproj + proj_off, in_total, hl.h[0], C, f.sd.PW, 1, 0});
+    v.push_back({b[0], f.d_bproj + proj_off, hl.h[0], 1, hl.h[0], hl.hp[0], 0, 0});
+  }
+  for (int l = 1; l < L; ++l) {
+    v.push_back({w[l], dst + hl.off_w[l], hl.h[l - 1], hl.h[l], hl.h[l - 1], hl.hp[l], 1, 0});
+    v.push_back({b[l], dst + hl.off_b[l], hl.h[l], 1, hl.h[l], hl.hp[l], 0, 0});
+  }
+  // last Linear: rows [0, dout) are t, rows [dout, 2 dout) are s (chunk(2, dim=1), cnf.py:104)
+  const int hin = hl.h[L - 1];
+  v.push_back({w[L], dst + hl.off_wout, hin, hl.dout, hin, 2 * hl.dop, 1, 0});
+  v.push_back({w[L] + (size_t)hl.dout * hin, dst + hl.off_wout + hl.dop, hin, hl.dout, hin, 2 * hl.dop, 1, 0});
+  v.push_back({b[L], dst + hl.off_bout, hl.dout, 1, hl.dout, 2 * hl.dop, 0, 0});
+  v.push_back({b[L] + hl.dout, dst + hl.off_bout + hl.dop, hl.dout, 1, hl.dout, 2 * hl.dop, 0, 0});
+  return 0;
+}
+
+extern "C" int bcnf_flow_set_params(bcnf_flow_t* f, const bcnf_op_params_t* ops, void* stream_) {
+  if (!f || !ops) return fail(BCNF_E_ARG, "bcnf_flow_set_params: null argument");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CUDA_TRY(cudaSetDevice(f->desc.device));
+  const int n = (int)f->op_types.size();
+  std::vector<PackDesc> v;
+  v.reserve(f->pack_cap);
+  const StackDims& sd = f->sd;
+  for (int dir = 0; dir < 2; ++dir) {
+    Program& p = f->prog[dir];
+    CUDA_TRY(cudaMemsetAsync(p.d_blob, 0, p.blob_floats * 4, stream));
+    int oi = 0;
+    for (int s = 0; s < n; ++s) {
+      const int i = dir == 0 ? s : n - 1 - s;
+      const bcnf_op_params_t& src = ops[i];
+      if (src.type != f->op_types[i])
+        return fail(BCNF_E_ARG, "layer %d: type %d does not match the handle's %d", i, src.type, f->op_types[i]);
+      float* dst = p.d_blob + p.ops[oi].off;
+      if (src.type == BCNF_OP_ACTNORM) {
+        if (!src.scale || !src.bias) return fail(BCNF_E_ARG, "layer %d: ActNorm needs scale and bias", i);
+        v.push_back({src.scale, dst, sd.D, 1, sd.D, sd.DP, 0, 0});
+        v.push_back({src.bias, dst + sd.DP, sd.D, 1, sd.D, sd.DP, 0, 0});
+        v.push_back({src.scale, dst + 2 * sd.DP, 1, sd.D, 1, 1, 2, 0});
+        oi += 1;
+      } else if (src.type == BCNF_OP_ORTHO) {
+        if (!src.q) return fail(BCNF_E_ARG, "layer %d: orthonormal_matrix missing", i);
+        v.push_back({src.q, dst, sd.D, sd.D, sd.D, sd.DP, dir == 0 ? 0 : 1, 0});   // Q or Q^T
+        oi += 1;
+      } else {
+        int rc = emit_half(*f, sd.half[0], dst, src.w_a, src.b_a, p.ops[oi].proj_off, dir == 0, v);
+        if (rc) return rc;
+        oi += 1;
+        if (f->desc.two_way) {
+          float* dst_b = p.d_blob + p.ops[oi].off;
+          rc = emit_half(*f, sd.half[1], dst_b, src.w_b, src.b_b, p.ops[oi].proj_off, dir == 0, v);
+          if (rc) return rc;
+          oi += 1;
+        }
+      }
+    }
+  }
+  if ((int)v.size() > f->pack_cap) return fail(BCNF_E_STATE, "internal: pack table overflow");
+  CUDA_TRY(cudaMemsetAsync(f->d_wproj, 0, (size_t)sd.C * sd.PW * 4, stream));
+  CUDA_TRY(cudaMemsetAsync(f->d_bproj, 0, (size_t)sd.PW * 4, stream));
+  // the pinned staging table is reused: wait for the previous upload on this handle
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  memcpy(f->h_pack, v.data(), v.size() * sizeof(PackDesc));
+  CUDA_TRY(cudaMemcpyAsync(f->d_pack, f->h_pack, v.size() * sizeof(PackDesc), cudaMemcpyHostToDevice, stream));
+  pack_kernel<<<dim3((unsigned)v.size(), 8), 256, 0, stream>>>(f->d_pack);
+  CUDA_TRY(cudaGetLastError());
+  f->params_set = true;
+  return BCNF_OK;
+}
+
+extern "C" int bcnf_cond_project(bcnf_flow_t* f, const float* h, int64_t n_inst, float* P, void* stream_) {
+  if (!f || !h || !P) return fail(BCNF_E_ARG, "bcnf_cond_project: null argument");
+  if (n_inst < 0) return fail(BCNF_E_ARG, "n_inst=%lld", (long long)n_inst);
+  if (!f->params_set) return fail(BCNF_E_STATE, "bcnf_flow_set_params has not been called");
+  if (n_inst == 0) return BCNF_OK;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CUDA_TRY(cudaSetDevice(f->desc.device));
+  const int N = f->sd.PW, K = f->sd.C;
+  const long long max_rows = 65535LL * kProjBM;
+  for (long long m0 = 0; m0 < n_inst; m0 += max_rows) {
+    const long long m = std::min<long long>(max_rows, n_inst - m0);
+    dim3 grid((N + kProjBN - 1) / kProjBN, (unsigned)((m + kProjBM - 1) / kProjBM));
+    cond_project_kernel<<<grid, 256, 0, stream>>>(h + m0 * K, f->d_wproj, f->d_bproj, P + m0 * N, m, N, K);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return BCNF_OK;
+}
+
+template <int D, int HP>
+static int launch_rowthread(bcnf_flow* f, const FlowArgs& a, int dir, cudaStream_t stream) {
+  const Program& p = f->prog[dir];
+  const int cap = round_up(std::max(f->prog[0].max_chunk_bytes, f->prog[1].max_chunk_bytes), 128);
+  const size_t smem = 2 * (size_t)cap + 16;
+  auto kern = flow_rowthread_kernel<D, HP>;
+  static thread_local size_t configured = 0;
+  if (configured < smem) { if (int rc = opt_in_smem(kern, smem)) return rc; configured = smem; }
+  int occ = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kRowThreadBlock, smem));
+  if (occ < 1) return fail(BCNF_E_UNSUPPORTED, "row-per-thread kernel does not fit on an SM");
+  const long long tiles = (a.n_rows + kRowThreadBlock - 1) / kRowThreadBlock;
+  const int grid = (int)std::min<long long>(tiles, (long long)f->num_sms * occ);
+  (void)p;
+  kern<<<grid, kRowThreadBlock, smem, stream>>>(a, f->sd, cap);
+  CUDA_TRY(cudaGetLastError());
+  return BCNF_OK;
+}
+
+template <int R>
+static int launch_tiled(bcnf_flow* f, const FlowArgs& a, cudaStream_t stream) {
+  const size_t smem = f->tiled_lay.bytes(R);
+  auto kern = flow_tiled_kernel<R>;
+  static thread_local size_t configured = 0;
+  if (configured < smem) { if (int rc = opt_in_smem(kern, smem)) return rc; configured = smem; }
+  int occ = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kTiledThreads, smem));
+  if (occ < 1) return fail(BCNF_E_UNSUPPORTED, "tiled kernel does not fit on an SM (%zu bytes)", smem);
+  const long long tiles = (a.n_rows + R - 1) / R;
+  const int grid = (int)std::min<long long>(tiles, (long long)f->num_sms * occ);
+  kern<<<grid, kTiledThreads, smem, stream>>>(a, f->sd, f->tiled_lay);
+  CUDA_TRY(cudaGetLastError());
+  return BCNF_OK;
+}
+
+static int run_flow(bcnf_flow_t* f, int dir, const float* in, const float* P, const int32_t* row2inst,
+                    int64_t inst_period, int64_t n_rows, float* out, float* logdet, void* stream_) {
+  if (!f || !in || !P || !out) return fail(BCNF_E_ARG, "bcnf_flow_%s: null argument", dir ? "inverse" : "forward");
+  if (n_rows < 0 || inst_period < 0) return fail(BCNF_E_ARG, "negative size");
+  if (!f->params_set) return fail(BCNF_E_STATE, "bcnf_flow_set_params has not been called");
+  if (n_rows == 0) return BCNF_OK;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CUDA_TRY(cudaSetDevice(f->desc.device));
+  const Program& p = f->prog[dir];
+  FlowArgs a;
+  a.in = in; a.out = out; a.logdet = logdet; a.P = P; a.row2inst = row2inst;
+  a.inst_period = inst_period; a.n_rows = n_rows;
+  a.blob = p.d_blob; a.ops = p.d_ops; a.n_ops = (int)p.ops.size();
+  a.chunks = p.d_chunks; a.n_chunks = (int)p.chunks.size();
+  if (f->kernel == BCNF_KERNEL_ROWTHREAD) {
+    const int hp = f->sd.half[0].hp[0];
+    if (f->sd.D == 19 && hp == 16) return launch_rowthread<19, 16>(f, a, dir, stream);
+    if (f->sd.D == 19 && hp == 32) return launch_rowthread<19, 32>(f, a, dir, stream);
+    if (f->sd.D == 21 && hp == 16) return launch_rowthread<21, 16>(f, a, dir, stream);
+    if (f->sd.D == 21 && hp == 32) return launch_rowthread<21, 32>(f, a, dir, stream);
+    return fail(BCNF_E_STATE, "internal: no row-per-thread instance for D=%d HP=%d", f->sd.D, hp);
+  }
+  if (f->tiled_R == 32) return launch_tiled<32>(f, a, stream);
+  return launch_tiled<16>(f, a, stream);
+}
+
+extern "C" int bcnf_flow_forward(bcnf_flow_t* f, const float* y, const float* P, const int32_t* row2inst,
+                                 int64_t inst_period, int64_t n_rows, float* z, float* logdet, void* stream) {
+  return run_flow(f, 0, y, P, row2inst, inst_period, n_rows, z, logdet, stream);
+}
+
+extern "C" int bcnf_flow_inverse(bcnf_flow_t* f, const float* z, const float* P, const int32_t* row2inst,
+                                 int64_t inst_period, int64_t n_rows, float* x, float* logdet, void* stream) {
+  return run_flow(f, 1, z, P, row2inst, inst_period, n_rows, x, logdet, stream);
+}

@@ -1,0 +1,90 @@
+// Shared host/device definitions of the packed coupling-stack program.
+//
+// A stack (CondRealNVP_v2.layers, reference cnf.py:392-423) is compiled at set_params time
+// into a linear "program" of device ops, one program per direction, and one fp32 parameter
+// blob per direction laid out in program order so that any run of consecutive ops is one
+// contiguous byte range (the row-per-thread kernel streams such ranges with TMA bulk copies).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bcnf {
+
+enum DevOpType : int {
+  DOP_ACTNORM_FWD = 0,  // y = s*y + b ; ld += c          blob: s[DP] b[DP] c[4]
+  DOP_ACTNORM_INV = 1,  // y = (y-b)/s ; ld += c(=-?)     same blob
+  DOP_MIX = 2,          // y = y @ M                       blob: M[D][DP]   (M = Q or Q^T)
+  DOP_HALF = 3          // one conditioner network + affine update of the other half
+};
+
+struct DevOp {
+  int type;
+  int src;        // DOP_HALF: 0 = conditioner reads first half (nn_a), 1 = second half (nn_b)
+  int proj_off;   // DOP_HALF: column offset of this network's slice in P
+  int inverse;    // DOP_HALF: 0 = z = exp(ls)*y + t ; 1 = y = (z - t)*exp(-ls)
+  long long off;  // float offset of the op's parameters in the blob of its direction
+};
+
+struct Chunk {      // a run of consecutive ops whose parameters are streamed together
+  long long off;    // float offset in blob (16-byte aligned)
+  int bytes;        // multiple of 16
+  int first_op;
+  int n_ops;
+  int pad;
+};
+
+// Parameter layout of one half-coupling inside the blob (all counts in floats).
+//   W1a  [DINP][HP0]                       rows >= din are zero
+//   for l = 1..L-1:  W_l [HP(l-1)][HP(l)] , b_l [HP(l)]
+//   Wout [HP(L-1)][2*DOP] , bout [2*DOP]   t in columns [0,dout), s in [DOP, DOP+dout)
+// Matrices are stored input-major (k-major): element (k, j) multiplies input k into output j.
+struct HalfLayout {
+  int din, dinp;     // conditioner's own-half input width, padded to 4
+  int dout, dop;     // width of the half being transformed, padded to 4
+  int L;
+  int hp[8];         // padded hidden widths (multiples of 16)
+  int h[8];          // true hidden widths
+  int off_w[8];      // off_w[0] = W1a; off_w[l] = W_l
+  int off_b[8];      // off_b[l] = b_l (l >= 1)
+  int off_wout, off_bout;
+  int total;         // floats, multiple of 4
+};
+
+struct StackDims {
+  int D, DP;         // flow dimension, padded to 4
+  int Da, Db;        // ceil(D/2), floor(D/2)   (torch.chunk(2), cnf.py:175)
+  int C;
+  int PW;            // projection width = sum over half-couplings of HP0
+  HalfLayout half[2];  // [0]: nn_a (reads a, updates b)   [1]: nn_b (reads b, updates a)
+};
+
+static inline __host__ __device__ int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  // nn.GELU() default (exact erf), as instantiated by LayerFactory (factories.py:65-66)
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+// Launch arguments common to the flow kernels.
+struct FlowArgs {
+  const float* in;        // (n_rows, D)
+  float* out;             // (n_rows, D)
+  float* logdet;          // (n_rows) or null
+  const float* P;         // (n_inst, PW)
+  const int* row2inst;    // or null
+  long long inst_period;  // used when row2inst == null; 0 = identity
+  long long n_rows;
+  const float* blob;
+  const DevOp* ops;
+  int n_ops;
+  const Chunk* chunks;
+  int n_chunks;
+};
+
+__device__ __forceinline__ long long row_instance(const FlowArgs& a, long long r) {
+  if (a.row2inst) return (long long)a.row2inst[r];
+  if (a.inst_period > 0) return r % a.inst_period;
+  return r;
+}
+
+}  // namespace bcnf

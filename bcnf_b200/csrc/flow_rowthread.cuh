@@ -1,0 +1,226 @@
+// Row-per-thread fused coupling stack (narrow conditioners: padded width 16 or 32).
+//
+// Replaces the per-layer Python loop of CondRealNVP_v2.forward / .inverse
+// (reference cnf.py:479-488, :500-506) and everything it calls for one row:
+// ActNorm (cnf.py:348-354), the conditioner MLP (cnf.py:98-107), the affine update and
+// log-det row sum (cnf.py:175-196, :198-213) and the orthonormal mixing (cnf.py:333-339).
+//
+// One thread owns one row: y (D floats), the hidden vector (HP floats) and the log-det
+// accumulator live in registers from the first layer to the last; HBM is read once (y, the
+// projection slices P) and written once (z, logdet).  Parameters are streamed chunk by chunk
+// into shared memory with TMA bulk copies (cp.async.bulk + mbarrier, double buffered); every
+// lane of a warp reads the same weight address, so shared-memory reads are broadcasts.
+#pragma once
+#include "common.cuh"
+
+namespace bcnf {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+// acc[j] += x * w[j], j < N, w in shared memory (broadcast reads)
+template <int N>
+__device__ __forceinline__ void axpy_row(float (&acc)[N], float x, const float* __restrict__ w) {
+#pragma unroll
+  for (int j = 0; j < N; j += 4) {
+    float4 v = lds4(w + j);
+    acc[j + 0] = fmaf(x, v.x, acc[j + 0]);
+    acc[j + 1] = fmaf(x, v.y, acc[j + 1]);
+    acc[j + 2] = fmaf(x, v.z, acc[j + 2]);
+    acc[j + 3] = fmaf(x, v.w, acc[j + 3]);
+  }
+}
+
+// One conditioner network + affine update of the other half (cnf.py:98-107, :178-190, :203-204).
+template <int D, int HP, int SRC>
+__device__ __forceinline__ void half_coupling(float (&y)[D], float& ld, const float* __restrict__ w,
+                                              const HalfLayout& hl, const float* __restrict__ prow,
+                                              int inverse) {
+  constexpr int DA = (D + 1) / 2, DB = D / 2;
+  constexpr int DIN = SRC == 0 ? DA : DB;
+  constexpr int DOUT = SRC == 0 ? DB : DA;
+  constexpr int IN0 = SRC == 0 ? 0 : DA;
+  constexpr int OUT0 = SRC == 0 ? DA : 0;
+  constexpr int DOP = (DOUT + 3) / 4 * 4;
+
+  float acc[HP];
+  // first Linear: the condition part (W1h.h + b1) was hoisted into P (bcnf_cond_project)
+#pragma unroll
+  for (int j = 0; j < HP; j += 4) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(prow + j));
+    acc[j] = v.x; acc[j + 1] = v.y; acc[j + 2] = v.z; acc[j + 3] = v.w;
+  }
+  {
+    const float* w1 = w + hl.off_w[0];
+#pragma unroll
+    for (int i = 0; i < DIN; ++i) axpy_row<HP>(acc, y[IN0 + i], w1 + i * HP);
+  }
+  const int L = hl.L;
+  for (int l = 1;; ++l) {
+    float hcur[HP];
+#pragma unroll
+    for (int j = 0; j < HP; ++j) hcur[j] = gelu_erf(acc[j]);   // nn.GELU(); Dropout = identity in eval
+    if (l >= L) {
+      // last Linear -> (t, s); t = first DOUT outputs, s = last DOUT (chunk(2, dim=1), cnf.py:104)
+      float ts[2 * DOP];
+      const float* wo = w + hl.off_wout;
+      const float* bo = w + hl.off_bout;
+#pragma unroll
+      for (int j = 0; j < 2 * DOP; j += 4) {
+        float4 v = lds4(bo + j);
+        ts[j] = v.x; ts[j + 1] = v.y; ts[j + 2] = v.z; ts[j + 3] = v.w;
+      }
+#pragma unroll
+      for (int k = 0; k < HP; ++k) axpy_row<2 * DOP>(ts, hcur[k], wo + k * (2 * DOP));
+      float ls_sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < DOUT; ++j) {
+        float ls = tanhf(ts[DOP + j]);                              // cnf.py:107
+        ls_sum += ls;
+        if (!inverse) y[OUT0 + j] = fmaf(expf(ls), y[OUT0 + j], ts[j]);   // cnf.py:179
+        else          y[OUT0 + j] = (y[OUT0 + j] - ts[j]) * expf(-ls);    // cnf.py:204
+      }
+      ld += ls_sum;                                                 // cnf.py:190, :488
+      return;
+    }
+    const float* wl = w + hl.off_w[l];
+    const float* bl = w + hl.off_b[l];
+#pragma unroll
+    for (int j = 0; j < HP; j += 4) {
+      float4 v = lds4(bl + j);
+      acc[j] = v.x; acc[j + 1] = v.y; acc[j + 2] = v.z; acc[j + 3] = v.w;
+    }
+#pragma unroll
+    for (int k = 0; k < HP; ++k) axpy_row<HP>(acc, hcur[k], wl + k * HP);
+  }
+}
+
+constexpr int kRowThreadBlock = 128;
+
+template <int D, int HP>
+__global__ void __launch_bounds__(kRowThreadBlock)
+flow_rowthread_kernel(const FlowArgs a, const StackDims sd, const int chunk_cap_bytes) {
+  constexpr int DP = (D + 3) / 4 * 4;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* buf[2] = {reinterpret_cast<float*>(smem_raw), reinterpret_cast<float*>(smem_raw + chunk_cap_bytes)};
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * (size_t)chunk_cap_bytes);
+
+  const int tid = threadIdx.x;
+  const long long n_tiles = (a.n_rows + kRowThreadBlock - 1) / kRowThreadBlock;
+  if ((long long)blockIdx.x >= n_tiles) return;
+  const long long my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  const long long total = my_tiles * a.n_chunks;   // chunk instances this CTA consumes
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int g = 0; g < 2 && g < total; ++g) {
+      const Chunk c = a.chunks[g % a.n_chunks];
+      mbar_expect_tx(&bars[g], (uint32_t)c.bytes);
+      tma_bulk_g2s(buf[g], a.blob + c.off, (uint32_t)c.bytes, &bars[g]);
+    }
+  }
+
+  long long g = 0;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long row = tile * kRowThreadBlock + tid;
+    const bool valid = row < a.n_rows;
+    float y[D];
+    float ld = 0.f;
+    const float* prow = a.P;
+    if (valid) {
+      const float* src = a.in + row * D;
+#pragma unroll
+      for (int j = 0; j < D; ++j) y[j] = __ldg(src + j);
+      prow = a.P + row_instance(a, row) * (long long)sd.PW;
+    } else {
+#pragma unroll
+      for (int j = 0; j < D; ++j) y[j] = 0.f;
+    }
+
+    for (int ci = 0; ci < a.n_chunks; ++ci, ++g) {
+      const int b = (int)(g & 1);
+      mbar_wait(&bars[b], (uint32_t)((g >> 1) & 1));
+      const Chunk c = a.chunks[ci];
+      const float* base = buf[b];
+      for (int oi = 0; oi < c.n_ops; ++oi) {
+        const DevOp op = a.ops[c.first_op + oi];
+        const float* w = base + (op.off - c.off);
+        if (op.type == DOP_HALF) {
+          if (op.src == 0) half_coupling<D, HP, 0>(y, ld, w, sd.half[0], prow + op.proj_off, op.inverse);
+          else             half_coupling<D, HP, 1>(y, ld, w, sd.half[1], prow + op.proj_off, op.inverse);
+        } else if (op.type == DOP_MIX) {
+          // y <- y @ M, M = Q (forward, cnf.py:335) or Q^T (inverse, cnf.py:339)
+          float o[DP];
+#pragma unroll
+          for (int j = 0; j < DP; ++j) o[j] = 0.f;
+#pragma unroll
+          for (int i = 0; i < D; ++i) axpy_row<DP>(o, y[i], w + i * DP);
+#pragma unroll
+          for (int j = 0; j < D; ++j) y[j] = o[j];
+        } else if (op.type == DOP_ACTNORM_FWD) {
+#pragma unroll
+          for (int j = 0; j < D; ++j) y[j] = fmaf(w[j], y[j], w[DP + j]);       // cnf.py:349
+          ld += w[2 * DP];                                                      // cnf.py:350
+        } else {  // DOP_ACTNORM_INV
+#pragma unroll
+          for (int j = 0; j < D; ++j) y[j] = __fdiv_rn(y[j] - w[DP + j], w[j]); // cnf.py:354
+          ld += w[2 * DP];
+        }
+      }
+      __syncthreads();   // every thread is done reading buf[b]
+      if (tid == 0 && g + 2 < total) {
+        const Chunk n = a.chunks[(int)((g + 2) % a.n_chunks)];
+        fence_proxy_async();
+        mbar_expect_tx(&bars[b], (uint32_t)n.bytes);
+        tma_bulk_g2s(buf[b], a.blob + n.off, (uint32_t)n.bytes, &bars[b]);
+      }
+    }
+
+    if (valid) {
+      float* dst = a.out + row * D;
+#pragma unroll
+      for (int j = 0; j < D; ++j) dst[j] = y[j];
+      if (a.logdet) a.logdet[row] = ld;
+    }
+  }
+}
+
+}  // namespace bcnf

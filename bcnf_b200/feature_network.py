@@ -1,0 +1,219 @@
+"""Condition encoders (adjacent to the hot path; they stay plain PyTorch modules).
+
+Same class names, constructor arguments and parameter names as the reference's
+``src/bcnf/models/feature_network.py`` so that ``state_dict`` keys under
+``feature_network_stack.feature_networks.{i}.`` match.  The B200 build changes only how often
+they run: once per conditioning instance, never once per (sample, instance) row
+(north star; the reference re-runs them on tiled conditions, cnf.py:579 + :497).
+"""
+from __future__ import annotations
+
+import math
+import warnings
+from typing import Any, Type
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+__all__ = ["FeatureNetwork", "FeatureNetworkStack", "ConcatenateCondition", "FrExpFeatureNetwork",
+           "FullyConnectedFeatureNetwork", "LSTMFeatureNetwork", "MultiHeadAttention", "TransformerBlock",
+           "Transformer"]
+
+
+class FeatureNetwork(nn.Module):
+    """Base class: records ``input_size`` / ``output_size`` (reference feature_network.py:10-25)."""
+    input_size: int
+    output_size: int
+
+    @property
+    def n_params(self) -> int:
+        return sum(p.numel() for p in self.parameters())
+
+
+class ConcatenateCondition(FeatureNetwork):
+    """Marker that consumes one raw condition (reference feature_network.py:76-88)."""
+
+    def __init__(self, input_size: int, output_size: int, dim: int = -1) -> None:
+        super().__init__()
+        self.input_size, self.output_size, self.dim = input_size, output_size, dim
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return x
+
+
+class FeatureNetworkStack(FeatureNetwork):
+    """Chain of feature networks; each ConcatenateCondition consumes the next raw condition
+    (reference feature_network.py:28-73)."""
+
+    def __init__(self, feature_networks: list[FeatureNetwork | nn.Module | None] | None = None) -> None:
+        super().__init__()
+        nets = [fn for fn in (feature_networks or []) if fn is not None]
+        if not nets:
+            raise ValueError("Feature network stack must contain at least one feature network.")
+        self.feature_networks = nn.Sequential(*nets)
+        self.n_distinct_conditions = sum(isinstance(fn, ConcatenateCondition) for fn in nets)
+        self.input_size = getattr(nets[0], "input_size", None)
+        self.output_size = getattr(nets[-1], "output_size", None)
+
+    def forward(self, *conditions: torch.Tensor) -> torch.Tensor:
+        if len(conditions) != self.n_distinct_conditions:
+            raise ValueError(f"Expected {self.n_distinct_conditions} conditions, but got {len(conditions)}.")
+        taken = 0
+        feats: torch.Tensor | None = None
+        for fn in self.feature_networks:
+            if isinstance(fn, ConcatenateCondition):
+                raw = conditions[taken]
+                taken += 1
+                feats = fn(raw if feats is None else torch.cat([feats, raw], dim=fn.dim))
+            else:
+                feats = fn(feats)
+        return feats
+
+
+class FrExpFeatureNetwork(FeatureNetwork):
+    """Mantissa / exponent split of the input (reference feature_network.py:91-111)."""
+
+    def __init__(self, input_size: int, separate_sign: bool = False) -> None:
+        super().__init__()
+        self.separate_sign = separate_sign
+        self.input_size = input_size
+        self.output_size = input_size * (3 if separate_sign else 2)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        mant, expo = torch.frexp(x)
+        if self.separate_sign:
+            return torch.cat([torch.sign(mant), mant.abs(), expo], dim=-1)
+        return torch.cat([mant, expo], dim=-1)
+
+
+class FullyConnectedFeatureNetwork(FeatureNetwork):
+    """Flatten + MLP (reference feature_network.py:114-145); parameters live in ``self.nn``."""
+
+    def __init__(self, sizes: list[int], activation: Type[nn.Module] = nn.GELU, dropout: float = 0.0,
+                 batch_norm: bool = False) -> None:
+        super().__init__()
+        self.input_size, self.output_size = sizes[0], sizes[-1]
+        self.output_size_lin = sizes[-1]
+        self.nn = nn.Sequential()
+        if len(sizes) < 2:
+            warnings.warn("No hidden layers in the fully connected network. Using identity function.")
+            self.nn.append(nn.Identity())
+            return
+        for fan_in, fan_out in zip(sizes[:-2], sizes[1:-1]):
+            self.nn.append(nn.Linear(fan_in, fan_out))
+            if batch_norm:
+                self.nn.append(nn.BatchNorm1d(fan_out))
+            self.nn.append(activation())
+            if dropout > 0.0:
+                self.nn.append(nn.Dropout(dropout))
+        self.nn.append(nn.Linear(sizes[-2], sizes[-1]))
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.nn(x.reshape(x.size(0), -1))
+
+
+class LSTMFeatureNetwork(FeatureNetwork):
+    """(bi)LSTM -> Linear -> pooling (reference feature_network.py:148-178).
+
+    Deviation, documented in DESIGN.md: the reference builds the LSTM with ``batch_first=True``
+    but pools with ``dim=0``, i.e. over the BATCH axis, so its output is (seq_len, output_size)
+    and the flow only runs when the batch size equals the sequence length (SURVEY.md section 8a
+    hazard).  ``pool_axis="time"`` (default) pools over the sequence axis, giving one feature
+    vector per instance, which is what every caller assumes; ``pool_axis="reference"``
+    reproduces the reference exactly.
+    """
+
+    def __init__(self, input_size: int, hidden_size: int, output_size: int, num_layers: int, dropout: float = 0.0,
+                 bidirectional: bool = False, pooling: str = "mean", pool_axis: str = "time") -> None:
+        super().__init__()
+        if pooling not in ("mean", "max"):
+            raise ValueError(f'Pooling method {pooling} not supported. Use either "mean" or "max".')
+        if pool_axis not in ("time", "reference"):
+            raise ValueError("pool_axis must be 'time' or 'reference'")
+        self.input_size, self.output_size = input_size, output_size
+        self.pooling, self.pool_axis = pooling, pool_axis
+        self.lstm = nn.LSTM(input_size=input_size, hidden_size=hidden_size, num_layers=num_layers, dropout=dropout,
+                            bidirectional=bidirectional, batch_first=True)
+        self.linear = nn.Linear(hidden_size * (2 if bidirectional else 1), output_size)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        seq, _ = self.lstm(x)
+        seq = self.linear(seq)
+        axis = 1 if self.pool_axis == "time" else 0
+        return seq.mean(dim=axis) if self.pooling == "mean" else seq.max(dim=axis).values
+
+
+class MultiHeadAttention(nn.Module):
+    """Reference feature_network.py:183-229 (parameter names q_linear/k_linear/v_linear/fc_out)."""
+
+    def __init__(self, d_model: int, n_heads: int) -> None:
+        super().__init__()
+        self.d_model, self.n_heads, self.head_dim = d_model, n_heads, d_model // n_heads
+        self.q_linear = nn.Linear(d_model, d_model)
+        self.k_linear = nn.Linear(d_model, d_model)
+        self.v_linear = nn.Linear(d_model, d_model)
+        self.fc_out = nn.Linear(d_model, d_model)
+
+    def forward(self, query: torch.Tensor, key: torch.Tensor, value: torch.Tensor, mask: Any = None) -> torch.Tensor:
+        b = query.size(0)
+
+        def heads(t: torch.Tensor, lin: nn.Linear) -> torch.Tensor:
+            return lin(t).view(b, -1, self.n_heads, self.head_dim).transpose(1, 2)
+
+        q, k, v = heads(query, self.q_linear), heads(key, self.k_linear), heads(value, self.v_linear)
+        scores = q @ k.transpose(-2, -1) / math.sqrt(self.head_dim)
+        if mask is not None:
+            scores = scores.masked_fill(mask == 0, -1e9)
+        ctx = F.softmax(scores, dim=-1) @ v
+        return self.fc_out(ctx.transpose(1, 2).contiguous().view(b, -1, self.d_model))
+
+
+class TransformerBlock(nn.Module):
+    """Post-norm block (reference feature_network.py:232-260)."""
+
+    def __init__(self, d_model: int, n_heads: int, ff_size: int, dropout: float = 0.1) -> None:
+        super().__init__()
+        self.attention = MultiHeadAttention(d_model, n_heads)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+        self.ffn = nn.Sequential(nn.Linear(d_model, ff_size), nn.GELU(), nn.Linear(ff_size, d_model))
+        self.dropout = nn.Dropout(dropout)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        x = self.norm1(x + self.dropout(self.attention(x, x, x)))
+        return self.norm2(x + self.dropout(self.ffn(x)))
+
+
+class Transformer(FeatureNetwork):
+    """Token embedding + blocks + Linear on token 0 (reference feature_network.py:263-307)."""
+
+    def __init__(self, input_size: int, trf_size: int, n_heads: int, ff_size: int, n_blocks: int, output_size: int,
+                 dropout: float = 0.5, trf_dropout: float = 0.1, add_positional_embeddings: bool = False) -> None:
+        super().__init__()
+        self.input_size, self.output_size = input_size, output_size
+        self.add_positional_embeddings = add_positional_embeddings
+        self.trf_size = trf_size
+        self.features = nn.Linear(input_size, trf_size)
+        self.layers = nn.ModuleList([TransformerBlock(trf_size, n_heads, ff_size, trf_dropout) for _ in range(n_blocks)])
+        self.output = nn.Linear(trf_size, output_size)
+        self.dropout = nn.Dropout(dropout)
+
+    def _positional(self, seq_len: int, device: torch.device) -> torch.Tensor:
+        # only the first `input_size` channels are filled, as in the reference (:293-299)
+        pe = torch.zeros(seq_len, self.trf_size, device=device)
+        pos = torch.arange(seq_len, dtype=torch.float64).unsqueeze(1)
+        j = torch.arange(self.input_size, dtype=torch.float64).unsqueeze(0)
+        ang = pos / torch.pow(torch.tensor(10000.0, dtype=torch.float64), 2 * j / self.input_size)
+        vals = torch.where((torch.arange(self.input_size) % 2 == 0).unsqueeze(0), torch.sin(ang), torch.cos(ang))
+        pe[:, : self.input_size] = vals.to(torch.float32).to(device)
+        return pe
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        x = self.dropout(self.features(x))
+        if self.add_positional_embeddings:
+            x = x + self._positional(x.size(1), x.device)
+        for layer in self.layers:
+            x = layer(x)
+        x = self.dropout(x)
+        return self.output(x[:, 0, :])

@@ -1,0 +1,139 @@
+/*
+ * bcnf_b200 -- C ABI of the B200-native CondRealNVP_v2 coupling-stack path.
+ *
+ * The reference (psaegert/bcnf) has no plugin / FFI interface: its boundary is the Python
+ * class CondRealNVP_v2 (src/bcnf/models/cnf.py:357-588) and its state_dict layout.  This
+ * header is the ABI that sits directly beneath that class; bcnf_b200/cnf.py binds it with
+ * ctypes.  Every entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - all data pointers are DEVICE pointers to contiguous row-major fp32, 16-byte aligned bases;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls are
+ *     asynchronous on it, make no hidden synchronisation and start no host threads;
+ *   - return value 0 = success, < 0 = argument/validation error (BCNF_E_*), > 0 = cudaError_t;
+ *     nothing throws across the ABI; bcnf_last_error() returns the message of the last
+ *     failing call on the calling thread;
+ *   - PyTorch (or any caller) owns inputs, outputs and the model parameters; the library owns
+ *     only the packed copy of the parameters held by a bcnf_flow_t.
+ */
+#ifndef BCNF_B200_H
+#define BCNF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BCNF_ABI_VERSION 1
+#define BCNF_MAX_HIDDEN_LAYERS 8
+#define BCNF_MAX_SIZE 64         /* largest supported flow dimension D */
+#define BCNF_MAX_HIDDEN 1024     /* largest supported conditioner width */
+
+enum {
+  BCNF_OK = 0,
+  BCNF_E_ARG = -1,          /* null pointer, negative size, bad enum */
+  BCNF_E_UNSUPPORTED = -2,  /* shape outside the supported envelope */
+  BCNF_E_STATE = -3,        /* parameters not set yet */
+  BCNF_E_NOMEM = -4
+};
+
+/* Layer kinds of CondRealNVP_v2.layers (cnf.py:392-423). */
+typedef enum {
+  BCNF_OP_ACTNORM = 0,   /* ActNorm, cnf.py:342-354 */
+  BCNF_OP_COUPLING = 1,  /* ConditionalAffineCouplingLayer, cnf.py:110-213 */
+  BCNF_OP_ORTHO = 2      /* OrthonormalTransformation, cnf.py:312-339 */
+} bcnf_op_type_t;
+
+/* Arithmetic of the conditioner GEMMs. */
+typedef enum {
+  BCNF_PREC_FP32 = 0,    /* fp32 FMA everywhere (all widths) */
+  BCNF_PREC_BF16X3 = 1,  /* tcgen05, 3-term bf16 split, fp32 accumulate: fp32-class accuracy */
+  BCNF_PREC_BF16 = 2     /* tcgen05, single bf16 pass, fp32 accumulate: stated bf16 tolerance */
+} bcnf_precision_t;
+
+/* Which kernel family a handle dispatches to (bcnf_flow_info). */
+typedef enum {
+  BCNF_KERNEL_ROWTHREAD = 0, /* one row per thread, hidden vector in registers (width <= 32) */
+  BCNF_KERNEL_TILED = 1,     /* row tile per CTA, fp32 FMA, activations in shared memory */
+  BCNF_KERNEL_TCGEN05 = 2    /* row tile per CTA, tcgen05 MMA with TMEM accumulators */
+} bcnf_kernel_t;
+
+/* Constructor arguments of CondRealNVP_v2 that shape the stack (cnf.py:358-375). */
+typedef struct {
+  int32_t size;                            /* D   (`size`) */
+  int32_t n_conditions;                    /* C   (`n_conditions`, > 0) */
+  int32_t n_hidden;                        /* L   (len(nested_sizes)), 1..BCNF_MAX_HIDDEN_LAYERS */
+  int32_t hidden[BCNF_MAX_HIDDEN_LAYERS];  /* H_1..H_L (`nested_sizes`) */
+  int32_t two_way;                         /* `two_way` */
+  int32_t n_ops;                           /* len(layers) of the (sub-)stack to run */
+  int32_t precision;                       /* bcnf_precision_t */
+  int32_t device;                          /* CUDA device ordinal */
+} bcnf_flow_desc_t;
+
+/* Parameters of one layer, in the reference's own storage layout (torch.nn.Linear.weight is
+ * (out, in) row-major).  Unused members are NULL. */
+typedef struct {
+  int32_t type;              /* bcnf_op_type_t */
+  int32_t reserved;
+  const float* scale;        /* ACTNORM  (D)      layers.{i}.scale              cnf.py:345 */
+  const float* bias;         /* ACTNORM  (D)      layers.{i}.bias               cnf.py:346 */
+  const float* q;            /* ORTHO    (D, D)   layers.{i}.orthonormal_matrix cnf.py:323 */
+  const float* const* w_a;   /* COUPLING L+1 ptrs layers.{i}.nn_a.nn.{j}.weight cnf.py:78-85 */
+  const float* const* b_a;   /* COUPLING L+1 ptrs layers.{i}.nn_a.nn.{j}.bias */
+  const float* const* w_b;   /* two_way only      layers.{i}.nn_b.nn.{j}.weight cnf.py:150-160 */
+  const float* const* b_b;
+} bcnf_op_params_t;
+
+typedef struct bcnf_flow bcnf_flow_t;
+
+typedef struct {
+  int32_t kernel;            /* bcnf_kernel_t used by forward / inverse */
+  int32_t proj_width;        /* floats per instance of the condition projection P */
+  int32_t n_half_couplings;  /* conditioner networks in the stack (2 per two-way coupling) */
+  int32_t rows_per_cta;      /* row tile of the flow kernel */
+  int64_t packed_bytes;      /* device bytes owned by the handle */
+  int64_t macs_per_row;      /* algorithmic multiply-accumulates per row, projection hoisted */
+  int64_t macs_per_instance; /* multiply-accumulates of the projection, per instance */
+} bcnf_flow_info_t;
+
+int bcnf_abi_version(void);
+const char* bcnf_last_error(void);
+
+/* Build a handle for a layer sequence `op_types[0..n_ops)` (the order of
+ * CondRealNVP_v2.layers, cnf.py:392-423, or any contiguous slice of it -- a single
+ * ConditionalAffineCouplingLayer is a 1-op stack).  Allocates the packed-parameter storage. */
+int bcnf_flow_create(const bcnf_flow_desc_t* desc, const int32_t* op_types, bcnf_flow_t** out);
+int bcnf_flow_destroy(bcnf_flow_t* flow);
+int bcnf_flow_info(const bcnf_flow_t* flow, bcnf_flow_info_t* info);
+
+/* (Re)pack the parameters from the caller's tensors (device pointers).  Call after
+ * load_state_dict / every optimiser step.  Replaces nothing in the reference: it is the
+ * price of not reading nn.Module parameters one ATen op at a time. */
+int bcnf_flow_set_params(bcnf_flow_t* flow, const bcnf_op_params_t* ops, void* stream);
+
+/* P[i, :] = W1h . h[i, :] + b1 for every conditioner network of the stack: the part of the
+ * first Linear of ConditionalNestedNeuralNetwork that multiplies the condition features
+ * (torch.cat([y, h]) then nn.Linear, cnf.py:101-104), hoisted so that it is computed once
+ * per conditioning instance instead of once per (sample, instance) row.
+ *   h: (n_inst, C)   P: (n_inst, proj_width) */
+int bcnf_cond_project(bcnf_flow_t* flow, const float* h, int64_t n_inst, float* P, void* stream);
+
+/* Row r uses instance row2inst[r] if row2inst != NULL, else r % inst_period if
+ * inst_period > 0 (the tiling of `c.repeat(m, 1)` in _sample(outer=True), cnf.py:579),
+ * else r. */
+
+/* Layer loop of CondRealNVP_v2.forward, cnf.py:476-488:  z (n_rows, D) and, if logdet != NULL,
+ * the accumulated log|det J| (n_rows) that the reference leaves in model.log_det_J. */
+int bcnf_flow_forward(bcnf_flow_t* flow, const float* y, const float* P, const int32_t* row2inst,
+                      int64_t inst_period, int64_t n_rows, float* z, float* logdet, void* stream);
+
+/* Layer loop of CondRealNVP_v2.inverse, cnf.py:500-506: x (n_rows, D).  If logdet != NULL it
+ * receives the log|det| of the forward map at x (i.e. minus the inverse's own). */
+int bcnf_flow_inverse(bcnf_flow_t* flow, const float* z, const float* P, const int32_t* row2inst,
+                      int64_t inst_period, int64_t n_rows, float* x, float* logdet, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BCNF_B200_H */

@@ -1,0 +1,136 @@
+"""Host-side boundary tests (no GPU): API surface, state_dict layout, config loading, C-ABI exports."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import bcnf_b200
+from bcnf_b200 import CondRealNVP_v2, _cabi
+from conftest import GOLDEN_DIR, ROOT, load_golden
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _cabi.lib()
+    header = open(os.path.join(ROOT, "include", "bcnf_b200.h")).read()
+    declared = set(re.findall(r"\b(bcnf_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(_cabi.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.bcnf_abi_version() == 1
+
+
+def test_abi_validation_errors_without_gpu():
+    lib = _cabi.lib()
+    assert lib.bcnf_flow_create(None, None, None) == -1
+    assert b"null" in lib.bcnf_last_error()
+    desc = _cabi.FlowDesc()
+    desc.size, desc.n_conditions, desc.n_hidden, desc.n_ops = 19, 0, 1, 1
+    desc.hidden[0] = 16
+    h = ctypes.c_void_p()
+    arr = (ctypes.c_int32 * 1)(1)
+    assert lib.bcnf_flow_create(ctypes.byref(desc), arr, ctypes.byref(h)) == -2     # n_conditions == 0
+    desc.n_conditions = 4
+    desc.size = 1000
+    assert lib.bcnf_flow_create(ctypes.byref(desc), arr, ctypes.byref(h)) == -2
+    desc.size = 19
+    arr[0] = 7
+    assert lib.bcnf_flow_create(ctypes.byref(desc), arr, ctypes.byref(h)) == -1     # unknown layer type
+    assert lib.bcnf_flow_forward(None, None, None, None, 0, 0, None, None, None) == -1
+    assert lib.bcnf_flow_destroy(None) == 0
+
+
+@pytest.mark.parametrize("name", ["trajectory_FC_small", "trajectory_FC_large", "trajectory_LSTM_large",
+                                  "trajectory_TRF_large"])
+def test_state_dict_layout_matches_reference(name):
+    rec = json.load(open(os.path.join(GOLDEN_DIR, "state_dict_keys.json")))[name]
+    model = CondRealNVP_v2.from_config(rec["config"])
+    mine = {k: list(v.shape) for k, v in model.state_dict().items()}
+    assert mine == rec["keys"]
+    assert model.n_params == rec["n_params"]
+    assert len(model.layers) == rec["n_layers"]
+
+
+def test_golden_state_dicts_load_strictly(golden):
+    name, data, sd, meta = golden
+    model = CondRealNVP_v2.from_config(meta["config"])
+    res = model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert model.n_params == meta["n_params"]
+
+
+def test_same_q_in_every_block_when_random_state_is_set():
+    kw = dict(size=5, nested_sizes=[8], n_blocks=4, n_conditions=3,
+              feature_networks=[bcnf_b200.ConcatenateCondition(None, 3)])
+    m = CondRealNVP_v2(random_state=7, **kw)
+    qs = [l.orthonormal_matrix for l in m.layers if isinstance(l, bcnf_b200.OrthonormalTransformation)]
+    assert all(torch.equal(qs[0], q) for q in qs[1:])        # reference quirk, cnf.py:319-320
+    m2 = CondRealNVP_v2(**kw)
+    qs2 = [l.orthonormal_matrix for l in m2.layers if isinstance(l, bcnf_b200.OrthonormalTransformation)]
+    assert not torch.equal(qs2[0], qs2[1])
+    assert not qs[0].requires_grad
+
+
+def test_unsupported_configurations_are_refused():
+    fn = [bcnf_b200.ConcatenateCondition(None, 3)]
+    with pytest.raises(NotImplementedError):
+        CondRealNVP_v2(5, [8], 2, 3, feature_networks=fn, layer="AnyGLU")
+    with pytest.raises(NotImplementedError):
+        CondRealNVP_v2(5, [8], 2, 3, feature_networks=fn, activation="ReLU")
+    with pytest.raises(NotImplementedError):
+        CondRealNVP_v2(5, [8], 2, 0, feature_networks=fn)
+    with pytest.raises(ValueError):
+        CondRealNVP_v2(5, [8], 2, 3, feature_networks=None)     # feature_network.py:32-33
+    with pytest.raises(NotImplementedError):
+        bcnf_b200.FeatureNetworkFactory.get_feature_network("Nope", {})
+
+
+def test_verify_rejects_mismatched_feature_sizes():
+    cfg = {"global": {"parameter_selection": list("abcde")},
+           "model": {"kwargs": dict(size=5, nested_sizes=[8], n_blocks=2, n_conditions=4)},
+           "feature_networks": [{"type": "ConcatenateCondition", "kwargs": {"input_size": None, "output_size": 6}},
+                                {"type": "FullyConnected", "kwargs": {"sizes": [6, 3]}}]}
+    with pytest.raises(AssertionError):
+        CondRealNVP_v2.from_config(cfg)
+
+
+def test_cpu_device_has_no_fallback():
+    cfg = json.load(open(os.path.join(GOLDEN_DIR, "state_dict_keys.json")))["trajectory_FC_small"]["config"]
+    model = CondRealNVP_v2.from_config(cfg).eval()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        model(torch.randn(2, 19), torch.randn(2, 30, 3))
+
+
+def test_training_mode_is_refused_until_backward_exists():
+    cfg = json.load(open(os.path.join(GOLDEN_DIR, "state_dict_keys.json")))["trajectory_FC_small"]["config"]
+    model = CondRealNVP_v2.from_config(cfg)
+    with pytest.raises(NotImplementedError):
+        model(torch.randn(2, 19), torch.randn(2, 30, 3))
+
+
+def test_load_config_coerces_yaml_numbers(tmp_path):
+    p = tmp_path / "run.yaml"
+    p.write_text("global:\n  parameter_selection: [a]\noptimizer:\n  kwargs:\n    lr: 2e-4\n"
+                 "training:\n  random_state: 2024_03_25\ndata:\n  path: '{{BCNF_ROOT}}/data'\n  config_file: 'x'\n")
+    cfg = bcnf_b200.load_config(str(p), root="/tmp/root")
+    assert cfg["optimizer"]["kwargs"]["lr"] == pytest.approx(2e-4)
+    assert cfg["training"]["random_state"] == 20240325
+    assert cfg["data"]["path"] == "/tmp/root/data"
+    assert cfg["global"]["hybrid_weight"] == 0
+
+
+def test_inn_nll_loss_matches_golden(golden):
+    name, data, sd, meta = golden
+    v = bcnf_b200.inn_nll_loss(torch.from_numpy(data["z"]), torch.from_numpy(data["logdet"]))
+    assert abs(float(v) - float(data["nll"])) < 1e-5 * max(1.0, abs(float(data["nll"])))
+
+
+def test_parameter_index_mapping():
+    m = bcnf_b200.ParameterIndexMapping(["a", "b"])
+    assert len(m) == 2 and m["b"] == 1 and "a" in m and list(m) == ["a", "b"]
+    assert m.vectorize({"a": [1, 2], "b": [3, 4]}).shape == (2, 2)
+    with pytest.raises(KeyError):
+        m.vectorize({"a": 1})
