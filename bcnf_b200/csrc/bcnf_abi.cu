@@ -489,10 +489,11 @@ static int launch_tiled(bcnf_flow* f, const FlowArgs& a, cudaStream_t stream) {
 
 static int run_flow(bcnf_flow_t* f, int dir, const float* in, const float* P, const int32_t* row2inst,
                     int64_t inst_period, int64_t n_rows, float* out, float* logdet, void* stream_) {
-  if (!f || !in || !P || !out) return fail(BCNF_E_ARG, "bcnf_flow_%s: null argument", dir ? "inverse" : "forward");
+  if (!f) return fail(BCNF_E_ARG, "bcnf_flow_%s: null handle", dir ? "inverse" : "forward");
   if (n_rows < 0 || inst_period < 0) return fail(BCNF_E_ARG, "negative size");
   if (!f->params_set) return fail(BCNF_E_STATE, "bcnf_flow_set_params has not been called");
-  if (n_rows == 0) return BCNF_OK;
+  if (n_rows == 0) return BCNF_OK;   // empty batch: nothing to read or write
+  if (!in || !P || !out) return fail(BCNF_E_ARG, "bcnf_flow_%s: null argument", dir ? "inverse" : "forward");
   cudaStream_t stream = (cudaStream_t)stream_;
   CUDA_TRY(cudaSetDevice(f->desc.device));
   const Program& p = f->prog[dir];

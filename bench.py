@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""Benchmark of the CondRealNVP_v2 coupling-stack hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+Default workload = BASELINE.json configs[1]: trajectory_FC_large posterior sampling, 500 samples
+per instance x 10 000 instances (5e6 rows), processed as K steps of `--instances-per-step`
+instances each (default 1000 -> K=10 steps is the whole job).  One JSON line on stdout (rank 0).
+
+  value        posterior samples/s (rows/s), whole job over all N GPUs, conditions resident in HBM;
+               timed region per step = feature network + condition projection + z draw + fused
+               inverse stack, CUDA events on the launching stream, max over ranks.
+  e2e          the same metric through the public API  model.sample(500, cond_host, outer=True,
+               output_device="cpu")  with host conditions (pinned) and the samples copied back.
+  roofline     the fused stack kernel alone: algorithmic FLOPs (2 x MACs/row hoisted, SURVEY 8d,
+               x rows per launch) / CUDA-event duration, vs the measured bf16 tensor peak.
+  cpu_baseline oracle port (torch CPU back end = the ATen kernels the reference's eager path runs
+               on a host) on a bounded sample of the same workload, all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (config key in tests/golden/state_dict_keys.json, samples per instance, instances, kind)
+    "fc_large_sample": ("trajectory_FC_large", 500, 10_000, "sample"),
+    "fc_small_sample": ("trajectory_FC_small", 500, 10_000, "sample"),
+    "fc_small_logprob": ("trajectory_FC_small", 1, 1 << 22, "log_prob"),
+    "fc_large_logprob": ("trajectory_FC_large", 1, 1 << 17, "log_prob"),
+}
+
+
+def load_run_config(key: str) -> dict:
+    rec = json.load(open(os.path.join(ROOT, "tests", "golden", "state_dict_keys.json")))[key]
+    return rec["config"]
+
+
+def measured_peaks() -> tuple[dict, str]:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def perturb_actnorm(model, seed: int = 1) -> None:
+    """scale ~ U(0.75, 1.25), bias ~ N(0, 0.1): ActNorm is not the identity, the stack stays well conditioned."""
+    from bcnf_b200 import ActNorm
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for layer in model.layers:
+            if isinstance(layer, ActNorm):
+                layer.scale.copy_((0.75 + 0.5 * torch.rand(layer.scale.shape, generator=g)).to(layer.scale.device))
+                layer.bias.copy_((0.1 * torch.randn(layer.bias.shape, generator=g)).to(layer.bias.device))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], None, [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0])); mx = float(r[1]); pw.append(float(r[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        # median over the busiest half of the samples = "under load"
+        sm_sorted = sorted(sm)
+        return {"sm_mhz": float(np.median(sm_sorted[: max(1, len(sm_sorted) // 2)])) if sm else None,
+                "sm_max_mhz": mx, "power_w_max": max(pw) if pw else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def build_model(cfg: dict, device):
+    from bcnf_b200 import CondRealNVP_v2
+    torch.manual_seed(0)
+    model = CondRealNVP_v2.from_config(cfg)
+    perturb_actnorm(model)
+    return model.to(device).eval()
+
+
+def oracle_cpu_rate(cfg: dict, kind: str, samples: int, budget_s: float = 12.0) -> dict:
+    """Time the oracle port (torch CPU back end) on a bounded sample of the workload."""
+    from bcnf_b200 import CondRealNVP_v2
+    from oracle import flow_oracle as fo
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    model = CondRealNVP_v2.from_config(cfg)          # CPU parameters; only used as a weight container
+    perturb_actnorm(model)
+    model.eval()
+    layers = fo.layers_from_state_dict(model.state_dict(), convert=lambda v: v.detach().clone())
+    mk = cfg["model"]["kwargs"]
+    d, big = mk["size"], mk["nested_sizes"][0] > 64
+    if kind == "sample":
+        m, n_inst = (256, 8) if big else (256, 64)     # BASELINE.md section 2 protocol
+    else:
+        m, n_inst = 1, (2048 if big else 16384)
+    rows = m * n_inst
+    g = torch.Generator().manual_seed(3)
+    cond = torch.randn(n_inst, 30, 3, generator=g)
+
+    def once():
+        with torch.no_grad():
+            # the reference tiles the raw conditions and re-runs the feature network per row (cnf.py:579, :497)
+            rep = cond.repeat(m, 1, 1)
+            h = model.feature_network_stack(rep)
+            z = torch.randn(rows, d, generator=g)
+            if kind == "sample":
+                return fo.stack_inverse(layers, z, h)
+            return fo.stack_forward(layers, z, h)
+
+    once()
+    best, t_end, reps = float("inf"), time.perf_counter() + budget_s, 0
+    while reps < 3 or (time.perf_counter() < t_end and reps < 50):
+        t0 = time.perf_counter(); once(); best = min(best, time.perf_counter() - t0); reps += 1
+    return {"value": rows / best, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{kind} {m} x {n_inst} instances = {rows} rows, best of {reps}, oracle/flow_oracle.py torch-CPU "
+                      f"back end incl. per-row feature network as the reference does"}
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="fc_large_sample", choices=sorted(WORKLOADS))
+    ap.add_argument("--instances-per-step", type=int, default=0, help="per GPU; 0 = workload default")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg_key, m_samples, n_inst_total, kind = WORKLOADS[args.workload]
+    cfg = load_run_config(cfg_key)
+    mk = cfg["model"]["kwargs"]
+    unit = "samples/s" if kind == "sample" else "evals/s"
+    metric = "posterior samples/sec" if kind == "sample" else "log_prob evals/sec"
+    inst_step = args.instances_per_step or (1000 if kind == "sample" else n_inst_total // 8)
+    workload_name = (f"{cfg_key} {'posterior sampling' if kind == 'sample' else 'log_prob'} "
+                     f"{m_samples} x {n_inst_total} (step = {m_samples} x {inst_step} instances per GPU)")
+
+    if args.impl == "reference":
+        # reference arm: the reference's own CPU implementation of the path = the oracle port on
+        # the host cores (the Python reference tree does not exist on the GPU box)
+        if rank != 0:
+            return
+        base = oracle_cpu_rate(cfg, kind, m_samples, budget_s=20.0)
+        rows_step = int(base["sample"].split("=")[1].split()[0])
+        line = {"impl": "reference", "metric": metric, "value": base["value"], "unit": unit, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * rows_step / base["value"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": {"workload": workload_name}, "cpu_baseline": base,
+                "e2e": {"value": base["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the coupling stack has no CPU path")
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+
+    from bcnf_b200 import _cabi
+    _cabi.lib()                                  # fail loudly if the extension is missing
+    model = build_model(cfg, device)
+    flow = model._flow()
+    d = mk["size"]
+    g = torch.Generator().manual_seed(100 + rank)
+    # each rank owns its own block of instances (shard by instance, no collective)
+    cond_host = torch.randn(inst_step, 30, 3, generator=g).pin_memory()
+    cond_dev = cond_host.to(device)
+    rows_step = m_samples * inst_step
+    launches = [0]
+
+    def step_resident():
+        with torch.no_grad():
+            h = model.features(cond_dev)
+            P = flow.project(h)
+            if kind == "sample":
+                z = torch.randn((rows_step, d), device=device)
+                out, _ = flow.run(True, z, P, inst_period=inst_step, out=z)
+            else:
+                out, _ = flow.run(False, y_dev, P, want_logdet=True)
+            launches[0] += 2
+            return out
+
+    def step_e2e():
+        if kind == "sample":
+            return model.sample(m_samples, cond_host, outer=True, output_device="cpu")
+        lp = model.log_prob(y_host.to(device, non_blocking=True), cond_host.to(device, non_blocking=True))
+        return lp.to("cpu")
+
+    if kind != "sample":
+        y_host = torch.randn(rows_step, d, generator=g).pin_memory()
+        y_dev = y_host.to(device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    launches[0] = 0
+    ms_total = timed(step_resident, args.steps)
+    n_launch = launches[0]
+    clocks = sampler.stop() if rank == 0 else {}
+    value = world * rows_step * args.steps / (ms_total * 1e-3)
+
+    # the fused stack kernel alone (roofline numerator/denominator)
+    with torch.no_grad():
+        P = flow.project(model.features(cond_dev))
+        zbuf = torch.randn((rows_step, d), device=device)
+        k_steps = max(3, min(args.steps, 10))
+
+        def kernel_only():
+            flow.run(kind == "sample", zbuf, P, inst_period=inst_step if kind == "sample" else 0,
+                     want_logdet=(kind != "sample"))
+        kernel_only()
+        ms_kernel = timed(kernel_only, k_steps) / k_steps
+    peaks, peak_src = measured_peaks()
+    flops_launch = 2.0 * int(flow.info.macs_per_row) * rows_step
+    achieved_tf = flops_launch / (ms_kernel * 1e-3) / 1e12
+    peak_tf = float(peaks.get("bf16_tflops_sustained" if ms_kernel > 500 else "bf16_tflops"))
+    fma_peak_tf = 148 * 128 * 2 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12
+    roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": achieved_tf / peak_tf, "traffic": None, "peak_source": f"{peak_src} bf16 dense",
+                "kernel": f"flow_{flow.kernel}", "kernel_ms": ms_kernel,
+                "fp32_fma_peak_tflops": fma_peak_tf, "fp32_fma_frac": achieved_tf / fma_peak_tf,
+                "algorithmic_bytes_per_row": 4 * d * 2 + 4, "flops_per_row": 2 * int(flow.info.macs_per_row)}
+
+    # end to end through the public API with host buffers
+    e2e_steps = max(1, min(args.steps, 5))
+    step_e2e()
+    ms_e2e = timed(step_e2e, e2e_steps)
+    e2e_value = world * rows_step * e2e_steps / (ms_e2e * 1e-3)
+    h2d = cond_host.numel() * 4 + (0 if kind == "sample" else rows_step * d * 4)
+    d2h = rows_step * d * 4 if kind == "sample" else rows_step * 4
+
+    if rank == 0:
+        line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload_name, "size": d, "nested_sizes": mk["nested_sizes"],
+                           "n_blocks": mk["n_blocks"], "n_conditions": mk["n_conditions"],
+                           "kernel": flow.kernel, "precision": "fp32",
+                           "l2": "inputs/outputs per step exceed L2 or are regenerated each step; weights "
+                                 f"({int(flow.info.packed_bytes) >> 20} MiB packed) stream from L2/HBM",
+                           "parallelism": f"instances sharded over {world} GPU(s), no collective"},
+                "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e / e2e_steps},
+                "gpu_launches": n_launch, "roofline": roofline, "clocks": clocks}
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = oracle_cpu_rate(cfg, kind, m_samples)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

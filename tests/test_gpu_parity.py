@@ -21,6 +21,14 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+@pytest.fixture(autouse=True)
+def _no_grad():
+    # inference tests: the feature networks are plain PyTorch modules whose outputs would
+    # otherwise carry autograd history
+    with torch.no_grad():
+        yield
+
+
 def _model_from_golden(meta, sd, **extra):
     model = CondRealNVP_v2.from_config(meta["config"], **extra)
     model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
