@@ -1,0 +1,70 @@
+"""Summarise gpurun_out/*.ncu-rep and launches_*.csv into profiles/ (text, committed).
+
+    python profiles/summarize.py <tag> <launches.csv> <prof.ncu-rep> [more pairs...]
+"""
+import collections
+import csv
+import subprocess
+import sys
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "smsp__inst_executed.sum", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tensor.sum", "sm__inst_executed_pipe_uniform.sum",
+        "lts__t_bytes.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio"]
+
+
+def launches(path, out):
+    rows = [r for r in csv.reader(open(path)) if len(r) > 10]
+    hdr = rows[0]
+    ik, iv = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for r in rows[1:]:
+        try:
+            v = float(r[iv].replace(",", ""))
+        except ValueError:
+            continue
+        agg[r[ik][:100]][0] += 1
+        agg[r[ik][:100]][1] += v
+    tot = sum(v for _, v in agg.values())
+    out.write(f"launch list {path}: {sum(n for n, _ in agg.values())} launches, {tot / 1e6:.3f} ms total "
+              "(ncu per-launch times are cold-cache and serialised: compare shares)\n")
+    for k, (n, v) in sorted(agg.items(), key=lambda x: -x[1][1])[:12]:
+        out.write(f"  {v / 1e6:12.3f} ms {100 * v / tot:7.2f}%  n={n:4d}  {k}\n")
+
+
+def full(path, out):
+    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(txt.splitlines()))
+    hdr, units = rows[0], rows[1]
+    for vals in rows[2:]:
+        name = vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?"
+        out.write(f"ncu --set full: {path}  kernel {name[:90]}\n")
+        for k in KEYS:
+            if k in hdr:
+                i = hdr.index(k)
+                out.write(f"  {k:88s} {vals[i]:>20s} {units[i]}\n")
+
+
+if __name__ == "__main__":
+    tag = sys.argv[1]
+    with open(f"profiles/{tag}.txt", "w") as out:
+        for p in sys.argv[2:]:
+            (launches if p.endswith(".csv") else full)(p, out)
+            out.write("\n")
+    print(open(f"profiles/{tag}.txt").read())
