@@ -45,6 +45,9 @@ def _dev_f32(t: torch.Tensor, device: torch.device, what: str) -> torch.Tensor:
     return t.contiguous()
 
 
+PRECISIONS = {"auto": -1, "fp32": _cabi.PREC_FP32, "bf16x3": _cabi.PREC_BF16X3, "bf16": _cabi.PREC_BF16}
+
+
 # ------------------------------------------------------------------------------------------
 # packed handle
 # ------------------------------------------------------------------------------------------
@@ -52,7 +55,7 @@ class PackedFlow:
     """A ``bcnf_flow_t`` built from a list of layer modules; repacks when parameters change."""
 
     def __init__(self, layers: Sequence[nn.Module], size: int, n_conditions: int, nested_sizes: Sequence[int],
-                 two_way: bool, device: torch.device, precision: int = _cabi.PREC_FP32) -> None:
+                 two_way: bool, device: torch.device, precision: str = "fp32") -> None:
         if device.type != "cuda":
             raise RuntimeError(f"bcnf_b200 runs on CUDA devices only (got {device}); there is no CPU path. "
                                "Move the model with .to('cuda').")
@@ -78,11 +81,29 @@ class PackedFlow:
             raise NotImplementedError(f"len(nested_sizes)={len(nested_sizes)} > {_cabi.MAX_HIDDEN_LAYERS}")
         for i, h in enumerate(nested_sizes):
             desc.hidden[i] = int(h)
-        desc.two_way, desc.n_ops, desc.precision = int(two_way), len(types), precision
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {precision!r}")
+        desc.two_way, desc.n_ops = int(two_way), len(types)
         desc.device = device.index if device.index is not None else torch.cuda.current_device()
         self._handle = C.c_void_p()
         arr = (C.c_int32 * len(types))(*types)
-        _cabi.check(self.lib.bcnf_flow_create(C.byref(desc), arr, C.byref(self._handle)), "bcnf_flow_create")
+        has_coupling = _cabi.OP_COUPLING in types
+        if precision == "auto":
+            # tensor-core 3-pass split (fp32-class accuracy) where the conditioner is wide enough to be a
+            # real GEMM, fp32 FMA kernels otherwise -- a choice between CUDA kernels, not a fallback
+            wide = has_coupling and min(nested_sizes) >= 48
+            precision = "bf16x3" if wide else "fp32"
+            desc.precision = PRECISIONS[precision]
+            rc = self.lib.bcnf_flow_create(C.byref(desc), arr, C.byref(self._handle))
+            if rc == -2 and precision != "fp32":
+                precision = "fp32"
+                desc.precision = PRECISIONS[precision]
+                rc = self.lib.bcnf_flow_create(C.byref(desc), arr, C.byref(self._handle))
+            _cabi.check(rc, "bcnf_flow_create")
+        else:
+            desc.precision = PRECISIONS[precision] if has_coupling else _cabi.PREC_FP32
+            _cabi.check(self.lib.bcnf_flow_create(C.byref(desc), arr, C.byref(self._handle)), "bcnf_flow_create")
+        self.precision = precision
         info = _cabi.FlowInfo()
         _cabi.check(self.lib.bcnf_flow_info(self._handle, C.byref(info)), "bcnf_flow_info")
         self.info = info
@@ -375,6 +396,10 @@ class CondRealNVP_v2(ConditionalInvertibleLayer):
 
     Extra keyword-only knobs (defaults keep the reference's call signatures valid):
 
+    ``precision``: arithmetic of the conditioner GEMMs -- ``"fp32"`` (FMA kernels), ``"bf16x3"``
+    (tcgen05, 3-term bf16 split, fp32-class accuracy), ``"bf16"`` (tcgen05, one bf16 pass, stated
+    tolerance) or ``"auto"`` (bf16x3 where the conditioner is wide enough, else fp32).
+
     ``sample_rng``: ``"device"`` (default) draws z on the GPU and evaluates all rows of an
     instance chunk in one launch; ``"reference"`` replays the reference's loops and draws z from
     the CPU generator exactly as cnf.py:566/:578/:584 do, so a seeded run reproduces the
@@ -390,7 +415,7 @@ class CondRealNVP_v2(ConditionalInvertibleLayer):
                  layer_kwargs: dict[str, Any] | None = None, activation: str = "GELU",
                  activation_kwargs: dict[str, Any] | None = None, device: Any = "cpu",
                  random_state: int | None = None, parameter_index_mapping: ParameterIndexMapping | None = None,
-                 hybrid: bool = False, *, sample_rng: str = "device") -> None:
+                 hybrid: bool = False, *, sample_rng: str = "device", precision: str = "fp32") -> None:
         super().__init__()
         if n_conditions <= 0:
             # the reference accepts n_conditions == 0 in the constructor but every forward then
@@ -411,6 +436,9 @@ class CondRealNVP_v2(ConditionalInvertibleLayer):
         self.parameter_index_mapping = parameter_index_mapping
         self.hybrid = hybrid
         self.sample_rng = sample_rng
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {precision!r}")
+        self.precision = precision
         self.log_det_J: torch.Tensor = torch.zeros(1)
         if hybrid:
             self.prediction_head = nn.Linear(n_conditions, size)     # cnf.py:391-392
@@ -476,7 +504,7 @@ class CondRealNVP_v2(ConditionalInvertibleLayer):
         dev = _as_device(self.device)
         if self._packed is None or self._packed.device != dev:
             self._packed = PackedFlow(list(self.layers), self.size, self.n_conditions, self.nested_sizes,
-                                      self.two_way, dev)
+                                      self.two_way, dev, self.precision)
         return self._packed
 
     def _check_mode(self, what: str) -> None:

@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "cond_project.cuh"
 #include "flow_rowthread.cuh"
+#include "flow_tc.cuh"
 #include "flow_tiled.cuh"
 
 using namespace bcnf;
@@ -101,6 +102,16 @@ struct bcnf_flow {
   // tiled launch configuration
   TiledSmem tiled_lay;
   int tiled_R = 32;
+  // tcgen05 path
+  TcDims td;
+  int npass = 0;                       // 0 = not a tensor-core handle
+  unsigned char* d_tc_blob = nullptr;  // bf16 hi/lo weight tile images (direction independent)
+  long long tc_blob_bytes = 0;
+  long long* d_tc_off[2] = {nullptr, nullptr};   // per direction, per device op: byte offset of its tile stream
+  std::vector<long long> tc_off_by_layer;        // per (layer index, net 0/1): offset in d_tc_blob
+  TcPackDesc* d_tc_pack = nullptr;
+  TcPackDesc* h_tc_pack = nullptr;
+  int tc_pack_cap = 0;
 };
 
 static const int kRowThreadChunkCap = 20 * 1024;  // bytes per streamed parameter chunk
@@ -205,8 +216,78 @@ extern "C" int bcnf_flow_destroy(bcnf_flow_t* f) {
   if (f->d_bproj) cudaFree(f->d_bproj);
   if (f->d_pack) cudaFree(f->d_pack);
   if (f->h_pack) cudaFreeHost(f->h_pack);
+  if (f->d_tc_blob) cudaFree(f->d_tc_blob);
+  for (int d = 0; d < 2; ++d) if (f->d_tc_off[d]) cudaFree(f->d_tc_off[d]);
+  if (f->d_tc_pack) cudaFree(f->d_tc_pack);
+  if (f->h_tc_pack) cudaFreeHost(f->h_tc_pack);
   delete f;
   return BCNF_OK;
+}
+
+// ---- tcgen05 path: layer / chunk structure of one conditioner network -------------------------------
+static void tc_set_chunks(TcLayer& ly) {
+  const int n = (ly.np + 255) / 256;
+  const int base = round_up((ly.np + n - 1) / n, 16);
+  ly.n_chunks = n;
+  for (int i = 0; i < 4; ++i) ly.chunk_n[i] = 0;
+  for (int i = 0, left = ly.np; i < n; ++i) { ly.chunk_n[i] = std::min(base, left); left -= ly.chunk_n[i]; }
+}
+
+static void tc_build_half(TcHalfLayout& tl, const HalfLayout& hl) {
+  memset(&tl, 0, sizeof(tl));
+  tl.L = hl.L;
+  tl.doh = round_up(hl.dout, 8);
+  for (int l = 0; l <= hl.L; ++l) {
+    TcLayer& ly = tl.layer[l];
+    const int k_real = l == 0 ? hl.din : hl.h[l - 1];
+    ly.np = l == hl.L ? 2 * tl.doh : hl.hp[l];
+    ly.kc = (k_real + 63) / 64;
+    ly.last_ksteps = (k_real - 64 * (ly.kc - 1) + 15) / 16;
+    tc_set_chunks(ly);
+  }
+  long long bytes = 0;
+  for (int l = 0; l <= hl.L; ++l)
+    for (int nc = 0; nc < tl.layer[l].n_chunks; ++nc)
+      bytes += (long long)tl.layer[l].kc * 4 * (tl.layer[l].chunk_n[nc] / 2) * 128;
+  tl.stream_bytes = bytes;
+}
+
+// Returns 0 and fills f.td if the stack fits the tensor-core kernel, else a reason string.
+static const char* tc_plan(bcnf_flow& f, int npass) {
+  const StackDims& sd = f.sd;
+  TcDims& td = f.td;
+  memset(&td, 0, sizeof(td));
+  int a_chunks = 1, max_half_rows = 8, max_doh = 8;
+  for (int s = 0; s < 2; ++s) {
+    const HalfLayout& hl = sd.half[s];
+    if (hl.din > 64) return "own-half width > 64";
+    for (int l = 0; l < hl.L; ++l) {
+      if (hl.h[l] < 48) return "hidden width < 48: the row-per-thread / tiled FMA kernels are the better fit";
+      if (hl.hp[l] > 1024) return "hidden width > 1024";
+    }
+    tc_build_half(td.half[s], hl);
+    for (int l = 0; l <= hl.L; ++l) {
+      const TcLayer& ly = td.half[s].layer[l];
+      if (l >= 1) a_chunks = std::max(a_chunks, ly.kc);
+      for (int nc = 0; nc < ly.n_chunks; ++nc) max_half_rows = std::max(max_half_rows, ly.chunk_n[nc] / 2);
+    }
+    max_doh = std::max(max_doh, td.half[s].doh);
+  }
+  td.a_chunks = a_chunks;
+  td.stage_bytes = max_half_rows * 128 * (npass == 3 ? 2 : 1);
+  td.off_alo = npass == 3 ? a_chunks * kTcATile : 0;
+  td.off_stage = (npass == 3 ? 2 : 1) * a_chunks * kTcATile;
+  td.yp = sd.DP;
+  td.tsp = 2 * max_doh;
+  const int tail = round_up(kTcRows * td.yp * 4, 16) + round_up(kTcRows * td.tsp * 4, 16) + 2048;
+  const int room = f.max_smem_optin - td.off_stage - tail;
+  td.n_stages = std::min(8, room / td.stage_bytes);
+  if (td.n_stages < 2) return "activation tiles + 2 weight stages exceed shared memory";
+  td.off_y = td.off_stage + td.n_stages * td.stage_bytes;
+  td.off_ts = td.off_y + round_up(kTcRows * td.yp * 4, 16);
+  td.off_misc = td.off_ts + round_up(kTcRows * td.tsp * 4, 16);
+  td.smem_bytes = td.off_misc + 2048;
+  return nullptr;
 }
 
 template <typename K>
@@ -229,8 +310,8 @@ extern "C" int bcnf_flow_create(const bcnf_flow_desc_t* desc, const int32_t* op_
     if (desc->hidden[l] < 1 || desc->hidden[l] > BCNF_MAX_HIDDEN)
       return fail(BCNF_E_UNSUPPORTED, "nested_sizes[%d]=%d outside [1, %d]", l, desc->hidden[l], BCNF_MAX_HIDDEN);
   if (desc->n_ops < 1) return fail(BCNF_E_ARG, "empty layer list");
-  if (desc->precision != BCNF_PREC_FP32)
-    return fail(BCNF_E_UNSUPPORTED, "precision %d not built in this version", desc->precision);
+  if (desc->precision < BCNF_PREC_FP32 || desc->precision > BCNF_PREC_BF16)
+    return fail(BCNF_E_ARG, "unknown precision %d", desc->precision);
   for (int i = 0; i < desc->n_ops; ++i)
     if (op_types[i] < 0 || op_types[i] > 2)
       return fail(BCNF_E_ARG, "layer %d has unknown type %d", i, op_types[i]);   // cnf.py:485
@@ -283,7 +364,14 @@ extern "C" int bcnf_flow_create(const bcnf_flow_desc_t* desc, const int32_t* op_
   const bool allow_rowthread = !(force && strcmp(force, "tiled") == 0);
   const bool rowthread_ok = allow_rowthread && uniform && (hp0 == 16 || hp0 == 32) && (sd.D == 19 || sd.D == 21) &&
                             std::max(f->prog[0].max_chunk_bytes, f->prog[1].max_chunk_bytes) <= kRowThreadChunkCap;
-  if (rowthread_ok) {
+  if (desc->precision != BCNF_PREC_FP32) {
+    const int npass = desc->precision == BCNF_PREC_BF16X3 ? 3 : 1;
+    if (prop.major != 10) { delete f; return fail(BCNF_E_UNSUPPORTED, "tcgen05 path needs an sm_100 device (got sm_%d%d)", prop.major, prop.minor); }
+    if (const char* why = tc_plan(*f, npass)) { delete f; return fail(BCNF_E_UNSUPPORTED, "tensor-core path: %s", why); }
+    f->npass = npass;
+    f->kernel = BCNF_KERNEL_TCGEN05;
+    f->rows_per_cta = kTcRows;
+  } else if (rowthread_ok) {
     f->kernel = BCNF_KERNEL_ROWTHREAD;
     f->rows_per_cta = kRowThreadBlock;
   } else {
@@ -334,6 +422,47 @@ extern "C" int bcnf_flow_create(const bcnf_flow_desc_t* desc, const int32_t* op_
     bcnf_flow_destroy(f);
     return fail(BCNF_E_NOMEM, "pack table allocation failed");
   }
+  if (f->npass) {
+    // one tile stream per conditioner network, in forward layer order; both directions index into it
+    const int n = (int)f->op_types.size();
+    f->tc_off_by_layer.assign(2 * n, -1);
+    long long off = 0;
+    int n_tiles = 0;
+    for (int i = 0; i < n; ++i)
+      if (f->op_types[i] == BCNF_OP_COUPLING)
+        for (int s = 0; s < (desc->two_way ? 2 : 1); ++s) {
+          f->tc_off_by_layer[2 * i + s] = off;
+          off += f->td.half[s].stream_bytes;
+          for (int l = 0; l <= f->td.half[s].L; ++l) n_tiles += f->td.half[s].layer[l].n_chunks * f->td.half[s].layer[l].kc;
+        }
+    f->tc_blob_bytes = off;
+    f->tc_pack_cap = n_tiles;
+    bool ok = cudaMalloc(&f->d_tc_blob, off) == cudaSuccess &&
+              cudaMalloc(&f->d_tc_pack, (size_t)n_tiles * sizeof(TcPackDesc)) == cudaSuccess &&
+              cudaMallocHost(&f->h_tc_pack, (size_t)n_tiles * sizeof(TcPackDesc)) == cudaSuccess;
+    for (int d = 0; d < 2 && ok; ++d) {
+      Program& p = f->prog[d];
+      std::vector<long long> offs(p.ops.size(), 0);
+      int oi = 0;
+      for (int sidx = 0; sidx < n; ++sidx) {
+        const int i = d == 0 ? sidx : n - 1 - sidx;
+        if (f->op_types[i] == BCNF_OP_COUPLING) {
+          offs[oi++] = f->tc_off_by_layer[2 * i];
+          if (desc->two_way) offs[oi++] = f->tc_off_by_layer[2 * i + 1];
+        } else {
+          oi++;
+        }
+      }
+      ok = cudaMalloc(&f->d_tc_off[d], offs.size() * sizeof(long long)) == cudaSuccess;
+      if (ok) cudaMemcpy(f->d_tc_off[d], offs.data(), offs.size() * sizeof(long long), cudaMemcpyHostToDevice);
+    }
+    if (!ok) {
+      cudaGetLastError();
+      bcnf_flow_destroy(f);
+      return fail(BCNF_E_NOMEM, "device allocation of %lld bytes (bf16 weight tiles) failed", off);
+    }
+    bytes += off;
+  }
   f->packed_bytes = bytes;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { bcnf_flow_destroy(f); return fail((int)e, "create: %s", cudaGetErrorString(e)); }
@@ -378,6 +507,33 @@ static int emit_half(const bcnf_flow& f, const HalfLayout& hl, float* dst, const
   v.push_back({b[L], dst + hl.off_bout, hl.dout, 1, hl.dout, 2 * hl.dop, 0, 0});
   v.push_back({b[L] + hl.dout, dst + hl.off_bout + hl.dop, hl.dout, 1, hl.dout, 2 * hl.dop, 0, 0});
   return 0;
+}
+
+// Emit the bf16 tile-image descriptors of one conditioner network.
+static void emit_tc_half(const bcnf_flow& f, int s, const float* const* w, long long off, std::vector<TcPackDesc>& v) {
+  const HalfLayout& hl = f.sd.half[s];
+  const TcHalfLayout& tl = f.td.half[s];
+  unsigned char* dst = f.d_tc_blob + off;
+  for (int l = 0; l <= hl.L; ++l) {
+    const TcLayer& ly = tl.layer[l];
+    TcPackDesc d{};
+    d.w = w[l];
+    d.pitch = l == 0 ? hl.din + f.sd.C : hl.h[l - 1];
+    d.col0 = 0;
+    d.k_valid = l == 0 ? hl.din : hl.h[l - 1];
+    d.out_mode = l == hl.L;
+    d.n_valid = l == hl.L ? hl.dout : hl.h[l];
+    d.doh = tl.doh;
+    int coff = 0;
+    for (int nc = 0; nc < ly.n_chunks; ++nc) {
+      for (int kc = 0; kc < ly.kc; ++kc) {
+        d.dst = dst; d.chunk_off = coff; d.chunk_n = ly.chunk_n[nc]; d.kc = kc;
+        v.push_back(d);
+        dst += (size_t)4 * (ly.chunk_n[nc] / 2) * 128;
+      }
+      coff += ly.chunk_n[nc];
+    }
+  }
 }
 
 extern "C" int bcnf_flow_set_params(bcnf_flow_t* f, const bcnf_op_params_t* ops, void* stream_) {
@@ -430,6 +586,21 @@ extern "C" int bcnf_flow_set_params(bcnf_flow_t* f, const bcnf_op_params_t* ops,
   CUDA_TRY(cudaMemcpyAsync(f->d_pack, f->h_pack, v.size() * sizeof(PackDesc), cudaMemcpyHostToDevice, stream));
   pack_kernel<<<dim3((unsigned)v.size(), 8), 256, 0, stream>>>(f->d_pack);
   CUDA_TRY(cudaGetLastError());
+  if (f->npass) {
+    std::vector<TcPackDesc> tv;
+    tv.reserve(f->tc_pack_cap);
+    for (int i = 0; i < n; ++i)
+      if (f->op_types[i] == BCNF_OP_COUPLING) {
+        emit_tc_half(*f, 0, ops[i].w_a, f->tc_off_by_layer[2 * i], tv);
+        if (f->desc.two_way) emit_tc_half(*f, 1, ops[i].w_b, f->tc_off_by_layer[2 * i + 1], tv);
+      }
+    if ((int)tv.size() > f->tc_pack_cap) return fail(BCNF_E_STATE, "internal: tile pack table overflow");
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    memcpy(f->h_tc_pack, tv.data(), tv.size() * sizeof(TcPackDesc));
+    CUDA_TRY(cudaMemcpyAsync(f->d_tc_pack, f->h_tc_pack, tv.size() * sizeof(TcPackDesc), cudaMemcpyHostToDevice, stream));
+    tc_pack_kernel<<<(unsigned)tv.size(), 256, 0, stream>>>(f->d_tc_pack);
+    CUDA_TRY(cudaGetLastError());
+  }
   f->params_set = true;
   return BCNF_OK;
 }
@@ -487,6 +658,19 @@ static int launch_tiled(bcnf_flow* f, const FlowArgs& a, cudaStream_t stream) {
   return BCNF_OK;
 }
 
+template <int NPASS>
+static int launch_tc(bcnf_flow* f, const FlowArgs& a, int dir, cudaStream_t stream) {
+  const size_t smem = (size_t)f->td.smem_bytes;
+  auto kern = flow_tc_kernel<NPASS>;
+  static thread_local size_t configured = 0;
+  if (configured < smem) { if (int rc = opt_in_smem(kern, smem)) return rc; configured = smem; }
+  const long long tiles = (a.n_rows + 2 * kTcRows - 1) / (2 * kTcRows);
+  const int clusters = (int)std::min<long long>(tiles, f->num_sms / 2);
+  kern<<<2 * clusters, kTcThreads, smem, stream>>>(a, f->sd, f->td, f->d_tc_blob, f->d_tc_off[dir]);
+  CUDA_TRY(cudaGetLastError());
+  return BCNF_OK;
+}
+
 static int run_flow(bcnf_flow_t* f, int dir, const float* in, const float* P, const int32_t* row2inst,
                     int64_t inst_period, int64_t n_rows, float* out, float* logdet, void* stream_) {
   if (!f) return fail(BCNF_E_ARG, "bcnf_flow_%s: null handle", dir ? "inverse" : "forward");
@@ -502,6 +686,8 @@ static int run_flow(bcnf_flow_t* f, int dir, const float* in, const float* P, co
   a.inst_period = inst_period; a.n_rows = n_rows;
   a.blob = p.d_blob; a.ops = p.d_ops; a.n_ops = (int)p.ops.size();
   a.chunks = p.d_chunks; a.n_chunks = (int)p.chunks.size();
+  if (f->kernel == BCNF_KERNEL_TCGEN05)
+    return f->npass == 3 ? launch_tc<3>(f, a, dir, stream) : launch_tc<1>(f, a, dir, stream);
   if (f->kernel == BCNF_KERNEL_ROWTHREAD) {
     const int hp = f->sd.half[0].hp[0];
     if (f->sd.D == 19 && hp == 16) return launch_rowthread<19, 16>(f, a, dir, stream);

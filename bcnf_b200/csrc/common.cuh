@@ -8,6 +8,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef BCNF_MAX_SIZE
+#define BCNF_MAX_SIZE 64
+#endif
+#define BCNF_TC_MAX_LAYERS 10
+
 namespace bcnf {
 
 enum DevOpType : int {

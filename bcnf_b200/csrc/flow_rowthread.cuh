@@ -134,9 +134,9 @@ template <int D, int HP>
 __global__ void __launch_bounds__(kRowThreadBlock)
 flow_rowthread_kernel(const FlowArgs a, const StackDims sd, const int chunk_cap_bytes) {
   constexpr int DP = (D + 3) / 4 * 4;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* buf[2] = {reinterpret_cast<float*>(smem_raw), reinterpret_cast<float*>(smem_raw + chunk_cap_bytes)};
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * (size_t)chunk_cap_bytes);
+  extern __shared__ __align__(128) unsigned char smem_rt[];
+  float* buf[2] = {reinterpret_cast<float*>(smem_rt), reinterpret_cast<float*>(smem_rt + chunk_cap_bytes)};
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_rt + 2 * (size_t)chunk_cap_bytes);
 
   const int tid = threadIdx.x;
   const long long n_tiles = (a.n_rows + kRowThreadBlock - 1) / kRowThreadBlock;

@@ -1,0 +1,496 @@
+// Row-tile fused coupling stack on the 5th-generation tensor cores (tcgen05 + TMEM + TMA).
+//
+// Same scope as the other flow kernels (reference cnf.py:479-488, :500-506 and callees) for
+// conditioners wide enough to be real GEMMs.  A CTA PAIR (cluster of 2, cta_group::2) owns 128
+// rows -- 64 per CTA -- from the first layer to the last:
+//
+//   * activations of the current layer live in shared memory as bf16 K-major SWIZZLE_128B tiles
+//     (one 64-row x 64-column tile per 128 bytes x 64 rows), as a hi part and, in the 3-pass
+//     mode, a lo part (x = hi + lo to ~16 mantissa bits);
+//   * weights are pre-split into hi/lo bf16 and pre-swizzled at pack time into exactly the
+//     shared-memory tile images the MMA wants, so the producer warp streams them with plain
+//     TMA bulk copies (cp.async.bulk + mbarrier) through a ring of stages; each CTA of the pair
+//     loads its half of the N rows of every tile, so a weight byte crosses L2->SM once per 128 rows;
+//   * one elected thread of the leader CTA issues tcgen05.mma.cta_group::2 (M = 128 over the pair,
+//     N <= 256 per instruction, K = 16), accumulating fp32 in TMEM: the whole layer output
+//     (64 rows x N per CTA = N/2 TMEM columns) stays there until the epilogue drains it;
+//   * eight epilogue warps per CTA read TMEM (tcgen05.ld), add the bias (or the hoisted
+//     condition projection P for the first layer), apply exact-erf GELU in fp32, split to bf16
+//     hi/lo and write the next layer's activation tiles in place;
+//   * the last Linear (N = 2 x 16) leaves t and s in TMEM; the row-owner threads apply
+//     tanh/exp, the affine update, the log-det row sum, ActNorm and the orthonormal mixing in
+//     fp32 on y kept in shared memory.
+//
+// Arithmetic: NPASS = 3 computes a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (fp32-class accuracy),
+// NPASS = 1 only a_hi*w_hi (plain bf16 inputs).  Accumulation, bias, GELU, tanh, exp, the
+// affine update and the log-det are fp32 in both modes.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "flow_rowthread.cuh"   // mbarrier / bulk-copy helpers
+
+namespace bcnf {
+
+constexpr int kTcThreads = 320;         // warp 0 producer, warp 1 MMA (leader) / relay (peer), warps 2-9 epilogue
+constexpr int kTcEpiThreads = 256;
+constexpr int kTcRows = 64;             // rows per CTA (128 per CTA pair)
+constexpr int kTcATile = kTcRows * 128; // bytes of one 64-row x 64-col bf16 activation tile
+constexpr int kTcMaxLayers = BCNF_TC_MAX_LAYERS;
+
+struct TcLayer {
+  int np;            // padded N (multiple of 16)
+  int n_chunks;      // N is processed in chunks of <= 256 columns
+  int chunk_n[4];
+  int kc;            // number of 64-wide K chunks
+  int last_ksteps;   // K=16 steps that carry data in the last chunk (1..4)
+};
+
+struct TcHalfLayout {
+  int L;                       // hidden layers; layer[0] first Linear, [1..L-1] hidden, [L] last Linear
+  int doh;                     // padded width of t (and of s) in the last Linear: N = 2 * doh
+  TcLayer layer[kTcMaxLayers];
+  long long stream_bytes;      // bytes of the weight tile stream of one conditioner network
+};
+
+struct TcDims {
+  TcHalfLayout half[2];
+  int a_chunks;        // 64-column activation tiles per part
+  int stage_bytes;     // bytes of one weight stage (hi [+ lo] of the largest half tile)
+  int n_stages;
+  int off_alo, off_stage, off_y, off_ts, off_misc;   // shared-memory carve-up (bytes)
+  int yp, tsp;         // pitches (floats) of y_s and ts_s
+  int smem_bytes;
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAITC_%=:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONEC_%=;\n"
+      "bra WAITC_%=;\n"
+      "DONEC_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiThreads) : "memory"); }
+
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  // K-major, SWIZZLE_128B: 8-row x 128-byte atoms, 1024 bytes apart (cute::UMMA::SmemDescriptor)
+  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;                 // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset
+  d |= (uint64_t)1 << 46;                 // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  // kind::f16, A = B = bf16 (1), D = f32 (1), both K-major, M = 128 over the CTA pair
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void umma_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+
+// store 8 consecutive activations (columns n0..n0+7 of `row`) as bf16 hi (and lo) into the tiles
+template <int NPASS>
+__device__ __forceinline__ void store_act8(unsigned char* a_hi, unsigned char* a_lo, int row, int n0, const float (&v)[8]) {
+  const int tile = n0 >> 6, c16 = (n0 & 63) >> 3;
+  const int off = tile * kTcATile + row * 128 + ((c16 ^ (row & 7)) << 4);
+  float hi[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) hi[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
+  *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]),
+                                                     pack_bf16x2(hi[4], hi[5]), pack_bf16x2(hi[6], hi[7]));
+  if (NPASS == 3)
+    *reinterpret_cast<uint4*>(a_lo + off) =
+        make_uint4(pack_bf16x2(v[0] - hi[0], v[1] - hi[1]), pack_bf16x2(v[2] - hi[2], v[3] - hi[3]),
+                   pack_bf16x2(v[4] - hi[4], v[5] - hi[5]), pack_bf16x2(v[6] - hi[6], v[7] - hi[7]));
+}
+
+template <int NPASS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsigned char* __restrict__ tc_blob,
+               const long long* __restrict__ tc_off) {
+  extern __shared__ __align__(1024) unsigned char smem_tc[];
+  unsigned char* a_hi = smem_tc;
+  unsigned char* a_lo = smem_tc + td.off_alo;
+  unsigned char* stage0 = smem_tc + td.off_stage;
+  float* y_s = reinterpret_cast<float*>(smem_tc + td.off_y);
+  float* ts_s = reinterpret_cast<float*>(smem_tc + td.off_ts);
+  unsigned char* misc = smem_tc + td.off_misc;
+  uint64_t* w_full = reinterpret_cast<uint64_t*>(misc);              // [8]
+  uint64_t* w_peer = w_full + 8;                                     // [8] leader only
+  uint64_t* w_empty = w_peer + 8;                                    // [8]
+  uint64_t* acc_full = w_empty + 8;                                  // [1]
+  uint64_t* a_ready = acc_full + 1;                                  // [1] leader only
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(a_ready + 1);
+  float* ld_s = reinterpret_cast<float*>(tmem_ptr_s + 2);            // [64]
+  const float** prow_s = reinterpret_cast<const float**>(ld_s + kTcRows);   // [64]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t cta = cluster_ctarank();
+  const bool leader = cta == 0;
+  const int n_stages = td.n_stages;
+  const long long n_tiles = (a.n_rows + 2 * kTcRows - 1) / (2 * kTcRows);
+  const long long n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < n_stages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_peer[s], 1); mbar_init(&w_empty[s], 1); }
+    mbar_init(acc_full, 1);
+    mbar_init(a_ready, 2);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  if (warp == 0) {
+    // ===================== weight producer (each CTA streams its half of every tile) =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long long tile = cluster_id; tile < n_tiles; tile += n_clusters) {
+        for (int oi = 0; oi < a.n_ops; ++oi) {
+          const DevOp op = a.ops[oi];
+          if (op.type != DOP_HALF) continue;
+          const TcHalfLayout& hl = td.half[op.src];
+          const unsigned char* src = tc_blob + tc_off[oi];
+          for (int l = 0; l <= hl.L; ++l) {
+            const TcLayer& ly = hl.layer[l];
+            for (int nc = 0; nc < ly.n_chunks; ++nc) {
+              const uint32_t rows_b = (uint32_t)(ly.chunk_n[nc] >> 1) * 128u;
+              for (int kc = 0; kc < ly.kc; ++kc, ++it) {
+                const int s = it % n_stages;
+                const uint32_t use = it / n_stages;
+                if (use > 0) mbar_wait_cluster(&w_empty[s], (use - 1) & 1);
+                const uint32_t bytes = rows_b * (NPASS == 3 ? 2u : 1u);
+                mbar_expect_tx(&w_full[s], bytes);
+                tma_bulk_g2s(stage0 + (size_t)s * td.stage_bytes, src + (size_t)cta * 2u * rows_b, bytes, &w_full[s]);
+                src += 4u * rows_b;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t it = 0, a_cnt = 0;
+      if (!leader) {
+        // ===================== relay: tell the leader when this CTA's half of a stage has landed =========
+        for (long long tile = cluster_id; tile < n_tiles; tile += n_clusters)
+          for (int oi = 0; oi < a.n_ops; ++oi) {
+            const DevOp op = a.ops[oi];
+            if (op.type != DOP_HALF) continue;
+            const TcHalfLayout& hl = td.half[op.src];
+            for (int l = 0; l <= hl.L; ++l)
+              for (int nc = 0; nc < hl.layer[l].n_chunks; ++nc)
+                for (int kc = 0; kc < hl.layer[l].kc; ++kc, ++it) {
+                  const int s = it % n_stages;
+                  mbar_wait(&w_full[s], (it / n_stages) & 1);
+                  fence_proxy_async();
+                  mbar_arrive_remote(mapa_u32(smem_u32(&w_peer[s]), 0));
+                }
+          }
+      } else {
+        // ===================== MMA issuer (leader CTA, one thread) ========================================
+        const uint32_t a_hi_addr = smem_u32(a_hi), a_lo_addr = smem_u32(a_lo), st_addr = smem_u32(stage0);
+        for (long long tile = cluster_id; tile < n_tiles; tile += n_clusters)
+          for (int oi = 0; oi < a.n_ops; ++oi) {
+            const DevOp op = a.ops[oi];
+            if (op.type != DOP_HALF) continue;
+            const TcHalfLayout& hl = td.half[op.src];
+            for (int l = 0; l <= hl.L; ++l) {
+              const TcLayer& ly = hl.layer[l];
+              mbar_wait_cluster(a_ready, a_cnt & 1);    // activations of layer l written by both CTAs
+              ++a_cnt;
+              tc_fence_after();
+              uint32_t col = 0;
+              for (int nc = 0; nc < ly.n_chunks; ++nc) {
+                const int cn = ly.chunk_n[nc];
+                const uint32_t idesc = make_idesc(cn);
+                const uint32_t rows_b = (uint32_t)(cn >> 1) * 128u;
+                for (int kc = 0; kc < ly.kc; ++kc, ++it) {
+                  const int s = it % n_stages;
+                  const uint32_t par = (it / n_stages) & 1;
+                  mbar_wait(&w_full[s], par);
+                  mbar_wait_cluster(&w_peer[s], par);
+                  tc_fence_after();
+                  const int ksteps = kc == ly.kc - 1 ? ly.last_ksteps : 4;
+                  const uint64_t ah = make_smem_desc(a_hi_addr + kc * kTcATile);
+                  const uint64_t al = make_smem_desc(a_lo_addr + kc * kTcATile);
+                  const uint64_t wh = make_smem_desc(st_addr + s * td.stage_bytes);
+                  const uint64_t wl = make_smem_desc(st_addr + s * td.stage_bytes + rows_b);
+                  for (int k = 0; k < ksteps; ++k) {
+                    const uint32_t first = (kc | k) == 0 ? 0u : 1u;
+                    umma_2sm(tmem_base + col, ah + 2 * k, wh + 2 * k, idesc, first);
+                    if (NPASS == 3) {
+                      umma_2sm(tmem_base + col, al + 2 * k, wh + 2 * k, idesc, 1u);
+                      umma_2sm(tmem_base + col, ah + 2 * k, wl + 2 * k, idesc, 1u);
+                    }
+                  }
+                  umma_commit_2sm(&w_empty[s]);      // stage free in both CTAs once these MMAs retire
+                }
+                col += (uint32_t)(cn >> 1);
+              }
+              umma_commit_2sm(acc_full);             // layer output complete in TMEM of both CTAs
+            }
+          }
+      }
+    }
+  } else {
+    // ===================== epilogue warps ================================================================
+    const int et = tid - 64;                       // 0..255
+    const int q = warp & 3;                        // TMEM lane quarter this warp may touch
+    const int ch = (warp - 2) >> 2;                // which half of the column groups
+    const int row = ((q & 1) << 5) + lane;         // row of this CTA held by this thread's TMEM lane
+    const int nhalf = q >> 1;                      // 2x2 layout: lanes 64..127 hold the second N half of a chunk
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int D = sd.D;
+    uint32_t acc_cnt = 0;
+    const uint32_t a_ready_leader = mapa_u32(smem_u32(a_ready), 0);
+
+    for (long long tile = cluster_id; tile < n_tiles; tile += n_clusters) {
+      const long long row0 = tile * (2 * kTcRows) + (long long)cta * kTcRows;
+      if (et < kTcRows) {
+        const long long r = row0 + et;
+        const bool valid = r < a.n_rows;
+        for (int j = 0; j < td.yp; ++j) y_s[et * td.yp + j] = (valid && j < D) ? __ldg(a.in + r * D + j) : 0.f;
+        ld_s[et] = 0.f;
+        prow_s[et] = a.P + (valid ? row_instance(a, r) : 0) * (long long)sd.PW;
+      }
+      epi_bar_sync();
+
+      for (int oi = 0; oi < a.n_ops; ++oi) {
+        const DevOp op = a.ops[oi];
+        const float* w = a.blob + op.off;
+        if (op.type != DOP_HALF) {
+          if (et < kTcRows) {
+            float* yr = y_s + et * td.yp;
+            if (op.type == DOP_MIX) {
+              float o[BCNF_MAX_SIZE];
+              for (int j = 0; j < D; ++j) {
+                float s = 0.f;
+                for (int i = 0; i < D; ++i) s = fmaf(yr[i], __ldg(w + i * sd.DP + j), s);
+                o[j] = s;
+              }
+              for (int j = 0; j < D; ++j) yr[j] = o[j];
+            } else {
+              for (int j = 0; j < D; ++j) {
+                const float s = __ldg(w + j), b = __ldg(w + sd.DP + j);
+                yr[j] = op.type == DOP_ACTNORM_FWD ? fmaf(s, yr[j], b) : __fdiv_rn(yr[j] - b, s);
+              }
+              ld_s[et] += __ldg(w + 2 * sd.DP);
+            }
+          }
+          continue;
+        }
+        const HalfLayout& hl = sd.half[op.src];
+        const TcHalfLayout& tl = td.half[op.src];
+        const int in0 = op.src == 0 ? 0 : sd.Da;
+        const int out0 = op.src == 0 ? sd.Da : 0;
+        // ---- input of the first Linear: own half of y, zero padded to the K=16 steps in use ----
+        if (et < kTcRows) {
+          const float* yr = y_s + et * td.yp + in0;
+          const int kcols = tl.layer[0].last_ksteps * 16;
+          for (int n0 = 0; n0 < kcols; n0 += 8) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = (n0 + i) < hl.din ? yr[n0 + i] : 0.f;
+            store_act8<NPASS>(a_hi, a_lo, et, n0, v);
+          }
+        }
+        fence_proxy_async();
+        epi_bar_sync();
+        if (et == 0) mbar_arrive_remote(a_ready_leader);
+
+        // ---- hidden layers: TMEM -> (+P | +bias) -> GELU -> bf16 hi/lo tiles of the next layer ----
+        for (int l = 0; l < tl.L; ++l) {
+          const TcLayer& ly = tl.layer[l];
+          mbar_wait_cluster(acc_full, acc_cnt & 1);
+          ++acc_cnt;
+          tc_fence_after();
+          const float* add = l == 0 ? prow_s[row] + op.proj_off : w + hl.off_b[l];
+          uint32_t col = 0;
+          int coff = 0;
+          for (int nc = 0; nc < ly.n_chunks; ++nc) {
+            const int cn = ly.chunk_n[nc];
+            const int groups = cn >> 4;                 // 8-column groups in this thread's half chunk
+            const int g0 = ch == 0 ? 0 : (groups + 1) >> 1;
+            const int g1 = ch == 0 ? (groups + 1) >> 1 : groups;
+            const int nbase = coff + nhalf * (cn >> 1);
+            for (int g = g0; g < g1; ++g) {
+              const int n0 = nbase + g * 8;
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(add + n0));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(add + n0 + 4));
+              float v[8];
+              tmem_ld8(lane_addr + col + g * 8, v);
+              v[0] = gelu_erf(v[0] + b0.x); v[1] = gelu_erf(v[1] + b0.y);
+              v[2] = gelu_erf(v[2] + b0.z); v[3] = gelu_erf(v[3] + b0.w);
+              v[4] = gelu_erf(v[4] + b1.x); v[5] = gelu_erf(v[5] + b1.y);
+              v[6] = gelu_erf(v[6] + b1.z); v[7] = gelu_erf(v[7] + b1.w);
+              store_act8<NPASS>(a_hi, a_lo, row, n0, v);
+            }
+            col += (uint32_t)(cn >> 1);
+            coff += cn;
+          }
+          tc_fence_before();
+          fence_proxy_async();
+          epi_bar_sync();
+          if (et == 0) mbar_arrive_remote(a_ready_leader);
+        }
+
+        // ---- last Linear: (t | s) from TMEM, then the affine update on the row-owner threads ----
+        mbar_wait_cluster(acc_full, acc_cnt & 1);
+        ++acc_cnt;
+        tc_fence_after();
+        {
+          const int doh = tl.doh;
+          const int groups = doh >> 3;                  // 8-column groups per half (t or s)
+          for (int g = ch; g < groups; g += 2) {
+            float v[8];
+            tmem_ld8(lane_addr + g * 8, v);
+            const int j0 = g * 8;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int j = j0 + i;
+              const float b = j < hl.dout ? __ldg(w + hl.off_bout + nhalf * hl.dop + j) : 0.f;
+              ts_s[row * td.tsp + nhalf * doh + j] = v[i] + b;
+            }
+          }
+          tc_fence_before();
+          epi_bar_sync();
+          if (et < kTcRows) {
+            const float* ts = ts_s + et * td.tsp;
+            float* yr = y_s + et * td.yp + out0;
+            float ls_sum = 0.f;
+            for (int j = 0; j < hl.dout; ++j) {
+              const float ls = tanhf(ts[doh + j]);                         // cnf.py:107
+              ls_sum += ls;
+              if (!op.inverse) yr[j] = fmaf(expf(ls), yr[j], ts[j]);       // cnf.py:179
+              else             yr[j] = (yr[j] - ts[j]) * expf(-ls);        // cnf.py:204
+            }
+            ld_s[et] += ls_sum;                                            // cnf.py:190
+          }
+        }
+      }
+
+      if (et < kTcRows) {
+        const long long r = row0 + et;
+        if (r < a.n_rows) {
+          for (int j = 0; j < D; ++j) a.out[r * D + j] = y_s[et * td.yp + j];
+          if (a.logdet) a.logdet[r] = ld_s[et];
+        }
+      }
+      epi_bar_sync();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
+// ---- pack: fp32 (out, in) weights -> bf16 hi/lo pre-swizzled tile images -----------------------------
+struct TcPackDesc {
+  const float* w;       // Linear weight (out, in) row-major
+  unsigned char* dst;   // tile base: [cta 0: hi, lo][cta 1: hi, lo]
+  int pitch;            // in_features of the Linear
+  int col0;             // first input column (skips nothing for the conditioner's own half)
+  int k_valid;          // real K
+  int n_valid;          // real N (hidden) / dout (last Linear)
+  int out_mode;         // 1: last Linear, rows [0,dout) -> n in [0,doh), rows [dout,2dout) -> n in [doh, 2doh)
+  int doh;
+  int chunk_off, chunk_n, kc;
+  int pad;
+};
+
+__global__ void tc_pack_kernel(const TcPackDesc* __restrict__ descs) {
+  const TcPackDesc d = descs[blockIdx.x];
+  const int half_rows = d.chunk_n >> 1;
+  const uint32_t rows_b = (uint32_t)half_rows * 128u;
+  for (int e = threadIdx.x; e < d.chunk_n * 8; e += blockDim.x) {
+    const int nl_all = e >> 3, c16 = e & 7;
+    const int r = nl_all / half_rows, nl = nl_all - r * half_rows;
+    const int n = d.chunk_off + nl_all;
+    int src_row = -1;
+    if (!d.out_mode) { if (n < d.n_valid) src_row = n; }
+    else if (n < d.doh) { if (n < d.n_valid) src_row = n; }
+    else if (n - d.doh < d.n_valid) src_row = d.n_valid + (n - d.doh);
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      float v[2];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int k = d.kc * 64 + c16 * 8 + p * 2 + t;
+        v[t] = (src_row >= 0 && k < d.k_valid) ? d.w[(size_t)src_row * d.pitch + d.col0 + k] : 0.f;
+      }
+      const float h0 = __bfloat162float(__float2bfloat16_rn(v[0])), h1 = __bfloat162float(__float2bfloat16_rn(v[1]));
+      hi[p] = pack_bf16x2(h0, h1);
+      lo[p] = pack_bf16x2(v[0] - h0, v[1] - h1);
+    }
+    unsigned char* base = d.dst + (size_t)r * 2u * rows_b + (size_t)nl * 128 + ((c16 ^ (nl & 7)) << 4);
+    *reinterpret_cast<uint4*>(base) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(base + rows_b) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+}  // namespace bcnf

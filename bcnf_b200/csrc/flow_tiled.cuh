@@ -99,8 +99,8 @@ struct TiledSmem {
 template <int R>
 __global__ void __launch_bounds__(kTiledThreads)
 flow_tiled_kernel(const FlowArgs a, const StackDims sd, const TiledSmem lay) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* y_s = reinterpret_cast<float*>(smem_raw);
+  extern __shared__ __align__(128) unsigned char smem_tl[];
+  float* y_s = reinterpret_cast<float*>(smem_tl);
   float* y2_s = y_s + R * lay.YP;
   float* xin_s = y2_s + R * lay.YP;
   float* ts_s = xin_s + R * lay.XP;

@@ -1,0 +1,104 @@
+"""tcgen05 path (bcnf_b200/csrc/flow_tc.cuh) against the CPU oracle, smallest shapes first.
+
+Tolerances (relative to max|ref|, SURVEY.md section 8d "correctness gates"):
+  bf16x3 (3-term bf16 split, fp32 accumulate): the fp32 gate of conftest.assert_parity, 1e-5.
+  bf16   (single pass):  z, x 1e-2; log-det 3e-2 -- the "stated bf16 tolerance" of north_star.
+"""
+import numpy as np
+import pytest
+import torch
+
+import bcnf_b200
+from bcnf_b200 import CondRealNVP_v2
+from conftest import assert_parity, rel_err
+from oracle import flow_oracle as fo
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+BF16_TOL = {"z": 1e-2, "x": 1e-2, "logdet": 3e-2}
+
+
+@pytest.fixture(autouse=True)
+def _no_grad():
+    with torch.no_grad():
+        yield
+
+
+def _model(size, nested, n_blocks, n_cond, precision, two_way=False, act_norm=True, seed=0):
+    torch.manual_seed(seed)
+    model = CondRealNVP_v2(size=size, nested_sizes=nested, n_blocks=n_blocks, n_conditions=n_cond,
+                           feature_networks=[bcnf_b200.ConcatenateCondition(None, n_cond)], dropout=0.3,
+                           act_norm=act_norm, two_way=two_way, precision=precision)
+    g = torch.Generator().manual_seed(seed + 1)
+    for layer in model.layers:
+        if isinstance(layer, bcnf_b200.ActNorm):
+            layer.scale.copy_(0.75 + 0.5 * torch.rand(layer.scale.shape, generator=g))
+            layer.bias.copy_(0.1 * torch.randn(layer.bias.shape, generator=g))
+    return model.to(DEV).eval()
+
+
+SHAPES = [
+    # (size, nested, blocks, C, two_way, rows)   -- ordered from the simplest MMA structure up
+    (19, [64], 1, 8, False, 128),               # one K chunk, one N chunk, one full tile
+    (19, [64, 64], 1, 8, False, 128),           # adds a hidden 64x64 layer
+    (19, [64, 64], 1, 8, False, 77),            # ragged tile
+    (19, [128, 128, 128], 2, 16, False, 300),   # 2 K chunks, several tiles, ActNorm + mixing
+    (19, [256] * 5, 2, 128, False, 257),        # sweep corner: N chunk of 256
+    (19, [512] * 5, 2, 128, False, 200),        # two N chunks
+    (19, [526] * 5, 3, 1360, False, 300),       # trajectory_*_large conditioner
+    (21, [175, 175, 175], 3, 107, True, 129),   # D=21, two-way, odd width
+    (19, [206, 206, 206], 3, 40, False, 513),
+]
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: f"D{s[0]}_H{s[1][0]}x{len(s[1])}_K{s[2]}_C{s[3]}_tw{int(s[4])}_B{s[5]}")
+def test_tensorcore_matches_oracle(shape, precision):
+    size, nested, blocks, n_cond, two_way, rows = shape
+    model = _model(size, nested, blocks, n_cond, precision, two_way)
+    assert model._flow().kernel == "tcgen05"
+    g = torch.Generator().manual_seed(11)
+    y = torch.randn(rows, size, generator=g)
+    h = torch.randn(rows, n_cond, generator=g)
+    z_in = torch.randn(rows, size, generator=g)
+    z = model(y, h, log_det_J=True)
+    ld = model.log_det_J
+    x = model.inverse(z_in, h)
+    sd = {k: v.cpu().numpy() for k, v in model.state_dict().items()}
+    l32 = fo.layers_from_state_dict(sd)
+    l64 = fo.layers_from_state_dict(sd, convert=lambda v: np.asarray(v, dtype=np.float64))
+    z32, ld32 = fo.stack_forward(l32, y.numpy(), h.numpy())
+    x32 = fo.stack_inverse(l32, z_in.numpy(), h.numpy())
+    z64, ld64 = fo.stack_forward(l64, y.numpy().astype(np.float64), h.numpy().astype(np.float64))
+    x64 = fo.stack_inverse(l64, z_in.numpy().astype(np.float64), h.numpy().astype(np.float64))
+    errs = {"z": rel_err(z.cpu().numpy(), z32), "logdet": rel_err(ld.cpu().numpy(), ld32),
+            "x": rel_err(x.cpu().numpy(), x32)}
+    print(f"\n{precision} {shape}: {errs}")
+    if precision == "bf16x3":
+        assert_parity(z.cpu().numpy(), z32, z64, what="z")
+        assert_parity(ld.cpu().numpy(), ld32, ld64, what="logdet")
+        assert_parity(x.cpu().numpy(), x32, x64, what="x")
+    else:
+        for k, tol in BF16_TOL.items():
+            assert errs[k] < tol, (k, errs)
+
+
+def test_tensorcore_agrees_with_fp32_kernels_on_golden_large_batch():
+    # same weights through the FMA kernel and the 3-pass tensor-core kernel, many tiles per CTA pair
+    m32 = _model(19, [128] * 3, 4, 32, "fp32")
+    mtc = _model(19, [128] * 3, 4, 32, "bf16x3")
+    g = torch.Generator().manual_seed(5)
+    n = 50_000
+    y = torch.randn(n, 19, generator=g).to(DEV)
+    h = torch.randn(n, 32, generator=g).to(DEV)
+    za = m32(y, h, log_det_J=True); la = m32.log_det_J
+    zb = mtc(y, h, log_det_J=True); lb = mtc.log_det_J
+    assert rel_err(zb.cpu().numpy(), za.cpu().numpy()) < 1e-5
+    assert rel_err(lb.cpu().numpy(), la.cpu().numpy()) < 1e-5
+
+
+def test_auto_precision_picks_the_kernel_family():
+    assert _model(19, [16] * 3, 2, 8, "auto")._flow().kernel == "rowthread"
+    assert _model(19, [128] * 3, 2, 8, "auto")._flow().kernel == "tcgen05"
+    assert _model(19, [1024] * 2, 2, 8, "auto")._flow().kernel == "tiled"   # 3-pass tiles do not fit in smem
+    assert _model(19, [1024] * 2, 2, 8, "bf16")._flow().kernel == "tcgen05"
