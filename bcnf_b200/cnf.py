@@ -415,7 +415,7 @@ class CondRealNVP_v2(ConditionalInvertibleLayer):
                  layer_kwargs: dict[str, Any] | None = None, activation: str = "GELU",
                  activation_kwargs: dict[str, Any] | None = None, device: Any = "cpu",
                  random_state: int | None = None, parameter_index_mapping: ParameterIndexMapping | None = None,
-                 hybrid: bool = False, *, sample_rng: str = "device", precision: str = "fp32") -> None:
+                 hybrid: bool = False, *, sample_rng: str = "device", precision: str = "auto") -> None:
         super().__init__()
         if n_conditions <= 0:
             # the reference accepts n_conditions == 0 in the constructor but every forward then

@@ -364,7 +364,7 @@ extern "C" int bcnf_flow_create(const bcnf_flow_desc_t* desc, const int32_t* op_
   const bool allow_rowthread = !(force && strcmp(force, "tiled") == 0);
   const bool rowthread_ok = allow_rowthread && uniform && (hp0 == 16 || hp0 == 32) && (sd.D == 19 || sd.D == 21) &&
                             std::max(f->prog[0].max_chunk_bytes, f->prog[1].max_chunk_bytes) <= kRowThreadChunkCap;
-  if (desc->precision != BCNF_PREC_FP32) {
+  if (desc->precision != BCNF_PREC_FP32 && allow_rowthread) {   // BCNF_FORCE_KERNEL=tiled pins the fp32 tiled kernel
     const int npass = desc->precision == BCNF_PREC_BF16X3 ? 3 : 1;
     if (prop.major != 10) { delete f; return fail(BCNF_E_UNSUPPORTED, "tcgen05 path needs an sm_100 device (got sm_%d%d)", prop.major, prop.minor); }
     if (const char* why = tc_plan(*f, npass)) { delete f; return fail(BCNF_E_UNSUPPORTED, "tensor-core path: %s", why); }

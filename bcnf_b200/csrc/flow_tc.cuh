@@ -32,8 +32,9 @@
 
 namespace bcnf {
 
-constexpr int kTcThreads = 320;         // warp 0 producer, warp 1 MMA (leader) / relay (peer), warps 2-9 epilogue
-constexpr int kTcEpiThreads = 256;
+constexpr int kTcEpiWarps = 16;
+constexpr int kTcEpiThreads = kTcEpiWarps * 32;
+constexpr int kTcThreads = 64 + kTcEpiThreads;   // warp 0 producer, warp 1 MMA (leader) / relay (peer), then epilogue
 constexpr int kTcRows = 64;             // rows per CTA (128 per CTA pair)
 constexpr int kTcATile = kTcRows * 128; // bytes of one 64-row x 64-col bf16 activation tile
 constexpr int kTcMaxLayers = BCNF_TC_MAX_LAYERS;
@@ -124,12 +125,17 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
       "h"((uint16_t)3)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
-  uint32_t r[8];
+// issue a TMEM load of 8 consecutive columns of this thread's lane (no wait)
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t (&r)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  tmem_ld8_issue(taddr, r);
+  tmem_ld_wait();
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
@@ -293,9 +299,9 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
     }
   } else {
     // ===================== epilogue warps ================================================================
-    const int et = tid - 64;                       // 0..255
+    const int et = tid - 64;                       // 0..kTcEpiThreads-1
     const int q = warp & 3;                        // TMEM lane quarter this warp may touch
-    const int ch = (warp - 2) >> 2;                // which half of the column groups
+    const int part = (warp - 2) >> 2;              // 4 warps share a quarter: each takes a quarter of the column groups
     const int row = ((q & 1) << 5) + lane;         // row of this CTA held by this thread's TMEM lane
     const int nhalf = q >> 1;                      // 2x2 layout: lanes 64..127 hold the second N half of a chunk
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -369,20 +375,36 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
           for (int nc = 0; nc < ly.n_chunks; ++nc) {
             const int cn = ly.chunk_n[nc];
             const int groups = cn >> 4;                 // 8-column groups in this thread's half chunk
-            const int g0 = ch == 0 ? 0 : (groups + 1) >> 1;
-            const int g1 = ch == 0 ? (groups + 1) >> 1 : groups;
+            const int g0 = (groups * part) >> 2, g1 = (groups * (part + 1)) >> 2;
             const int nbase = coff + nhalf * (cn >> 1);
-            for (int g = g0; g < g1; ++g) {
+            for (int g = g0; g < g1; g += 2) {
+              const bool two = g + 1 < g1;
               const int n0 = nbase + g * 8;
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(add + n0));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(add + n0 + 4));
+              // bias / projection values first (global, L1/L2), then two TMEM loads under one wait
+              float4 b[4];
+              b[0] = __ldg(reinterpret_cast<const float4*>(add + n0));
+              b[1] = __ldg(reinterpret_cast<const float4*>(add + n0 + 4));
+              if (two) {
+                b[2] = __ldg(reinterpret_cast<const float4*>(add + n0 + 8));
+                b[3] = __ldg(reinterpret_cast<const float4*>(add + n0 + 12));
+              }
+              uint32_t r0[8], r1[8];
+              tmem_ld8_issue(lane_addr + col + g * 8, r0);
+              if (two) tmem_ld8_issue(lane_addr + col + g * 8 + 8, r1);
+              tmem_ld_wait();
               float v[8];
-              tmem_ld8(lane_addr + col + g * 8, v);
-              v[0] = gelu_erf(v[0] + b0.x); v[1] = gelu_erf(v[1] + b0.y);
-              v[2] = gelu_erf(v[2] + b0.z); v[3] = gelu_erf(v[3] + b0.w);
-              v[4] = gelu_erf(v[4] + b1.x); v[5] = gelu_erf(v[5] + b1.y);
-              v[6] = gelu_erf(v[6] + b1.z); v[7] = gelu_erf(v[7] + b1.w);
+              v[0] = gelu_erf_fast(__uint_as_float(r0[0]) + b[0].x); v[1] = gelu_erf_fast(__uint_as_float(r0[1]) + b[0].y);
+              v[2] = gelu_erf_fast(__uint_as_float(r0[2]) + b[0].z); v[3] = gelu_erf_fast(__uint_as_float(r0[3]) + b[0].w);
+              v[4] = gelu_erf_fast(__uint_as_float(r0[4]) + b[1].x); v[5] = gelu_erf_fast(__uint_as_float(r0[5]) + b[1].y);
+              v[6] = gelu_erf_fast(__uint_as_float(r0[6]) + b[1].z); v[7] = gelu_erf_fast(__uint_as_float(r0[7]) + b[1].w);
               store_act8<NPASS>(a_hi, a_lo, row, n0, v);
+              if (two) {
+                v[0] = gelu_erf_fast(__uint_as_float(r1[0]) + b[2].x); v[1] = gelu_erf_fast(__uint_as_float(r1[1]) + b[2].y);
+                v[2] = gelu_erf_fast(__uint_as_float(r1[2]) + b[2].z); v[3] = gelu_erf_fast(__uint_as_float(r1[3]) + b[2].w);
+                v[4] = gelu_erf_fast(__uint_as_float(r1[4]) + b[3].x); v[5] = gelu_erf_fast(__uint_as_float(r1[5]) + b[3].y);
+                v[6] = gelu_erf_fast(__uint_as_float(r1[6]) + b[3].z); v[7] = gelu_erf_fast(__uint_as_float(r1[7]) + b[3].w);
+                store_act8<NPASS>(a_hi, a_lo, row, n0 + 8, v);
+              }
             }
             col += (uint32_t)(cn >> 1);
             coff += cn;
@@ -400,7 +422,7 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
         {
           const int doh = tl.doh;
           const int groups = doh >> 3;                  // 8-column groups per half (t or s)
-          for (int g = ch; g < groups; g += 2) {
+          for (int g = part; g < groups; g += 4) {
             float v[8];
             tmem_ld8(lane_addr + g * 8, v);
             const int j0 = g * 8;

@@ -114,10 +114,10 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-def build_model(cfg: dict, device):
+def build_model(cfg: dict, device, precision: str = "auto"):
     from bcnf_b200 import CondRealNVP_v2
     torch.manual_seed(0)
-    model = CondRealNVP_v2.from_config(cfg)
+    model = CondRealNVP_v2.from_config(cfg, precision=precision)
     perturb_actnorm(model)
     return model.to(device).eval()
 
@@ -170,6 +170,9 @@ def main() -> None:
     ap.add_argument("--workload", default="fc_large_sample", choices=sorted(WORKLOADS))
     ap.add_argument("--instances-per-step", type=int, default=0, help="per GPU; 0 = workload default")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16x3", "bf16"],
+                    help="conditioner GEMM arithmetic; auto = bf16x3 on tcgen05 for wide conditioners (fp32-class "
+                         "accuracy, 1e-5 gate), fp32 FMA for narrow ones")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -210,7 +213,7 @@ def main() -> None:
 
     from bcnf_b200 import _cabi
     _cabi.lib()                                  # fail loudly if the extension is missing
-    model = build_model(cfg, device)
+    model = build_model(cfg, device, args.precision)
     flow = model._flow()
     d = mk["size"]
     g = torch.Generator().manual_seed(100 + rank)
@@ -306,10 +309,13 @@ def main() -> None:
     if rank == 0:
         line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "scaling": "weak", "vs_baseline": None,
+                "dtype": {"fp32": "f32", "bf16x3": "bf16x3 split, f32 accumulate (fp32-class, 1e-5 gate)",
+                          "bf16": "bf16, f32 accumulate"}[flow.precision],
+                "data": "synthetic",
                 "config": {"workload": workload_name, "size": d, "nested_sizes": mk["nested_sizes"],
                            "n_blocks": mk["n_blocks"], "n_conditions": mk["n_conditions"],
-                           "kernel": flow.kernel, "precision": "fp32",
+                           "kernel": flow.kernel, "precision": flow.precision,
                            "l2": "inputs/outputs per step exceed L2 or are regenerated each step; weights "
                                  f"({int(flow.info.packed_bytes) >> 20} MiB packed) stream from L2/HBM",
                            "parallelism": f"instances sharded over {world} GPU(s), no collective"},
