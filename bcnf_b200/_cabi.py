@@ -14,9 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "libbcnf_b200.so")
 SOURCES = [os.path.join(HERE, "csrc", "bcnf_abi.cu")]
-HEADERS = [os.path.join(HERE, "csrc", n) for n in
-           ("common.cuh", "cond_project.cuh", "flow_rowthread.cuh", "flow_tiled.cuh")] + \
-          [os.path.join(REPO, "include", "bcnf_b200.h")]
+HEADERS = sorted(os.path.join(HERE, "csrc", n) for n in os.listdir(os.path.join(HERE, "csrc"))
+                 if n.endswith((".cuh", ".h"))) + [os.path.join(REPO, "include", "bcnf_b200.h")]
 
 MAX_HIDDEN_LAYERS = 8
 OP_ACTNORM, OP_COUPLING, OP_ORTHO = 0, 1, 2

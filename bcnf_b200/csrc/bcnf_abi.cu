@@ -524,14 +524,14 @@ static void emit_tc_half(const bcnf_flow& f, int s, const float* const* w, long 
     d.out_mode = l == hl.L;
     d.n_valid = l == hl.L ? hl.dout : hl.h[l];
     d.doh = tl.doh;
-    int coff = 0;
-    for (int nc = 0; nc < ly.n_chunks; ++nc) {
-      for (int kc = 0; kc < ly.kc; ++kc) {
+    for (int kc = 0; kc < ly.kc; ++kc) {          // K-major stream order, as the kernel consumes it
+      int coff = 0;
+      for (int nc = 0; nc < ly.n_chunks; ++nc) {
         d.dst = dst; d.chunk_off = coff; d.chunk_n = ly.chunk_n[nc]; d.kc = kc;
         v.push_back(d);
         dst += (size_t)4 * (ly.chunk_n[nc] / 2) * 128;
+        coff += ly.chunk_n[nc];
       }
-      coff += ly.chunk_n[nc];
     }
   }
 }
@@ -686,6 +686,29 @@ static int run_flow(bcnf_flow_t* f, int dir, const float* in, const float* P, co
   a.inst_period = inst_period; a.n_rows = n_rows;
   a.blob = p.d_blob; a.ops = p.d_ops; a.n_ops = (int)p.ops.size();
   a.chunks = p.d_chunks; a.n_chunks = (int)p.chunks.size();
+  a.trace = nullptr;
+  if (const char* tp = getenv("BCNF_TC_TRACE")) {
+    // debug aid: dump clock64 stamps of the first tile's pipeline to the named file (synchronises!)
+    if (f->kernel == BCNF_KERNEL_TCGEN05) {
+      long long* d_tr = nullptr;
+      CUDA_TRY(cudaMalloc(&d_tr, 64 * 8 * sizeof(long long)));
+      CUDA_TRY(cudaMemsetAsync(d_tr, 0, 64 * 8 * sizeof(long long), stream));
+      a.trace = d_tr;
+      int rc = f->npass == 3 ? launch_tc<3>(f, a, dir, stream) : launch_tc<1>(f, a, dir, stream);
+      std::vector<long long> h(64 * 8);
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      CUDA_TRY(cudaMemcpy(h.data(), d_tr, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+      cudaFree(d_tr);
+      if (FILE* fp = fopen(tp, "w")) {
+        for (int i = 0; i < 64; ++i) {
+          for (int j = 0; j < 8; ++j) fprintf(fp, "%lld ", h[i * 8 + j]);
+          fprintf(fp, "\n");
+        }
+        fclose(fp);
+      }
+      return rc;
+    }
+  }
   if (f->kernel == BCNF_KERNEL_TCGEN05)
     return f->npass == 3 ? launch_tc<3>(f, a, dir, stream) : launch_tc<1>(f, a, dir, stream);
   if (f->kernel == BCNF_KERNEL_ROWTHREAD) {

@@ -106,6 +106,7 @@ struct FlowArgs {
   int n_ops;
   const Chunk* chunks;
   int n_chunks;
+  long long* trace;       // debug: clock64 stamps of the tensor-core pipeline (null in normal runs)
 };
 
 __device__ __forceinline__ long long row_instance(const FlowArgs& a, long long r) {

@@ -34,7 +34,10 @@ namespace bcnf {
 
 constexpr int kTcEpiWarps = 16;
 constexpr int kTcEpiThreads = kTcEpiWarps * 32;
-constexpr int kTcThreads = 64 + kTcEpiThreads;   // warp 0 producer, warp 1 MMA (leader) / relay (peer), then epilogue
+constexpr int kTcIssuers = 4;                    // one MMA-issuing warp per N chunk (<= 4 chunks of <= 256 columns)
+constexpr int kTcFirstEpiWarp = 1 + kTcIssuers;
+// warp 0 producer; warps 1..4 MMA issuers (leader CTA; warp 1 of the peer relays stage arrivals); then epilogue
+constexpr int kTcThreads = 32 * kTcFirstEpiWarp + kTcEpiThreads;
 constexpr int kTcRows = 64;             // rows per CTA (128 per CTA pair)
 constexpr int kTcATile = kTcRows * 128; // bytes of one 64-row x 64-col bf16 activation tile
 constexpr int kTcMaxLayers = BCNF_TC_MAX_LAYERS;
@@ -175,8 +178,8 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
   uint64_t* w_full = reinterpret_cast<uint64_t*>(misc);              // [8]
   uint64_t* w_peer = w_full + 8;                                     // [8] leader only
   uint64_t* w_empty = w_peer + 8;                                    // [8]
-  uint64_t* acc_full = w_empty + 8;                                  // [1]
-  uint64_t* a_ready = acc_full + 1;                                  // [1] leader only
+  uint64_t* acc_full = w_empty + 8;                                  // [4] one per N chunk / issuer
+  uint64_t* a_ready = acc_full + 4;                                  // [1] leader only
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(a_ready + 1);
   float* ld_s = reinterpret_cast<float*>(tmem_ptr_s + 2);            // [64]
   const float** prow_s = reinterpret_cast<const float**>(ld_s + kTcRows);   // [64]
@@ -190,7 +193,7 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
 
   if (tid == 0) {
     for (int s = 0; s < n_stages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_peer[s], 1); mbar_init(&w_empty[s], 1); }
-    mbar_init(acc_full, 1);
+    for (int j = 0; j < kTcIssuers; ++j) mbar_init(&acc_full[j], 1);
     mbar_init(a_ready, 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -216,9 +219,10 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
           const unsigned char* src = tc_blob + tc_off[oi];
           for (int l = 0; l <= hl.L; ++l) {
             const TcLayer& ly = hl.layer[l];
-            for (int nc = 0; nc < ly.n_chunks; ++nc) {
-              const uint32_t rows_b = (uint32_t)(ly.chunk_n[nc] >> 1) * 128u;
-              for (int kc = 0; kc < ly.kc; ++kc, ++it) {
+            // K-major tile order: (kc, nc); issuer nc consumes every n_chunks-th tile
+            for (int kc = 0; kc < ly.kc; ++kc) {
+              for (int nc = 0; nc < ly.n_chunks; ++nc, ++it) {
+                const uint32_t rows_b = (uint32_t)(ly.chunk_n[nc] >> 1) * 128u;
                 const int s = it % n_stages;
                 const uint32_t use = it / n_stages;
                 if (use > 0) mbar_wait_cluster(&w_empty[s], (use - 1) & 1);
@@ -232,81 +236,101 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
         }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      uint32_t it = 0, a_cnt = 0;
-      if (!leader) {
-        // ===================== relay: tell the leader when this CTA's half of a stage has landed =========
-        for (long long tile = cluster_id; tile < n_tiles; tile += n_clusters)
-          for (int oi = 0; oi < a.n_ops; ++oi) {
-            const DevOp op = a.ops[oi];
-            if (op.type != DOP_HALF) continue;
-            const TcHalfLayout& hl = td.half[op.src];
-            for (int l = 0; l <= hl.L; ++l)
-              for (int nc = 0; nc < hl.layer[l].n_chunks; ++nc)
-                for (int kc = 0; kc < hl.layer[l].kc; ++kc, ++it) {
-                  const int s = it % n_stages;
-                  mbar_wait(&w_full[s], (it / n_stages) & 1);
-                  fence_proxy_async();
-                  mbar_arrive_remote(mapa_u32(smem_u32(&w_peer[s]), 0));
-                }
-          }
-      } else {
-        // ===================== MMA issuer (leader CTA, one thread) ========================================
-        const uint32_t a_hi_addr = smem_u32(a_hi), a_lo_addr = smem_u32(a_lo), st_addr = smem_u32(stage0);
-        for (long long tile = cluster_id; tile < n_tiles; tile += n_clusters)
-          for (int oi = 0; oi < a.n_ops; ++oi) {
-            const DevOp op = a.ops[oi];
-            if (op.type != DOP_HALF) continue;
-            const TcHalfLayout& hl = td.half[op.src];
-            for (int l = 0; l <= hl.L; ++l) {
-              const TcLayer& ly = hl.layer[l];
-              mbar_wait_cluster(a_ready, a_cnt & 1);    // activations of layer l written by both CTAs
-              ++a_cnt;
-              tc_fence_after();
-              uint32_t col = 0;
-              for (int nc = 0; nc < ly.n_chunks; ++nc) {
-                const int cn = ly.chunk_n[nc];
-                const uint32_t idesc = make_idesc(cn);
-                const uint32_t rows_b = (uint32_t)(cn >> 1) * 128u;
-                for (int kc = 0; kc < ly.kc; ++kc, ++it) {
-                  const int s = it % n_stages;
-                  const uint32_t par = (it / n_stages) & 1;
-                  mbar_wait(&w_full[s], par);
-                  mbar_wait_cluster(&w_peer[s], par);
-                  tc_fence_after();
-                  const int ksteps = kc == ly.kc - 1 ? ly.last_ksteps : 4;
-                  const uint64_t ah = make_smem_desc(a_hi_addr + kc * kTcATile);
-                  const uint64_t al = make_smem_desc(a_lo_addr + kc * kTcATile);
-                  const uint64_t wh = make_smem_desc(st_addr + s * td.stage_bytes);
-                  const uint64_t wl = make_smem_desc(st_addr + s * td.stage_bytes + rows_b);
-                  for (int k = 0; k < ksteps; ++k) {
-                    const uint32_t first = (kc | k) == 0 ? 0u : 1u;
-                    umma_2sm(tmem_base + col, ah + 2 * k, wh + 2 * k, idesc, first);
-                    if (NPASS == 3) {
-                      umma_2sm(tmem_base + col, al + 2 * k, wh + 2 * k, idesc, 1u);
-                      umma_2sm(tmem_base + col, ah + 2 * k, wl + 2 * k, idesc, 1u);
-                    }
-                  }
-                  umma_commit_2sm(&w_empty[s]);      // stage free in both CTAs once these MMAs retire
-                }
-                col += (uint32_t)(cn >> 1);
-              }
-              umma_commit_2sm(acc_full);             // layer output complete in TMEM of both CTAs
-            }
-          }
+  } else if (warp < kTcFirstEpiWarp) {
+    if (!leader) {
+      // ===================== relay: tell the leader when this CTA's half of a stage has landed ===========
+      // one lane per stage, so the waits of different stages overlap instead of serialising
+      if (warp == 1 && lane < n_stages) {
+        long long per_tile = 0;
+        for (int oi = 0; oi < a.n_ops; ++oi) {
+          const DevOp op = a.ops[oi];
+          if (op.type != DOP_HALF) continue;
+          const TcHalfLayout& hl = td.half[op.src];
+          for (int l = 0; l <= hl.L; ++l) per_tile += (long long)hl.layer[l].n_chunks * hl.layer[l].kc;
+        }
+        const long long my_tiles = cluster_id < n_tiles ? (n_tiles - cluster_id + n_clusters - 1) / n_clusters : 0;
+        const long long total = per_tile * my_tiles;
+        const uint32_t peer_bar = mapa_u32(smem_u32(&w_peer[lane]), 0);
+        uint32_t use = 0;
+        for (long long it = lane; it < total; it += n_stages, ++use) {
+          mbar_wait(&w_full[lane], use & 1);
+          mbar_arrive_remote(peer_bar);
+        }
       }
+    } else if (lane == 0) {
+      // ===================== MMA issuers (leader CTA): warp 1+j issues every MMA of N chunk j ==============
+      // Several issuing threads keep the tensor pipe fed while each one waits on barriers and builds
+      // descriptors; chunks write disjoint TMEM columns, so their relative order does not matter.
+      const int j = warp - 1;
+      const uint32_t a_hi_addr = smem_u32(a_hi), a_lo_addr = smem_u32(a_lo), st_addr = smem_u32(stage0);
+      uint32_t a_cnt = 0;
+      int s = 0;            // ring position of the next tile of the stream (all chunks)
+      uint32_t par = 0;
+      for (long long tile = cluster_id; tile < n_tiles; tile += n_clusters)
+        for (int oi = 0; oi < a.n_ops; ++oi) {
+          const DevOp op = a.ops[oi];
+          if (op.type != DOP_HALF) continue;
+          const TcHalfLayout& hl = td.half[op.src];
+          for (int l = 0; l <= hl.L; ++l) {
+            const TcLayer& ly = hl.layer[l];
+            const int nch = ly.n_chunks;
+            // every issuer observes every phase of a_ready (a parity wait must not skip phases)
+            mbar_wait_cluster(a_ready, a_cnt & 1);    // activations of layer l written by both CTAs
+            ++a_cnt;
+            tc_fence_after();
+            if (j >= nch) {                    // not my layer: only keep the ring position in step
+              int adv = nch * ly.kc;
+              while (adv > 0) { const int d = adv < n_stages - s ? adv : n_stages - s; s += d; adv -= d; if (s == n_stages) { s = 0; par ^= 1; } }
+              continue;
+            }
+            const bool tr = a.trace && j == 0 && blockIdx.x == 0 && tile == cluster_id && a_cnt <= 32;
+            if (tr) a.trace[(a_cnt - 1) * 8 + 0] = clock64();
+            uint32_t col = 0;
+            for (int c = 0; c < j; ++c) col += (uint32_t)(ly.chunk_n[c] >> 1);
+            const int cn = ly.chunk_n[j];
+            const uint32_t idesc = make_idesc(cn);
+            const uint32_t rows_b = (uint32_t)(cn >> 1) * 128u;
+            for (int kc = 0; kc < ly.kc; ++kc) {
+              // my tile of this K step sits j positions further in the ring
+              int sj = s + j; uint32_t pj = par;
+              while (sj >= n_stages) { sj -= n_stages; pj ^= 1; }
+              mbar_wait(&w_full[sj], pj);
+              mbar_wait_cluster(&w_peer[sj], pj);
+              tc_fence_after();
+              if (tr && kc == 0) a.trace[(a_cnt - 1) * 8 + 1] = clock64();
+              const int ksteps = kc == ly.kc - 1 ? ly.last_ksteps : 4;
+              const uint64_t ah = make_smem_desc(a_hi_addr + kc * kTcATile);
+              const uint64_t al = make_smem_desc(a_lo_addr + kc * kTcATile);
+              const uint64_t wh = make_smem_desc(st_addr + sj * td.stage_bytes);
+              const uint64_t wl = make_smem_desc(st_addr + sj * td.stage_bytes + rows_b);
+              for (int k = 0; k < ksteps; ++k) {
+                const uint32_t first = (kc | k) == 0 ? 0u : 1u;
+                umma_2sm(tmem_base + col, ah + 2 * k, wh + 2 * k, idesc, first);
+                if (NPASS == 3) {
+                  umma_2sm(tmem_base + col, al + 2 * k, wh + 2 * k, idesc, 1u);
+                  umma_2sm(tmem_base + col, ah + 2 * k, wl + 2 * k, idesc, 1u);
+                }
+              }
+              umma_commit_2sm(&w_empty[sj]);      // stage free in both CTAs once these MMAs retire
+              s += nch;
+              while (s >= n_stages) { s -= n_stages; par ^= 1; }
+            }
+            umma_commit_2sm(&acc_full[j]);        // chunk j of the layer output complete in TMEM of both CTAs
+            if (tr) a.trace[(a_cnt - 1) * 8 + 2] = clock64();
+          }
+        }
     }
   } else {
     // ===================== epilogue warps ================================================================
-    const int et = tid - 64;                       // 0..kTcEpiThreads-1
+    const int et = tid - 32 * kTcFirstEpiWarp;     // 0..kTcEpiThreads-1
     const int q = warp & 3;                        // TMEM lane quarter this warp may touch
-    const int part = (warp - 2) >> 2;              // 4 warps share a quarter: each takes a quarter of the column groups
+    const int part = (warp - kTcFirstEpiWarp) >> 2;   // 4 warps share a quarter: each takes a quarter of the column groups
     const int row = ((q & 1) << 5) + lane;         // row of this CTA held by this thread's TMEM lane
     const int nhalf = q >> 1;                      // 2x2 layout: lanes 64..127 hold the second N half of a chunk
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const int D = sd.D;
-    uint32_t acc_cnt = 0;
+    uint32_t acc_cnt = 0;                          // layers seen (trace index)
+    uint32_t acc_use[kTcIssuers] = {0, 0, 0, 0};   // phase counters of the per-chunk accumulator barriers
     const uint32_t a_ready_leader = mapa_u32(smem_u32(a_ready), 0);
 
     for (long long tile = cluster_id; tile < n_tiles; tile += n_clusters) {
@@ -366,9 +390,13 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
         // ---- hidden layers: TMEM -> (+P | +bias) -> GELU -> bf16 hi/lo tiles of the next layer ----
         for (int l = 0; l < tl.L; ++l) {
           const TcLayer& ly = tl.layer[l];
-          mbar_wait_cluster(acc_full, acc_cnt & 1);
+#pragma unroll
+          for (int j = 0; j < kTcIssuers; ++j)
+            if (j < ly.n_chunks) { mbar_wait_cluster(&acc_full[j], acc_use[j] & 1); ++acc_use[j]; }
           ++acc_cnt;
           tc_fence_after();
+          const bool tr = a.trace && blockIdx.x == 0 && tile == cluster_id && acc_cnt <= 32 && et == 0;
+          if (tr) a.trace[(acc_cnt - 1) * 8 + 3] = clock64();
           const float* add = l == 0 ? prow_s[row] + op.proj_off : w + hl.off_b[l];
           uint32_t col = 0;
           int coff = 0;
@@ -409,14 +437,17 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
             col += (uint32_t)(cn >> 1);
             coff += cn;
           }
+          if (tr) a.trace[(acc_cnt - 1) * 8 + 4] = clock64();
           tc_fence_before();
           fence_proxy_async();
           epi_bar_sync();
+          if (tr) a.trace[(acc_cnt - 1) * 8 + 5] = clock64();
           if (et == 0) mbar_arrive_remote(a_ready_leader);
         }
 
         // ---- last Linear: (t | s) from TMEM, then the affine update on the row-owner threads ----
-        mbar_wait_cluster(acc_full, acc_cnt & 1);
+        mbar_wait_cluster(&acc_full[0], acc_use[0] & 1);   // the last Linear is a single chunk
+        ++acc_use[0];
         ++acc_cnt;
         tc_fence_after();
         {
