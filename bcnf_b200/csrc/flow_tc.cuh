@@ -121,11 +121,26 @@ __device__ __forceinline__ void umma_2sm(uint32_t tmem_d, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
-__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
+  // arrives (once the MMAs issued so far by this thread retire) on the barrier at this offset in every CTA of the mask
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
           smem_u32(bar)),
-      "h"((uint16_t)3)
+      "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+// TMA bulk copy global -> the same shared-memory offset of every CTA in cta_mask; each destination's
+// mbarrier (same offset) receives the complete_tx
+__device__ __forceinline__ void tma_bulk_g2s_mc(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
       : "memory");
 }
 // issue a TMEM load of 8 consecutive columns of this thread's lane (no wait)
@@ -164,8 +179,11 @@ __device__ __forceinline__ void store_act8(unsigned char* a_hi, unsigned char* a
                    pack_bf16x2(v[4] - hi[4], v[5] - hi[5]), pack_bf16x2(v[6] - hi[6], v[7] - hi[7]));
 }
 
+// Launched with a cluster of CS = 2, 4 or 8 CTAs = CS/2 CTA pairs.  Each pair owns its own 128-row tile;
+// the pairs of a cluster walk the same weight stream in lockstep, and every weight half-tile is fetched
+// from L2 once per cluster and multicast to the same-rank CTA of every pair.
 template <int NPASS>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kTcThreads, 1)
 flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsigned char* __restrict__ tc_blob,
                const long long* __restrict__ tc_off) {
   extern __shared__ __align__(1024) unsigned char smem_tc[];
@@ -185,14 +203,23 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
   const float** prow_s = reinterpret_cast<const float**>(ld_s + kTcRows);   // [64]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t cta = cluster_ctarank();
-  const bool leader = cta == 0;
+  const uint32_t cta = cluster_ctarank();         // rank in the cluster
+  const uint32_t csize = cluster_nctarank();
+  const uint32_t n_pairs = csize >> 1, pair = cta >> 1, prank = cta & 1u, lead_rank = cta & ~1u;
+  const bool leader = prank == 0;                 // even rank of a pair issues the MMAs
   const int n_stages = td.n_stages;
   const long long n_tiles = (a.n_rows + 2 * kTcRows - 1) / (2 * kTcRows);
-  const long long n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
+  const long long n_clusters = gridDim.x / csize, cluster_id = blockIdx.x / csize;
+  // every pair of every cluster runs the same number of iterations (the weight stream is shared);
+  // iterations whose tile index is past the end run on padding rows and store nothing
+  const long long n_iter = (n_tiles + n_clusters * n_pairs - 1) / (n_clusters * n_pairs);
+  const uint16_t mask_all = (uint16_t)((1u << csize) - 1u);
+  const uint16_t mask_pair = (uint16_t)(3u << (2u * pair));
+  uint16_t mask_same_rank = 0;
+  for (uint32_t p2 = 0; p2 < n_pairs; ++p2) mask_same_rank |= (uint16_t)(1u << (2u * p2 + prank));
 
   if (tid == 0) {
-    for (int s = 0; s < n_stages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_peer[s], 1); mbar_init(&w_empty[s], 1); }
+    for (int s = 0; s < n_stages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_peer[s], 1); mbar_init(&w_empty[s], (int)n_pairs); }
     for (int j = 0; j < kTcIssuers; ++j) mbar_init(&acc_full[j], 1);
     mbar_init(a_ready, 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -211,7 +238,7 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
     // ===================== weight producer (each CTA streams its half of every tile) =====================
     if (lane == 0) {
       uint32_t it = 0;
-      for (long long tile = cluster_id; tile < n_tiles; tile += n_clusters) {
+      for (long long iter = 0; iter < n_iter; ++iter) {
         for (int oi = 0; oi < a.n_ops; ++oi) {
           const DevOp op = a.ops[oi];
           if (op.type != DOP_HALF) continue;
@@ -227,8 +254,11 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
                 const uint32_t use = it / n_stages;
                 if (use > 0) mbar_wait_cluster(&w_empty[s], (use - 1) & 1);
                 const uint32_t bytes = rows_b * (NPASS == 3 ? 2u : 1u);
-                mbar_expect_tx(&w_full[s], bytes);
-                tma_bulk_g2s(stage0 + (size_t)s * td.stage_bytes, src + (size_t)cta * 2u * rows_b, bytes, &w_full[s]);
+                mbar_expect_tx(&w_full[s], bytes);     // every CTA arms its own barrier for every tile
+                unsigned char* dst = stage0 + (size_t)s * td.stage_bytes;
+                const unsigned char* half = src + (size_t)prank * 2u * rows_b;
+                if (n_pairs == 1) tma_bulk_g2s(dst, half, bytes, &w_full[s]);
+                else if (it % n_pairs == pair) tma_bulk_g2s_mc(dst, half, bytes, &w_full[s], mask_same_rank);
                 src += 4u * rows_b;
               }
             }
@@ -248,9 +278,8 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
           const TcHalfLayout& hl = td.half[op.src];
           for (int l = 0; l <= hl.L; ++l) per_tile += (long long)hl.layer[l].n_chunks * hl.layer[l].kc;
         }
-        const long long my_tiles = cluster_id < n_tiles ? (n_tiles - cluster_id + n_clusters - 1) / n_clusters : 0;
-        const long long total = per_tile * my_tiles;
-        const uint32_t peer_bar = mapa_u32(smem_u32(&w_peer[lane]), 0);
+        const long long total = per_tile * n_iter;
+        const uint32_t peer_bar = mapa_u32(smem_u32(&w_peer[lane]), lead_rank);
         uint32_t use = 0;
         for (long long it = lane; it < total; it += n_stages, ++use) {
           mbar_wait(&w_full[lane], use & 1);
@@ -266,7 +295,7 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
       uint32_t a_cnt = 0;
       int s = 0;            // ring position of the next tile of the stream (all chunks)
       uint32_t par = 0;
-      for (long long tile = cluster_id; tile < n_tiles; tile += n_clusters)
+      for (long long iter = 0; iter < n_iter; ++iter)
         for (int oi = 0; oi < a.n_ops; ++oi) {
           const DevOp op = a.ops[oi];
           if (op.type != DOP_HALF) continue;
@@ -283,7 +312,7 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
               while (adv > 0) { const int d = adv < n_stages - s ? adv : n_stages - s; s += d; adv -= d; if (s == n_stages) { s = 0; par ^= 1; } }
               continue;
             }
-            const bool tr = a.trace && j == 0 && blockIdx.x == 0 && tile == cluster_id && a_cnt <= 32;
+            const bool tr = a.trace && j == 0 && blockIdx.x == 0 && iter == 0 && a_cnt <= 32;
             if (tr) a.trace[(a_cnt - 1) * 8 + 0] = clock64();
             uint32_t col = 0;
             for (int c = 0; c < j; ++c) col += (uint32_t)(ly.chunk_n[c] >> 1);
@@ -311,11 +340,11 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
                   umma_2sm(tmem_base + col, ah + 2 * k, wl + 2 * k, idesc, 1u);
                 }
               }
-              umma_commit_2sm(&w_empty[sj]);      // stage free in both CTAs once these MMAs retire
+              umma_commit_2sm(&w_empty[sj], mask_all);   // one of n_pairs arrivals that free the stage cluster-wide
               s += nch;
               while (s >= n_stages) { s -= n_stages; par ^= 1; }
             }
-            umma_commit_2sm(&acc_full[j]);        // chunk j of the layer output complete in TMEM of both CTAs
+            umma_commit_2sm(&acc_full[j], mask_pair);  // chunk j of the layer output complete in TMEM of both CTAs
             if (tr) a.trace[(a_cnt - 1) * 8 + 2] = clock64();
           }
         }
@@ -331,10 +360,11 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
     const int D = sd.D;
     uint32_t acc_cnt = 0;                          // layers seen (trace index)
     uint32_t acc_use[kTcIssuers] = {0, 0, 0, 0};   // phase counters of the per-chunk accumulator barriers
-    const uint32_t a_ready_leader = mapa_u32(smem_u32(a_ready), 0);
+    const uint32_t a_ready_leader = mapa_u32(smem_u32(a_ready), lead_rank);
 
-    for (long long tile = cluster_id; tile < n_tiles; tile += n_clusters) {
-      const long long row0 = tile * (2 * kTcRows) + (long long)cta * kTcRows;
+    for (long long iter = 0; iter < n_iter; ++iter) {
+      const long long tile = (iter * n_clusters + cluster_id) * n_pairs + pair;   // >= n_tiles: padding iteration
+      const long long row0 = tile * (2 * kTcRows) + (long long)prank * kTcRows;
       if (et < kTcRows) {
         const long long r = row0 + et;
         const bool valid = r < a.n_rows;
@@ -395,7 +425,7 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
             if (j < ly.n_chunks) { mbar_wait_cluster(&acc_full[j], acc_use[j] & 1); ++acc_use[j]; }
           ++acc_cnt;
           tc_fence_after();
-          const bool tr = a.trace && blockIdx.x == 0 && tile == cluster_id && acc_cnt <= 32 && et == 0;
+          const bool tr = a.trace && blockIdx.x == 0 && iter == 0 && acc_cnt <= 32 && et == 0;
           if (tr) a.trace[(acc_cnt - 1) * 8 + 3] = clock64();
           const float* add = l == 0 ? prow_s[row] + op.proj_off : w + hl.off_b[l];
           uint32_t col = 0;

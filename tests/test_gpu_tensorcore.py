@@ -97,6 +97,28 @@ def test_tensorcore_agrees_with_fp32_kernels_on_golden_large_batch():
     assert rel_err(lb.cpu().numpy(), la.cpu().numpy()) < 1e-5
 
 
+@pytest.mark.parametrize("cluster", ["2", "4", "8"])
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+def test_cluster_multicast_sizes_agree(cluster, precision, monkeypatch):
+    # 2, 4 and 8-CTA clusters (1, 2, 4 CTA pairs on one multicast weight stream) give bit-identical results,
+    # including ragged tile counts where some pairs run padding iterations
+    monkeypatch.setenv("BCNF_TC_CLUSTER", "2")
+    ref_model = _model(19, [176, 176, 176], 3, 24, precision)
+    g = torch.Generator().manual_seed(21)
+    outs = {}
+    for rows in (1, 129, 128 * 5 + 3, 128 * 40 + 77):
+        y = torch.randn(rows, 19, generator=g).to(DEV)
+        h = torch.randn(rows, 24, generator=g).to(DEV)
+        monkeypatch.setenv("BCNF_TC_CLUSTER", "2")
+        z2 = ref_model(y, h, log_det_J=True).clone(); l2 = ref_model.log_det_J.clone()
+        monkeypatch.setenv("BCNF_TC_CLUSTER", cluster)
+        zc = ref_model(y, h, log_det_J=True); lc = ref_model.log_det_J
+        assert torch.equal(z2, zc) and torch.equal(l2, lc), (rows, cluster)
+        xc = ref_model.inverse(zc, h)
+        monkeypatch.setenv("BCNF_TC_CLUSTER", "2")
+        assert torch.equal(xc, ref_model.inverse(z2, h))
+
+
 def test_auto_precision_picks_the_kernel_family():
     assert _model(19, [16] * 3, 2, 8, "auto")._flow().kernel == "rowthread"
     assert _model(19, [128] * 3, 2, 8, "auto")._flow().kernel == "tcgen05"
