@@ -49,14 +49,26 @@ __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-__device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+// Shared-memory reads by 32-bit shared-window address.  The parameter buffers are reached through
+// runtime-selected pointers, which the compiler would otherwise treat as generic (LD.E instead of
+// LDS: measured 44 % of all stall samples in the first version of this kernel).
+__device__ __forceinline__ float4 lds4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds1(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
 
-// acc[j] += x * w[j], j < N, w in shared memory (broadcast reads)
+// acc[j] += x * w[j], j < N, w = shared-window byte address (broadcast reads)
 template <int N>
-__device__ __forceinline__ void axpy_row(float (&acc)[N], float x, const float* __restrict__ w) {
+__device__ __forceinline__ void axpy_row(float (&acc)[N], float x, uint32_t w) {
 #pragma unroll
   for (int j = 0; j < N; j += 4) {
-    float4 v = lds4(w + j);
+    float4 v = lds4(w + 4 * j);
     acc[j + 0] = fmaf(x, v.x, acc[j + 0]);
     acc[j + 1] = fmaf(x, v.y, acc[j + 1]);
     acc[j + 2] = fmaf(x, v.z, acc[j + 2]);
@@ -66,7 +78,7 @@ __device__ __forceinline__ void axpy_row(float (&acc)[N], float x, const float* 
 
 // One conditioner network + affine update of the other half (cnf.py:98-107, :178-190, :203-204).
 template <int D, int HP, int SRC>
-__device__ __forceinline__ void half_coupling(float (&y)[D], float& ld, const float* __restrict__ w,
+__device__ __forceinline__ void half_coupling(float (&y)[D], float& ld, uint32_t w,
                                               const HalfLayout& hl, const float* __restrict__ prow,
                                               int inverse) {
   constexpr int DA = (D + 1) / 2, DB = D / 2;
@@ -84,27 +96,27 @@ __device__ __forceinline__ void half_coupling(float (&y)[D], float& ld, const fl
     acc[j] = v.x; acc[j + 1] = v.y; acc[j + 2] = v.z; acc[j + 3] = v.w;
   }
   {
-    const float* w1 = w + hl.off_w[0];
+    const uint32_t w1 = w + 4u * hl.off_w[0];
 #pragma unroll
-    for (int i = 0; i < DIN; ++i) axpy_row<HP>(acc, y[IN0 + i], w1 + i * HP);
+    for (int i = 0; i < DIN; ++i) axpy_row<HP>(acc, y[IN0 + i], w1 + 4u * (i * HP));
   }
   const int L = hl.L;
   for (int l = 1;; ++l) {
     float hcur[HP];
 #pragma unroll
-    for (int j = 0; j < HP; ++j) hcur[j] = gelu_erf(acc[j]);   // nn.GELU(); Dropout = identity in eval
+    for (int j = 0; j < HP; ++j) hcur[j] = gelu_erf_fast(acc[j]);   // nn.GELU() (exact-erf form); Dropout = identity in eval
     if (l >= L) {
       // last Linear -> (t, s); t = first DOUT outputs, s = last DOUT (chunk(2, dim=1), cnf.py:104)
       float ts[2 * DOP];
-      const float* wo = w + hl.off_wout;
-      const float* bo = w + hl.off_bout;
+      const uint32_t wo = w + 4u * hl.off_wout;
+      const uint32_t bo = w + 4u * hl.off_bout;
 #pragma unroll
       for (int j = 0; j < 2 * DOP; j += 4) {
-        float4 v = lds4(bo + j);
+        float4 v = lds4(bo + 4 * j);
         ts[j] = v.x; ts[j + 1] = v.y; ts[j + 2] = v.z; ts[j + 3] = v.w;
       }
 #pragma unroll
-      for (int k = 0; k < HP; ++k) axpy_row<2 * DOP>(ts, hcur[k], wo + k * (2 * DOP));
+      for (int k = 0; k < HP; ++k) axpy_row<2 * DOP>(ts, hcur[k], wo + 4u * (k * (2 * DOP)));
       float ls_sum = 0.f;
 #pragma unroll
       for (int j = 0; j < DOUT; ++j) {
@@ -116,15 +128,15 @@ __device__ __forceinline__ void half_coupling(float (&y)[D], float& ld, const fl
       ld += ls_sum;                                                 // cnf.py:190, :488
       return;
     }
-    const float* wl = w + hl.off_w[l];
-    const float* bl = w + hl.off_b[l];
+    const uint32_t wl = w + 4u * hl.off_w[l];
+    const uint32_t bl = w + 4u * hl.off_b[l];
 #pragma unroll
     for (int j = 0; j < HP; j += 4) {
-      float4 v = lds4(bl + j);
+      float4 v = lds4(bl + 4 * j);
       acc[j] = v.x; acc[j + 1] = v.y; acc[j + 2] = v.z; acc[j + 3] = v.w;
     }
 #pragma unroll
-    for (int k = 0; k < HP; ++k) axpy_row<HP>(acc, hcur[k], wl + k * HP);
+    for (int k = 0; k < HP; ++k) axpy_row<HP>(acc, hcur[k], wl + 4u * (k * HP));
   }
 }
 
@@ -136,6 +148,7 @@ flow_rowthread_kernel(const FlowArgs a, const StackDims sd, const int chunk_cap_
   constexpr int DP = (D + 3) / 4 * 4;
   extern __shared__ __align__(128) unsigned char smem_rt[];
   float* buf[2] = {reinterpret_cast<float*>(smem_rt), reinterpret_cast<float*>(smem_rt + chunk_cap_bytes)};
+  const uint32_t buf_addr0 = smem_u32(smem_rt);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_rt + 2 * (size_t)chunk_cap_bytes);
 
   const int tid = threadIdx.x;
@@ -179,10 +192,10 @@ flow_rowthread_kernel(const FlowArgs a, const StackDims sd, const int chunk_cap_
       const int b = (int)(g & 1);
       mbar_wait(&bars[b], (uint32_t)((g >> 1) & 1));
       const Chunk c = a.chunks[ci];
-      const float* base = buf[b];
+      const uint32_t base = buf_addr0 + (uint32_t)b * (uint32_t)chunk_cap_bytes;
       for (int oi = 0; oi < c.n_ops; ++oi) {
         const DevOp op = a.ops[c.first_op + oi];
-        const float* w = base + (op.off - c.off);
+        const uint32_t w = base + 4u * (uint32_t)(op.off - c.off);
         if (op.type == DOP_HALF) {
           if (op.src == 0) half_coupling<D, HP, 0>(y, ld, w, sd.half[0], prow + op.proj_off, op.inverse);
           else             half_coupling<D, HP, 1>(y, ld, w, sd.half[1], prow + op.proj_off, op.inverse);
@@ -192,17 +205,17 @@ flow_rowthread_kernel(const FlowArgs a, const StackDims sd, const int chunk_cap_
 #pragma unroll
           for (int j = 0; j < DP; ++j) o[j] = 0.f;
 #pragma unroll
-          for (int i = 0; i < D; ++i) axpy_row<DP>(o, y[i], w + i * DP);
+          for (int i = 0; i < D; ++i) axpy_row<DP>(o, y[i], w + 4u * (i * DP));
 #pragma unroll
           for (int j = 0; j < D; ++j) y[j] = o[j];
         } else if (op.type == DOP_ACTNORM_FWD) {
 #pragma unroll
-          for (int j = 0; j < D; ++j) y[j] = fmaf(w[j], y[j], w[DP + j]);       // cnf.py:349
-          ld += w[2 * DP];                                                      // cnf.py:350
+          for (int j = 0; j < D; ++j) y[j] = fmaf(lds1(w + 4 * j), y[j], lds1(w + 4 * (DP + j)));   // cnf.py:349
+          ld += lds1(w + 4 * (2 * DP));                                                              // cnf.py:350
         } else {  // DOP_ACTNORM_INV
 #pragma unroll
-          for (int j = 0; j < D; ++j) y[j] = __fdiv_rn(y[j] - w[DP + j], w[j]); // cnf.py:354
-          ld += w[2 * DP];
+          for (int j = 0; j < D; ++j) y[j] = __fdiv_rn(y[j] - lds1(w + 4 * (DP + j)), lds1(w + 4 * j));   // cnf.py:354
+          ld += lds1(w + 4 * (2 * DP));
         }
       }
       __syncthreads();   // every thread is done reading buf[b]
