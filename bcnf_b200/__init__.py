@@ -6,6 +6,7 @@ from .factories import FeatureNetworkFactory, OptimizerFactory, SchedulerFactory
 from .feature_network import (ConcatenateCondition, FeatureNetwork, FeatureNetworkStack,  # noqa: F401
                               FrExpFeatureNetwork, FullyConnectedFeatureNetwork, LSTMFeatureNetwork,
                               Transformer)
+from .train import Trainer  # noqa: F401
 from .utils import ParameterIndexMapping, inn_nll_loss, load_config  # noqa: F401
 
 __version__ = "0.1.0"

@@ -24,7 +24,8 @@ KERNEL_NAMES = {0: "rowthread", 1: "tiled", 2: "tcgen05"}
 
 EXPORTS = ["bcnf_abi_version", "bcnf_last_error", "bcnf_flow_create", "bcnf_flow_destroy",
            "bcnf_flow_info", "bcnf_flow_set_params", "bcnf_cond_project", "bcnf_flow_forward",
-           "bcnf_flow_inverse"]
+           "bcnf_flow_inverse", "bcnf_train_gemm", "bcnf_train_colsum", "bcnf_train_dropout_mask"]
+EPI_NONE, EPI_BIAS, EPI_BIAS_GELU_DROP, EPI_DGELU_DROP = 0, 1, 2, 3
 
 
 class FlowDesc(C.Structure):
@@ -45,6 +46,14 @@ class FlowInfo(C.Structure):
     _fields_ = [("kernel", C.c_int32), ("proj_width", C.c_int32), ("n_half_couplings", C.c_int32),
                 ("rows_per_cta", C.c_int32), ("packed_bytes", C.c_int64), ("macs_per_row", C.c_int64),
                 ("macs_per_instance", C.c_int64)]
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [("A", C.c_void_p), ("B", C.c_void_p), ("C", C.c_void_p), ("M", C.c_int32), ("N", C.c_int32),
+                ("K", C.c_int32), ("as0", C.c_int64), ("as1", C.c_int64), ("bs0", C.c_int64), ("bs1", C.c_int64),
+                ("cs0", C.c_int64), ("beta", C.c_float), ("epilogue", C.c_int32), ("bias", C.c_void_p),
+                ("save", C.c_void_p), ("saved", C.c_void_p), ("seed", C.c_uint64), ("layer_uid", C.c_uint32),
+                ("p_drop", C.c_float)]
 
 
 def nvcc_command(out_path: str = LIB_PATH) -> list[str]:
@@ -94,6 +103,10 @@ def lib() -> C.CDLL:
                  C.c_void_p, C.c_void_p]
     L.bcnf_flow_forward.argtypes = flow_args
     L.bcnf_flow_inverse.argtypes = flow_args
+    L.bcnf_train_gemm.argtypes = [C.POINTER(GemmArgs), C.c_int32, C.c_void_p]
+    L.bcnf_train_colsum.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_float, C.c_int32, C.c_void_p]
+    L.bcnf_train_dropout_mask.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_uint64, C.c_uint32, C.c_float,
+                                          C.c_int32, C.c_void_p]
     for name in EXPORTS:
         if name not in ("bcnf_last_error",):
             getattr(L, name).restype = C.c_int if name != "bcnf_last_error" else C.c_char_p

@@ -510,8 +510,8 @@ class CondRealNVP_v2(ConditionalInvertibleLayer):
     def _check_mode(self, what: str) -> None:
         if self.training and self.dropout > 0.0:
             raise NotImplementedError(
-                f"{what} in training mode: conditioner dropout (p={self.dropout}, cnf.py:82-83) and the backward "
-                "pass are not built yet -- call .eval() for NLL evaluation and sampling")
+                f"{what} in training mode would run the conditioner with dropout (p={self.dropout}, cnf.py:82-83); "
+                "only forward() has a training path -- call .eval() before inverse() / sample()")
 
     def features(self, *conditions: torch.Tensor) -> torch.Tensor:
         """Condition features h = feature_network_stack(*conditions) on the model's device."""
@@ -521,8 +521,12 @@ class CondRealNVP_v2(ConditionalInvertibleLayer):
     # -- reference API ------------------------------------------------------------------
     def forward(self, y: torch.Tensor, *conditions: torch.Tensor, log_det_J: bool = False,
                 return_features: bool = False, deterministic_features: bool = False):
-        """cnf.py:467-493.  ``self.log_det_J`` is set as a side effect when ``log_det_J=True``."""
-        self._check_mode("forward")
+        """cnf.py:467-493.  ``self.log_det_J`` is set as a side effect when ``log_det_J=True``.
+
+        In training mode (``model.train()``) the call goes through the differentiable path of
+        ``bcnf_b200/train.py`` (conditioner dropout active, autograd history on z and ``log_det_J``); in
+        eval mode through the fused inference kernels, without autograd history.
+        """
         if deterministic_features:
             self.feature_network_stack.eval()
             condition = self.features(*conditions).detach()
@@ -530,6 +534,12 @@ class CondRealNVP_v2(ConditionalInvertibleLayer):
             condition = self.features(*conditions)
         if condition.shape[0] != y.shape[0]:
             raise ValueError(f"got {y.shape[0]} rows but {condition.shape[0]} condition rows")
+        if self.training:
+            from .train import stack_forward_train
+            z, ld = stack_forward_train(self, y, condition)
+            if log_det_J:
+                self.log_det_J = ld
+            return (z, condition) if return_features else z
         flow = self._flow()
         with torch.no_grad():
             z, ld = flow.run(False, y, flow.project(condition), want_logdet=log_det_J)

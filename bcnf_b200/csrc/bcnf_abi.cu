@@ -15,6 +15,7 @@
 #include "flow_rowthread.cuh"
 #include "flow_tc.cuh"
 #include "flow_tiled.cuh"
+#include "train_ops.cuh"
 
 using namespace bcnf;
 
@@ -752,4 +753,59 @@ extern "C" int bcnf_flow_forward(bcnf_flow_t* f, const float* y, const float* P,
 extern "C" int bcnf_flow_inverse(bcnf_flow_t* f, const float* z, const float* P, const int32_t* row2inst,
                                  int64_t inst_period, int64_t n_rows, float* x, float* logdet, void* stream) {
   return run_flow(f, 1, z, P, row2inst, inst_period, n_rows, x, logdet, stream);
+}
+
+// ----------------------------------------------------------------------------------------------
+// training primitives
+// ----------------------------------------------------------------------------------------------
+static_assert(sizeof(bcnf_gemm_args_t) == sizeof(GemmArgs), "bcnf_gemm_args_t and GemmArgs must match");
+
+extern "C" int bcnf_train_gemm(const bcnf_gemm_args_t* args, int32_t device, void* stream_) {
+  if (!args || !args->A || !args->B || !args->C) return fail(BCNF_E_ARG, "bcnf_train_gemm: null argument");
+  if (args->M < 0 || args->N < 0 || args->K < 0) return fail(BCNF_E_ARG, "bcnf_train_gemm: negative size");
+  if (args->epilogue < 0 || args->epilogue > 3) return fail(BCNF_E_ARG, "bcnf_train_gemm: unknown epilogue %d", args->epilogue);
+  if ((args->epilogue == BCNF_EPI_BIAS || args->epilogue == BCNF_EPI_BIAS_GELU_DROP) && !args->bias)
+    return fail(BCNF_E_ARG, "bcnf_train_gemm: bias missing");
+  if (args->epilogue == BCNF_EPI_BIAS_GELU_DROP && !args->save) return fail(BCNF_E_ARG, "bcnf_train_gemm: save missing");
+  if (args->epilogue == BCNF_EPI_DGELU_DROP && !args->saved) return fail(BCNF_E_ARG, "bcnf_train_gemm: saved missing");
+  if (args->p_drop < 0.f || args->p_drop >= 1.f) return fail(BCNF_E_ARG, "bcnf_train_gemm: p_drop=%f", args->p_drop);
+  if (args->M == 0 || args->N == 0) return BCNF_OK;
+  CUDA_TRY(cudaSetDevice(device));
+  GemmArgs g;
+  memcpy(&g, args, sizeof(g));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  // small problems: 32x32 tiles put more CTAs in flight (a 256-row batch is 4 tiles of 64)
+  const long long ctas64 = (long long)((g.M + 63) / 64) * ((g.N + 63) / 64);
+  if (ctas64 >= 296) {
+    dim3 grid((g.N + 63) / 64, (g.M + 63) / 64);
+    train_gemm_kernel<64, 64><<<grid, 256, 0, stream>>>(g);
+  } else {
+    dim3 grid((g.N + 31) / 32, (g.M + 31) / 32);
+    train_gemm_kernel<32, 32><<<grid, 256, 0, stream>>>(g);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return BCNF_OK;
+}
+
+extern "C" int bcnf_train_colsum(const float* X, int32_t M, int32_t N, int64_t ldx, float* out, float beta,
+                                 int32_t device, void* stream_) {
+  if (!X || !out) return fail(BCNF_E_ARG, "bcnf_train_colsum: null argument");
+  if (M < 0 || N < 0) return fail(BCNF_E_ARG, "bcnf_train_colsum: negative size");
+  if (N == 0) return BCNF_OK;
+  CUDA_TRY(cudaSetDevice(device));
+  colsum_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream_>>>(X, M, N, ldx, out, beta);
+  CUDA_TRY(cudaGetLastError());
+  return BCNF_OK;
+}
+
+extern "C" int bcnf_train_dropout_mask(float* out, int32_t M, int32_t N, uint64_t seed, uint32_t layer_uid, float p_drop,
+                                       int32_t device, void* stream_) {
+  if (!out) return fail(BCNF_E_ARG, "bcnf_train_dropout_mask: null argument");
+  if (M < 0 || N < 0 || p_drop < 0.f || p_drop >= 1.f) return fail(BCNF_E_ARG, "bcnf_train_dropout_mask: bad argument");
+  const long long n = (long long)M * N;
+  if (n == 0) return BCNF_OK;
+  CUDA_TRY(cudaSetDevice(device));
+  dropout_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(out, M, N, seed, layer_uid, p_drop);
+  CUDA_TRY(cudaGetLastError());
+  return BCNF_OK;
 }

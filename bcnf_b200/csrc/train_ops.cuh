@@ -1,0 +1,150 @@
+// Training primitives of the conditioner MLP (fp32): one strided, tiled SGEMM with fused epilogues.
+//
+// The training step of the reference (Trainer._train_batch, src/bcnf/train/trainer.py:244-277) runs the
+// conditioner as nn.Linear -> nn.GELU -> nn.Dropout per hidden layer (cnf.py:78-83) and back-propagates
+// through it with autograd: per Linear one addmm forward, one mm for the data gradient, one mm for the
+// weight gradient, a column sum for the bias gradient, plus separate gelu / dropout kernels.  Here the
+// three GEMMs are one kernel with the surrounding element-wise work fused into its epilogue:
+//
+//   forward        h_l   = drop(gelu(h_{l-1} W_l^T + b_l)),  pre-activation saved       (EPI_BIAS_GELU_DROP)
+//   data gradient  da_{l-1} = (da_l W_l) * gelu'(a_{l-1}) * mask_{l-1} / (1-p)            (EPI_DGELU_DROP)
+//   weight gradient dW_l += da_l^T h_{l-1}                                                (EPI_NONE, beta = 1)
+//
+// Dropout masks are a counter-based hash of (seed, layer id, row, column): regenerated, never stored.
+// Parameters stay in the reference's own layout ((out, in) row-major), so gradients land directly in
+// tensors shaped like the parameters.
+#pragma once
+#include "common.cuh"
+
+namespace bcnf {
+
+enum TrainEpi : int { TEPI_NONE = 0, TEPI_BIAS = 1, TEPI_BIAS_GELU_DROP = 2, TEPI_DGELU_DROP = 3 };
+
+struct GemmArgs {
+  const float* A;  // A(i, r) = A[i*as0 + r*as1]
+  const float* B;  // B(r, j) = B[r*bs0 + j*bs1]
+  float* C;        // C(i, j) = C[i*cs0 + j]
+  int M, N, K;
+  long long as0, as1, bs0, bs1, cs0;
+  float beta;          // C = epi(acc) + beta * C   (beta in {0, 1})
+  int epi;
+  const float* bias;   // [N]
+  float* save;         // TEPI_BIAS_GELU_DROP: pre-activation out, same indexing as C
+  const float* saved;  // TEPI_DGELU_DROP: pre-activation in, same indexing as C
+  unsigned long long seed;
+  unsigned int layer_uid;
+  float p_drop;
+};
+
+// uniform [0,1) from (seed, layer, element): two rounds of a 64-bit mix (splitmix64 finaliser)
+__host__ __device__ __forceinline__ float dropout_uniform(unsigned long long seed, unsigned int layer_uid,
+                                                          unsigned long long elem) {
+  unsigned long long x = seed ^ (0x9E3779B97F4A7C15ull * (unsigned long long)(layer_uid + 1u)) ^ (elem * 0xD1B54A32D192ED03ull);
+  x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+  x ^= x >> 27; x *= 0x94D049BB133111EBull;
+  x ^= x >> 31;
+  return (float)(x >> 40) * (1.0f / 16777216.0f);
+}
+
+__device__ __forceinline__ float dgelu_erf(float x) {
+  // d/dx [0.5 x (1 + erf(x/sqrt2))] = Phi(x) + x phi(x)
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+  return fmaf(x, pdf, cdf);
+}
+
+template <int BM, int BN>
+__global__ void __launch_bounds__(256)
+train_gemm_kernel(const GemmArgs g) {
+  constexpr int BK = 16;
+  constexpr int TM = BM / 16, TN = BN / 16;     // per-thread micro tile (16 x 16 threads)
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int i0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
+  float acc[TM][TN];
+#pragma unroll
+  for (int a = 0; a < TM; ++a)
+#pragma unroll
+    for (int b = 0; b < TN; ++b) acc[a][b] = 0.f;
+
+  const bool a_r_fast = g.as1 == 1;   // r contiguous in A
+  const bool b_j_fast = g.bs1 == 1;   // j contiguous in B
+  for (int k0 = 0; k0 < g.K; k0 += BK) {
+    for (int e = tid; e < BM * BK; e += 256) {
+      int i, r;
+      if (a_r_fast) { i = e / BK; r = e % BK; } else { r = e / BM; i = e % BM; }
+      const int gi = i0 + i, gr = k0 + r;
+      As[r][i] = (gi < g.M && gr < g.K) ? __ldg(g.A + gi * g.as0 + gr * g.as1) : 0.f;
+    }
+    for (int e = tid; e < BN * BK; e += 256) {
+      int j, r;
+      if (b_j_fast) { r = e / BN; j = e % BN; } else { j = e / BK; r = e % BK; }
+      const int gj = j0 + j, gr = k0 + r;
+      Bs[r][j] = (gj < g.N && gr < g.K) ? __ldg(g.B + gr * g.bs0 + gj * g.bs1) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < BK; ++r) {
+      float av[TM], bv[TN];
+#pragma unroll
+      for (int a = 0; a < TM; ++a) av[a] = As[r][ty * TM + a];
+#pragma unroll
+      for (int b = 0; b < TN; ++b) bv[b] = Bs[r][tx * TN + b];
+#pragma unroll
+      for (int a = 0; a < TM; ++a)
+#pragma unroll
+        for (int b = 0; b < TN; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+    }
+    __syncthreads();
+  }
+
+  const float keep_scale = g.p_drop > 0.f ? 1.0f / (1.0f - g.p_drop) : 1.0f;
+#pragma unroll
+  for (int a = 0; a < TM; ++a) {
+    const int i = i0 + ty * TM + a;
+    if (i >= g.M) continue;
+#pragma unroll
+    for (int b = 0; b < TN; ++b) {
+      const int j = j0 + tx * TN + b;
+      if (j >= g.N) continue;
+      const long long idx = i * g.cs0 + j;
+      float v = acc[a][b];
+      if (g.epi == TEPI_BIAS) {
+        v += __ldg(g.bias + j);
+      } else if (g.epi == TEPI_BIAS_GELU_DROP) {
+        v += __ldg(g.bias + j);
+        g.save[idx] = v;
+        v = gelu_erf(v);
+        if (g.p_drop > 0.f)
+          v = dropout_uniform(g.seed, g.layer_uid, (unsigned long long)i * (unsigned)g.N + (unsigned)j) >= g.p_drop
+                  ? v * keep_scale : 0.f;
+      } else if (g.epi == TEPI_DGELU_DROP) {
+        v *= dgelu_erf(__ldg(g.saved + idx));
+        if (g.p_drop > 0.f)
+          v = dropout_uniform(g.seed, g.layer_uid, (unsigned long long)i * (unsigned)g.N + (unsigned)j) >= g.p_drop
+                  ? v * keep_scale : 0.f;
+      }
+      if (g.beta != 0.f) v += g.beta * g.C[idx];
+      g.C[idx] = v;
+    }
+  }
+}
+
+// out[j] = sum_i X[i*ldx + j] (+ beta * out[j]): bias gradients and ActNorm reductions
+__global__ void colsum_kernel(const float* __restrict__ X, int M, int N, long long ldx, float* __restrict__ out, float beta) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  float s = 0.f;
+  for (int i = 0; i < M; ++i) s += X[i * ldx + j];
+  out[j] = beta != 0.f ? fmaf(beta, out[j], s) : s;
+}
+
+__global__ void dropout_mask_kernel(float* __restrict__ out, int M, int N, unsigned long long seed, unsigned int layer_uid, float p) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)M * N) return;
+  const float scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
+  out[e] = (p > 0.f && dropout_uniform(seed, layer_uid, (unsigned long long)e) < p) ? 0.f : scale;
+}
+
+}  // namespace bcnf

@@ -133,6 +133,39 @@ int bcnf_flow_forward(bcnf_flow_t* flow, const float* y, const float* P, const i
 int bcnf_flow_inverse(bcnf_flow_t* flow, const float* z, const float* P, const int32_t* row2inst,
                       int64_t inst_period, int64_t n_rows, float* x, float* logdet, void* stream);
 
+/* ---- training primitives (Trainer._train_batch, src/bcnf/train/trainer.py:244-277) ------------------
+ * The conditioner's Linear -> GELU -> Dropout chain (cnf.py:78-83) forward and backward as one strided
+ * SGEMM with fused epilogues; parameters and gradients stay in the reference's (out, in) layout. */
+typedef enum {
+  BCNF_EPI_NONE = 0,            /* C = A.B (+ beta C)                                        */
+  BCNF_EPI_BIAS = 1,            /* C = A.B + bias[j]                         (last Linear)   */
+  BCNF_EPI_BIAS_GELU_DROP = 2,  /* save = A.B + bias[j]; C = dropout(gelu(save))  (nn.Linear, nn.GELU, nn.Dropout) */
+  BCNF_EPI_DGELU_DROP = 3       /* C = (A.B) * gelu'(saved) * dropout mask        (their autograd backward)        */
+} bcnf_epilogue_t;
+
+typedef struct {
+  const float* A;        /* A(i, r) = A[i*as0 + r*as1] */
+  const float* B;        /* B(r, j) = B[r*bs0 + j*bs1] */
+  float* C;              /* C(i, j) = C[i*cs0 + j]     */
+  int32_t M, N, K;
+  int64_t as0, as1, bs0, bs1, cs0;
+  float beta;            /* 0 or 1 */
+  int32_t epilogue;      /* bcnf_epilogue_t */
+  const float* bias;     /* [N] */
+  float* save;           /* BCNF_EPI_BIAS_GELU_DROP: pre-activations out (indexed like C) */
+  const float* saved;    /* BCNF_EPI_DGELU_DROP: pre-activations in (indexed like C) */
+  uint64_t seed;         /* dropout: mask(i, j) = hash(seed, layer_uid, i*N + j) >= p_drop */
+  uint32_t layer_uid;
+  float p_drop;
+} bcnf_gemm_args_t;
+
+int bcnf_train_gemm(const bcnf_gemm_args_t* args, int32_t device, void* stream);
+/* out[j] = sum_i X[i*ldx + j] + beta*out[j]   (bias gradients: the sum(0) of autograd's Linear backward) */
+int bcnf_train_colsum(const float* X, int32_t M, int32_t N, int64_t ldx, float* out, float beta, int32_t device, void* stream);
+/* the multiplicative dropout mask (0 or 1/(1-p)) the fused epilogues apply, materialised for tests */
+int bcnf_train_dropout_mask(float* out, int32_t M, int32_t N, uint64_t seed, uint32_t layer_uid, float p_drop,
+                            int32_t device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

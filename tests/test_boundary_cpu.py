@@ -104,11 +104,13 @@ def test_cpu_device_has_no_fallback():
         model(torch.randn(2, 19), torch.randn(2, 30, 3))
 
 
-def test_training_mode_is_refused_until_backward_exists():
+def test_training_mode_needs_cuda_too_and_sampling_needs_eval():
     cfg = json.load(open(os.path.join(GOLDEN_DIR, "state_dict_keys.json")))["trajectory_FC_small"]["config"]
-    model = CondRealNVP_v2.from_config(cfg)
-    with pytest.raises(NotImplementedError):
+    model = CondRealNVP_v2.from_config(cfg)          # a fresh module is in training mode
+    with pytest.raises(RuntimeError):                  # CPU parameters: no fallback in the training path either
         model(torch.randn(2, 19), torch.randn(2, 30, 3))
+    with pytest.raises(NotImplementedError):
+        model.sample(3, torch.randn(2, 30, 3), outer=True)
 
 
 def test_load_config_coerces_yaml_numbers(tmp_path):

@@ -1,0 +1,183 @@
+"""Training path (bcnf_b200/train.py + csrc/train_ops.cuh) on the GPU: fused GEMM epilogues vs torch, and
+gradient parity of the whole stack against autograd through the CPU oracle (torch back end).
+
+Gradient tolerance: 2e-5 of max|ref grad| per tensor in fp32 (the reference's own fp32 autograd differs
+from its fp64 evaluation by ~1e-6 of scale; dropout is tested with the masks the kernels generate,
+because no RNG stream can match nn.Dropout's)."""
+import numpy as np
+import pytest
+import torch
+
+import bcnf_b200
+from bcnf_b200 import CondRealNVP_v2, _cabi, train
+from conftest import rel_err
+from oracle import flow_oracle as fo
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _model(size, nested, n_blocks, n_cond, dropout, two_way=False, seed=0):
+    torch.manual_seed(seed)
+    model = CondRealNVP_v2(size=size, nested_sizes=nested, n_blocks=n_blocks, n_conditions=n_cond,
+                           feature_networks=[bcnf_b200.ConcatenateCondition(None, n_cond)], dropout=dropout,
+                           act_norm=True, two_way=two_way)
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for layer in model.layers:
+            if isinstance(layer, bcnf_b200.ActNorm):
+                layer.scale.copy_(0.75 + 0.5 * torch.rand(layer.scale.shape, generator=g))
+                layer.bias.copy_(0.1 * torch.randn(layer.bias.shape, generator=g))
+    return model.to(DEV)
+
+
+def test_fused_gemm_epilogues_match_torch():
+    g = torch.Generator().manual_seed(0)
+    B, K, N = 77, 90, 53
+    x = torch.randn(B, K, generator=g).to(DEV)
+    w = (torch.randn(N, K, generator=g) / 8).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    # forward: bias + gelu + dropout, pre-activation saved
+    pre, out = torch.empty(B, N, device=DEV), torch.empty(B, N, device=DEV)
+    train._gemm(x, (K, 1), w, (1, K), out, B, N, K, epi=_cabi.EPI_BIAS_GELU_DROP, bias=b, save=pre, seed=7, uid=3, p=0.4)
+    mask = train.dropout_mask(B, N, 7, 3, 0.4, DEV)
+    ref_pre = x @ w.t() + b
+    assert torch.allclose(pre, ref_pre, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(out, torch.nn.functional.gelu(ref_pre) * mask, rtol=1e-5, atol=1e-5)
+    keep = (mask > 0).float().mean().item()
+    assert abs(keep - 0.6) < 0.05
+    assert all(v == 0.0 or abs(v - 1 / 0.6) < 1e-6 for v in mask.unique().tolist())
+    # data gradient: (d W) * gelu'(pre) * mask
+    d = torch.randn(B, N, generator=g).to(DEV)
+    pre_in = torch.randn(B, K, generator=g).to(DEV)
+    din = torch.empty(B, K, device=DEV)
+    train._gemm(d, (N, 1), w, (K, 1), din, B, K, N, epi=_cabi.EPI_DGELU_DROP, saved=pre_in, seed=7, uid=9, p=0.4)
+    xg = pre_in.clone().requires_grad_(True)
+    torch.nn.functional.gelu(xg).sum().backward()
+    mask_in = train.dropout_mask(B, K, 7, 9, 0.4, DEV)
+    assert torch.allclose(din, (d @ w) * xg.grad * mask_in, rtol=1e-5, atol=1e-5)
+    # weight gradient and bias gradient
+    dw = torch.empty(N, K, device=DEV)
+    train._gemm(d, (1, N), x, (K, 1), dw, N, K, B)
+    assert torch.allclose(dw, d.t() @ x, rtol=1e-5, atol=1e-4)
+    db = torch.empty(N, device=DEV)
+    train._colsum(d, db)
+    assert torch.allclose(db, d.sum(0), rtol=1e-5, atol=1e-5)
+    # beta = 1 accumulates
+    train._gemm(d, (1, N), x, (K, 1), dw, N, K, B, beta=1.0)
+    assert torch.allclose(dw, 2 * (d.t() @ x), rtol=1e-5, atol=2e-4)
+
+
+@pytest.mark.parametrize("shape", [(19, [16] * 3, 4, 24, False, 64), (21, [40, 40], 3, 12, True, 33),
+                                   (19, [526] * 5, 2, 1360, False, 256)],
+                         ids=["D19_H16", "D21_H40_two_way", "large_conditioner"])
+def test_gradients_match_autograd_through_the_oracle(shape):
+    size, nested, blocks, n_cond, two_way, rows = shape
+    model = _model(size, nested, blocks, n_cond, dropout=0.0, two_way=two_way).train()
+    g = torch.Generator().manual_seed(4)
+    y = torch.randn(rows, size, generator=g)
+    h = torch.randn(rows, n_cond, generator=g)
+    y_d, h_d = y.to(DEV).requires_grad_(True), h.to(DEV).requires_grad_(True)
+    z = model(y_d, h_d, log_det_J=True)
+    loss = bcnf_b200.inn_nll_loss(z, model.log_det_J)
+    loss.backward()
+    # reference: autograd through the oracle (torch back end) on CPU, same parameters
+    sd = {k: v.detach().cpu().clone().requires_grad_(v.dtype.is_floating_point) for k, v in model.state_dict().items()}
+    layers = fo.layers_from_state_dict(sd, convert=lambda v: v)
+    y_r, h_r = y.clone().requires_grad_(True), h.clone().requires_grad_(True)
+    z_r, ld_r = fo.stack_forward(layers, y_r, h_r)
+    loss_r = fo.inn_nll(z_r, ld_r)
+    loss_r.backward()
+    assert abs(loss.item() - loss_r.item()) < 1e-4 * max(1.0, abs(loss_r.item()))
+    assert rel_err(z.detach().cpu().numpy(), z_r.detach().numpy()) < 1e-5
+    assert rel_err(y_d.grad.cpu().numpy(), y_r.grad.numpy()) < 2e-5
+    assert rel_err(h_d.grad.cpu().numpy(), h_r.grad.numpy()) < 2e-5
+    for name, p in model.named_parameters():
+        if not p.requires_grad:
+            assert p.grad is None
+            continue
+        ref = sd[name].grad
+        assert ref is not None, name
+        assert rel_err(p.grad.cpu().numpy(), ref.numpy()) < 2e-5, name
+
+
+def test_dropout_gradients_with_the_kernels_own_masks():
+    size, nested, n_cond, rows, p, seed = 19, [32, 32], 8, 50, 0.35, 1234
+    model = _model(size, nested, 2, n_cond, dropout=p).train()
+    g = torch.Generator().manual_seed(5)
+    y = torch.randn(rows, size, generator=g).to(DEV).requires_grad_(True)
+    h = torch.randn(rows, n_cond, generator=g).to(DEV)
+    z, ld = train.stack_forward_train(model, y, h, seed=seed)
+    (0.5 * (z ** 2).sum(1) - ld).mean().backward()
+    # same computation in plain torch on the GPU with the masks materialised
+    y2 = y.detach().clone().requires_grad_(True)
+    v, ld2 = y2, torch.zeros(rows, device=DEV)
+    params = {n: q.detach().clone().requires_grad_(q.requires_grad) for n, q in model.named_parameters()}
+    da = (size + 1) // 2
+    for li, layer in enumerate(model.layers):
+        pre = f"layers.{li}."
+        if isinstance(layer, bcnf_b200.ActNorm):
+            v = params[pre + "scale"] * v + params[pre + "bias"]
+            ld2 = ld2 + params[pre + "scale"].abs().log().sum()
+        elif isinstance(layer, bcnf_b200.OrthonormalTransformation):
+            v = v @ params[pre + "orthonormal_matrix"]
+        else:
+            u = torch.cat([v[:, :da], h], 1)
+            idx = [int(k.split(".")[-2]) for k in params if k.startswith(pre + "nn_a.nn.") and k.endswith("weight")]
+            for l, j in enumerate(sorted(idx)):
+                u = u @ params[f"{pre}nn_a.nn.{j}.weight"].t() + params[f"{pre}nn_a.nn.{j}.bias"]
+                if l < len(idx) - 1:
+                    u = torch.nn.functional.gelu(u) * train.dropout_mask(rows, u.shape[1], seed, train.layer_uid(li, 0, l), p, DEV)
+            t, ls = u[:, : size - da], torch.tanh(u[:, size - da:])
+            v = torch.cat([v[:, :da], torch.exp(ls) * v[:, da:] + t], 1)
+            ld2 = ld2 + ls.sum(1)
+    (0.5 * (v ** 2).sum(1) - ld2).mean().backward()
+    assert torch.allclose(z, v, rtol=1e-4, atol=1e-5)
+    assert rel_err(y.grad.cpu().numpy(), y2.grad.cpu().numpy()) < 2e-5
+    for n, q in model.named_parameters():
+        if q.requires_grad:
+            assert rel_err(q.grad.cpu().numpy(), params[n].grad.cpu().numpy()) < 2e-5, n
+    # a different seed gives a different mask, the same seed the same result
+    z3, _ = train.stack_forward_train(model, y.detach(), h, seed=seed)
+    z4, _ = train.stack_forward_train(model, y.detach(), h, seed=seed + 1)
+    assert torch.equal(z3, z.detach()) and not torch.equal(z4, z.detach())
+
+
+def test_trainer_step_reduces_the_loss_and_eval_path_sees_the_update():
+    import json, os
+    from conftest import GOLDEN_DIR
+    cfg = json.load(open(os.path.join(GOLDEN_DIR, "state_dict_keys.json")))["trajectory_FC_small"]["config"]
+    torch.manual_seed(0)
+    model = CondRealNVP_v2.from_config(cfg).to(DEV).train()
+    opt = bcnf_b200.OptimizerFactory.get_optimizer("Adam", model.parameters(), {"lr": 2e-4})
+    trainer = bcnf_b200.Trainer(model, opt)
+    g = torch.Generator().manual_seed(1)
+    y = torch.randn(256, 19, generator=g)
+    cond = torch.randn(256, 30, 3, generator=g)
+    model.eval()
+    before = trainer.validate_batch(y, cond)[1]
+    model.train()
+    losses = [trainer.train_batch(y, cond)[0] for _ in range(30)]
+    assert all(np.isfinite(losses))
+    model.eval()
+    after = trainer.validate_batch(y, cond)[1]
+    assert after < before          # 30 Adam steps on one batch lower its NLL; the fused eval kernels saw the new weights
+
+
+def test_ddp_wraps_the_model_single_rank_nccl():
+    import torch.distributed as dist
+    import os, socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device(DEV))
+    try:
+        model = _model(19, [16] * 2, 3, 8, dropout=0.2).train()
+        ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[0])
+        opt = torch.optim.Adam(ddp.parameters(), lr=1e-3)
+        trainer = bcnf_b200.Trainer(ddp, opt)
+        g = torch.Generator().manual_seed(2)
+        out = trainer.train_batch(torch.randn(64, 19, generator=g), torch.randn(64, 8, generator=g))
+        assert all(np.isfinite(out))
+    finally:
+        dist.destroy_process_group()
