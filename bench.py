@@ -39,6 +39,11 @@ WORKLOADS = {
     "fc_small_sample": ("trajectory_FC_small", 500, 10_000, "sample"),
     "fc_small_logprob": ("trajectory_FC_small", 1, 1 << 22, "log_prob"),
     "fc_large_logprob": ("trajectory_FC_large", 1, 1 << 17, "log_prob"),
+    "lstm_large_logprob": ("trajectory_LSTM_large", 1, 1 << 17, "log_prob"),
+    "lstm_large_sample": ("trajectory_LSTM_large", 500, 10_000, "sample"),
+    # BASELINE config 4: training step (forward NLL + backward + Adam), batch 256 per GPU, DDP over N GPUs
+    "trf_large_train": ("trajectory_TRF_large", 1, 256, "train"),
+    "fc_small_train": ("trajectory_FC_small", 1, 256, "train"),
 }
 
 
@@ -161,6 +166,133 @@ def oracle_cpu_rate(cfg: dict, kind: str, samples: int, budget_s: float = 12.0) 
                       f"back end incl. per-row feature network as the reference does"}
 
 
+def oracle_cpu_train_rate(cfg: dict, batch: int, budget_s: float = 15.0) -> dict:
+    """One optimisation step (forward NLL + backward + Adam) of the oracle port on the host cores."""
+    from bcnf_b200 import CondRealNVP_v2
+    from oracle import flow_oracle as fo
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    model = CondRealNVP_v2.from_config(cfg)          # CPU parameter container + PyTorch feature network
+    perturb_actnorm(model)
+    model.train()
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.Adam(params, lr=2e-4)
+    layers = fo.layers_from_state_dict(dict(model.named_parameters()), convert=lambda v: v)
+    g = torch.Generator().manual_seed(3)
+    y = torch.randn(batch, cfg["model"]["kwargs"]["size"], generator=g)
+    cond = torch.randn(batch, 30, 3, generator=g)
+
+    def once():
+        opt.zero_grad()
+        h = model.feature_network_stack(cond)
+        z, ld = fo.stack_forward(layers, y, h)     # eval-mode conditioner (no dropout): a lower bound on the reference's cost
+        fo.inn_nll(z, ld).backward()
+        opt.step()
+
+    once()
+    best, t_end, reps = float("inf"), time.perf_counter() + budget_s, 0
+    while reps < 2 or (time.perf_counter() < t_end and reps < 20):
+        t0 = time.perf_counter(); once(); best = min(best, time.perf_counter() - t0); reps += 1
+    return {"value": batch / best, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"train step batch {batch}, best of {reps}: oracle/flow_oracle.py torch-CPU back end with autograd + Adam "
+                      f"(no dropout kernels, i.e. a lower bound on the reference's step time)"}
+
+
+def main_train(args, cfg, cfg_key, batch, rank, world, local_rank) -> None:
+    """Workload kind 'train': one optimisation step per bench step (Trainer.train_batch)."""
+    import torch.distributed as dist
+    import bcnf_b200
+    mk = cfg["model"]["kwargs"]
+    metric, unit = "training samples/sec", "samples/s"
+    workload_name = f"{cfg_key} training step (forward NLL + backward + Adam), batch {batch} per GPU, dropout on"
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        base = oracle_cpu_train_rate(cfg, batch, budget_s=20.0)
+        print(json.dumps({"impl": "reference", "metric": metric, "value": base["value"], "unit": unit, "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * batch / base["value"],
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic", "config": {"workload": workload_name}, "cpu_baseline": base,
+                          "e2e": {"value": base["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}))
+        return
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    torch.manual_seed(0)
+    model = bcnf_b200.CondRealNVP_v2.from_config(cfg)
+    perturb_actnorm(model)
+    model = model.to(device).train()
+    net = model
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank])
+    opt = torch.optim.Adam(model.parameters(), lr=2e-4)
+    trainer = bcnf_b200.Trainer(model, opt)
+    g = torch.Generator().manual_seed(100 + rank)
+    y_host = torch.randn(batch, mk["size"], generator=g).pin_memory()
+    c_host = torch.randn(batch, 30, 3, generator=g).pin_memory()
+    y_dev, c_dev = y_host.to(device), c_host.to(device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier(); ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record(); barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        trainer.train_batch(y_dev, c_dev)
+    ms_total = timed(lambda: trainer.train_batch(y_dev, c_dev), args.steps)
+    clocks = sampler.stop() if rank == 0 else {}
+    e2e_steps = max(1, min(args.steps, 5))
+    ms_e2e = timed(lambda: trainer.train_batch(y_host, c_host), e2e_steps)
+    value = world * batch * args.steps / (ms_total * 1e-3)
+    n_lin = len(mk["nested_sizes"]) + 1
+    n_coupling = mk["n_blocks"] * (2 if mk.get("two_way") else 1)
+    from oracle.flow_oracle import macs_per_row
+    flops_step = 3 * 2.0 * macs_per_row(mk["size"], mk["nested_sizes"], mk["n_blocks"], mk["n_conditions"], hoisted=False) * batch
+    peaks, peak_src = measured_peaks()
+    achieved = flops_step / (ms_total / args.steps * 1e-3) / 1e12
+    if rank == 0:
+        line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload_name, "size": mk["size"], "nested_sizes": mk["nested_sizes"],
+                           "n_blocks": mk["n_blocks"], "n_conditions": mk["n_conditions"], "kernel": "train_gemm (fp32 FMA)",
+                           "precision": "fp32", "optimizer": "torch.optim.Adam", "l2": "weights (195 MB) exceed nothing; "
+                           "each step touches every parameter, gradient and Adam moment",
+                           "parallelism": f"data parallel over {world} GPU(s), NCCL all-reduce of gradients via DDP"},
+                "e2e": {"value": world * batch * e2e_steps / (ms_e2e * 1e-3), "unit": unit,
+                        "h2d_bytes_per_step": (y_host.numel() + c_host.numel()) * 4, "d2h_bytes_per_step": 12,
+                        "ms_per_step": ms_e2e / e2e_steps},
+                "gpu_launches": args.steps * n_coupling * (3 * n_lin + n_lin),
+                "roofline": {"bound": "tensor", "achieved": achieved, "peak": float(peaks["bf16_tflops"]), "unit": "TFLOP/s",
+                             "frac": achieved / float(peaks["bf16_tflops"]), "traffic": None,
+                             "peak_source": f"{peak_src} bf16 dense", "kernel": "train_gemm_kernel (all launches of the step)",
+                             "note": "fp32 FMA GEMMs; at batch 256 the step is launch- and weight-traffic-bound (SURVEY 8d)"},
+                "clocks": clocks}
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = oracle_cpu_train_rate(cfg, batch)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -181,6 +313,8 @@ def main() -> None:
     cfg_key, m_samples, n_inst_total, kind = WORKLOADS[args.workload]
     cfg = load_run_config(cfg_key)
     mk = cfg["model"]["kwargs"]
+    if kind == "train":
+        return main_train(args, cfg, cfg_key, args.instances_per_step or n_inst_total, rank, world, local_rank)
     unit = "samples/s" if kind == "sample" else "evals/s"
     metric = "posterior samples/sec" if kind == "sample" else "log_prob evals/sec"
     inst_step = args.instances_per_step or (1000 if kind == "sample" else n_inst_total // 8)
