@@ -15,6 +15,7 @@
 #include "flow_rowthread.cuh"
 #include "flow_tc.cuh"
 #include "flow_tiled.cuh"
+#include "proj_tc.cuh"
 #include "train_ops.cuh"
 
 using namespace bcnf;
@@ -113,6 +114,12 @@ struct bcnf_flow {
   TcPackDesc* d_tc_pack = nullptr;
   TcPackDesc* h_tc_pack = nullptr;
   int tc_pack_cap = 0;
+  // tensor-core condition projection
+  ProjTcDims pd;
+  unsigned char* d_proj_blob = nullptr;
+  ProjNet* d_proj_nets = nullptr;
+  std::vector<ProjNet> proj_nets;
+  std::vector<int> proj_net_layer;   // index in op_types of each conditioner network's coupling layer
 };
 
 static const int kRowThreadChunkCap = 20 * 1024;  // bytes per streamed parameter chunk
@@ -221,6 +228,8 @@ extern "C" int bcnf_flow_destroy(bcnf_flow_t* f) {
   for (int d = 0; d < 2; ++d) if (f->d_tc_off[d]) cudaFree(f->d_tc_off[d]);
   if (f->d_tc_pack) cudaFree(f->d_tc_pack);
   if (f->h_tc_pack) cudaFreeHost(f->h_tc_pack);
+  if (f->d_proj_blob) cudaFree(f->d_proj_blob);
+  if (f->d_proj_nets) cudaFree(f->d_proj_nets);
   delete f;
   return BCNF_OK;
 }
@@ -437,6 +446,8 @@ extern "C" int bcnf_flow_create(const bcnf_flow_desc_t* desc, const int32_t* op_
           for (int l = 0; l <= f->td.half[s].L; ++l) n_tiles += f->td.half[s].layer[l].n_chunks * f->td.half[s].layer[l].kc;
         }
     f->tc_blob_bytes = off;
+    // flow tiles + projection tiles (K = C in 64-wide chunks, <= 4 N chunks per conditioner network)
+    n_tiles += f->n_half * 4 * ((sd.C + 63) / 64);
     f->tc_pack_cap = n_tiles;
     bool ok = cudaMalloc(&f->d_tc_blob, off) == cudaSuccess &&
               cudaMalloc(&f->d_tc_pack, (size_t)n_tiles * sizeof(TcPackDesc)) == cudaSuccess &&
@@ -463,6 +474,52 @@ extern "C" int bcnf_flow_create(const bcnf_flow_desc_t* desc, const int32_t* op_
       return fail(BCNF_E_NOMEM, "device allocation of %lld bytes (bf16 weight tiles) failed", off);
     }
     bytes += off;
+    // ---- tensor-core projection: tile streams of the h-columns of every first Linear ----
+    ProjTcDims& pd = f->pd;
+    memset(&pd, 0, sizeof(pd));
+    pd.C = sd.C; pd.PW = sd.PW;
+    const int kc_total = (sd.C + 63) / 64;
+    for (int s = 0; s < 2; ++s) {
+      pd.layer[s] = f->td.half[s].layer[0];
+      pd.layer[s].kc = kc_total;
+      long long b = 0;
+      for (int nc = 0; nc < pd.layer[s].n_chunks; ++nc) b += (long long)4 * (pd.layer[s].chunk_n[nc] / 2) * 128;
+      pd.stream_bytes[s] = b * kc_total;
+    }
+    pd.stage_bytes = f->td.stage_bytes;
+    pd.a_stages = 3;
+    const int a_bytes = pd.a_stages * (f->npass == 3 ? 2 : 1) * kTcATile;
+    pd.off_b = a_bytes;
+    pd.b_stages = std::min(8, (f->max_smem_optin - a_bytes - 2048) / pd.stage_bytes);
+    pd.off_misc = pd.off_b + pd.b_stages * pd.stage_bytes;
+    pd.smem_bytes = pd.off_misc + 2048;
+    long long poff = 0;
+    f->proj_nets.clear(); f->proj_net_layer.clear();
+    {
+      const Program& p0 = f->prog[0];
+      int oi = 0;
+      for (int i = 0; i < n; ++i) {
+        if (f->op_types[i] == BCNF_OP_COUPLING) {
+          for (int s = 0; s < (desc->two_way ? 2 : 1); ++s) {
+            ProjNet pn; pn.stream_off = poff; pn.proj_off = p0.ops[oi + s].proj_off; pn.src = s;
+            f->proj_nets.push_back(pn); f->proj_net_layer.push_back(i);
+            poff += pd.stream_bytes[s];
+          }
+          oi += desc->two_way ? 2 : 1;
+        } else {
+          oi += 1;
+        }
+      }
+    }
+    if (pd.b_stages < 2 || f->proj_nets.empty() ||
+        cudaMalloc(&f->d_proj_blob, poff) != cudaSuccess ||
+        cudaMalloc(&f->d_proj_nets, f->proj_nets.size() * sizeof(ProjNet)) != cudaSuccess) {
+      cudaGetLastError();
+      bcnf_flow_destroy(f);
+      return fail(BCNF_E_NOMEM, "device allocation of %lld bytes (projection weight tiles) failed", poff);
+    }
+    cudaMemcpy(f->d_proj_nets, f->proj_nets.data(), f->proj_nets.size() * sizeof(ProjNet), cudaMemcpyHostToDevice);
+    bytes += poff;
   }
   f->packed_bytes = bytes;
   cudaError_t e = cudaGetLastError();
@@ -595,6 +652,30 @@ extern "C" int bcnf_flow_set_params(bcnf_flow_t* f, const bcnf_op_params_t* ops,
         emit_tc_half(*f, 0, ops[i].w_a, f->tc_off_by_layer[2 * i], tv);
         if (f->desc.two_way) emit_tc_half(*f, 1, ops[i].w_b, f->tc_off_by_layer[2 * i + 1], tv);
       }
+    for (size_t k = 0; k < f->proj_nets.size(); ++k) {
+      const ProjNet& pn = f->proj_nets[k];
+      const int li = f->proj_net_layer[k];
+      const HalfLayout& hl = sd.half[pn.src];
+      const TcLayer& ly = f->pd.layer[pn.src];
+      const float* const* wsrc = pn.src == 0 ? ops[li].w_a : ops[li].w_b;
+      TcPackDesc d{};
+      d.w = wsrc[0];
+      d.pitch = hl.din + sd.C;
+      d.col0 = hl.din;                 // the feature columns of cat([y_half, h]) (cnf.py:101)
+      d.k_valid = sd.C;
+      d.n_valid = hl.h[0];
+      d.out_mode = 0; d.doh = 0;
+      unsigned char* dst = f->d_proj_blob + pn.stream_off;
+      for (int kc = 0; kc < ly.kc; ++kc) {
+        int coff = 0;
+        for (int nc = 0; nc < ly.n_chunks; ++nc) {
+          d.dst = dst; d.chunk_off = coff; d.chunk_n = ly.chunk_n[nc]; d.kc = kc;
+          tv.push_back(d);
+          dst += (size_t)4 * (ly.chunk_n[nc] / 2) * 128;
+          coff += ly.chunk_n[nc];
+        }
+      }
+    }
     if ((int)tv.size() > f->tc_pack_cap) return fail(BCNF_E_STATE, "internal: tile pack table overflow");
     CUDA_TRY(cudaStreamSynchronize(stream));
     memcpy(f->h_tc_pack, tv.data(), tv.size() * sizeof(TcPackDesc));
@@ -613,6 +694,33 @@ extern "C" int bcnf_cond_project(bcnf_flow_t* f, const float* h, int64_t n_inst,
   if (n_inst == 0) return BCNF_OK;
   cudaStream_t stream = (cudaStream_t)stream_;
   CUDA_TRY(cudaSetDevice(f->desc.device));
+  if (f->npass && !getenv("BCNF_PROJ_FMA")) {
+    // tensor-core projection (same arithmetic mode as the flow kernel of this handle)
+    auto launch = [&](auto kern) -> int {
+      static thread_local size_t configured = 0;
+      const size_t smem = (size_t)f->pd.smem_bytes;
+      if (configured < smem) { if (int rc = opt_in_smem(kern, smem)) return rc; configured = smem; }
+      const long long n_mt = (n_inst + 2 * kTcRows - 1) / (2 * kTcRows);
+      const long long items = n_mt * (long long)f->proj_nets.size();
+      const int clusters = (int)std::min<long long>(items, f->num_sms / 2);
+      cudaLaunchConfig_t cfg{};
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(kTcThreads);
+      cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+      const float* bp = f->d_bproj;
+      const unsigned char* blob = f->d_proj_blob;
+      const ProjNet* nets = f->d_proj_nets;
+      const int n_nets = (int)f->proj_nets.size();
+      const long long ni = n_inst;
+      const ProjTcDims pd = f->pd;
+      CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, h, P, bp, blob, nets, n_nets, ni, pd));
+      return BCNF_OK;
+    };
+    return f->npass == 3 ? launch(proj_tc_kernel<3>) : launch(proj_tc_kernel<1>);
+  }
   const int N = f->sd.PW, K = f->sd.C;
   const long long max_rows = 65535LL * kProjBM;
   for (long long m0 = 0; m0 < n_inst; m0 += max_rows) {

@@ -119,6 +119,37 @@ def test_cluster_multicast_sizes_agree(cluster, precision, monkeypatch):
         assert torch.equal(xc, ref_model.inverse(z2, h))
 
 
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("shape", [(19, [526] * 2, 3, 1360, False, 300), (21, [175, 175], 2, 107, True, 129),
+                                   (19, [64], 1, 8, False, 5)], ids=["large", "two_way_odd", "tiny"])
+def test_tensorcore_projection_matches_torch(shape, precision, monkeypatch):
+    # P = h . W1h^T + b1 for every conditioner network (cnf.py:101-104, feature columns of the first Linear)
+    size, nested, blocks, n_cond, two_way, n_inst = shape
+    model = _model(size, nested, blocks, n_cond, precision, two_way)
+    flow = model._flow()
+    g = torch.Generator().manual_seed(31)
+    h = torch.randn(n_inst, n_cond, generator=g).to(DEV)
+    P = flow.project(h)
+    monkeypatch.setenv("BCNF_PROJ_FMA", "1")
+    P_fma = flow.project(h)                      # the fp32 FMA projection kernel of the same handle
+    hp = -(-nested[0] // 16) * 16
+    col, da = 0, (size + 1) // 2
+    for layer in model.layers:
+        if not isinstance(layer, bcnf_b200.ConditionalAffineCouplingLayer):
+            continue
+        for net, din in ([(layer.nn_a, da), (layer.nn_b, size - da)] if two_way else [(layer.nn_a, da)]):
+            lin = net.linears()[0]
+            ref = h.double() @ lin.weight.double()[:, din:].t() + lin.bias.double()
+            got = P[:, col: col + nested[0]].double()
+            scale = ref.abs().max().item()
+            tol = 1e-5 if precision == "bf16x3" else 1e-2
+            assert (got - ref).abs().max().item() < tol * scale
+            assert (P_fma[:, col: col + nested[0]].double() - ref).abs().max().item() < 1e-5 * scale
+            assert torch.all(P[:, col + nested[0]: col + hp] == 0)     # padding columns stay exactly zero
+            col += hp
+    assert col == flow.proj_width
+
+
 def test_auto_precision_picks_the_kernel_family():
     assert _model(19, [16] * 3, 2, 8, "auto")._flow().kernel == "rowthread"
     assert _model(19, [128] * 3, 2, 8, "auto")._flow().kernel == "tcgen05"
