@@ -697,9 +697,8 @@ extern "C" int bcnf_cond_project(bcnf_flow_t* f, const float* h, int64_t n_inst,
   if (f->npass && !getenv("BCNF_PROJ_FMA")) {
     // tensor-core projection (same arithmetic mode as the flow kernel of this handle)
     auto launch = [&](auto kern) -> int {
-      static thread_local size_t configured = 0;
       const size_t smem = (size_t)f->pd.smem_bytes;
-      if (configured < smem) { if (int rc = opt_in_smem(kern, smem)) return rc; configured = smem; }
+      if (int rc = opt_in_smem(kern, smem)) return rc;   // both instantiations share this lambda's type: no caching
       const long long n_mt = (n_inst + 2 * kTcRows - 1) / (2 * kTcRows);
       const long long items = n_mt * (long long)f->proj_nets.size();
       const int clusters = (int)std::min<long long>(items, f->num_sms / 2);
