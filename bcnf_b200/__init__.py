@@ -6,6 +6,7 @@ from .factories import FeatureNetworkFactory, OptimizerFactory, SchedulerFactory
 from .feature_network import (ConcatenateCondition, FeatureNetwork, FeatureNetworkStack,  # noqa: F401
                               FrExpFeatureNetwork, FullyConnectedFeatureNetwork, LSTMFeatureNetwork,
                               Transformer)
+from .calibration import compute_CDF_residuals, compute_y_hat_ranks  # noqa: F401
 from .train import Trainer  # noqa: F401
 from .utils import ParameterIndexMapping, inn_nll_loss, load_config  # noqa: F401
 

