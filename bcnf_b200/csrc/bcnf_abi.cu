@@ -243,7 +243,7 @@ static void tc_set_chunks(TcLayer& ly) {
   for (int i = 0, left = ly.np; i < n; ++i) { ly.chunk_n[i] = std::min(base, left); left -= ly.chunk_n[i]; }
 }
 
-static void tc_build_half(TcHalfLayout& tl, const HalfLayout& hl) {
+static void tc_build_half(TcHalfLayout& tl, const HalfLayout& hl, int kw) {
   memset(&tl, 0, sizeof(tl));
   tl.L = hl.L;
   tl.doh = round_up(hl.dout, 8);
@@ -251,14 +251,14 @@ static void tc_build_half(TcHalfLayout& tl, const HalfLayout& hl) {
     TcLayer& ly = tl.layer[l];
     const int k_real = l == 0 ? hl.din : hl.h[l - 1];
     ly.np = l == hl.L ? 2 * tl.doh : hl.hp[l];
-    ly.kc = (k_real + 63) / 64;
-    ly.last_ksteps = (k_real - 64 * (ly.kc - 1) + 15) / 16;
+    ly.kc = (k_real + kw - 1) / kw;
+    ly.last_ksteps = (k_real - kw * (ly.kc - 1) + 15) / 16;
     tc_set_chunks(ly);
   }
   long long bytes = 0;
   for (int l = 0; l <= hl.L; ++l)
     for (int nc = 0; nc < tl.layer[l].n_chunks; ++nc)
-      bytes += (long long)tl.layer[l].kc * 4 * (tl.layer[l].chunk_n[nc] / 2) * 128;
+      bytes += (long long)tl.layer[l].kc * 4 * (tl.layer[l].chunk_n[nc] / 2) * (2 * kw);
   tl.stream_bytes = bytes;
 }
 
@@ -268,6 +268,13 @@ static const char* tc_plan(bcnf_flow& f, int npass) {
   TcDims& td = f.td;
   memset(&td, 0, sizeof(td));
   int a_chunks = 1, max_half_rows = 8, max_doh = 8;
+  // Weight tile width: 64 columns (SWIZZLE_128B) by default.  32-column tiles (SWIZZLE_64B, BCNF_TC_KW=32) halve the
+  // stage size so that every issuing warp is double-buffered in the 3-pass mode; measured on B200 (r01) they are
+  // not faster (2.65 vs 2.76 M samples/s on FC_large): the MMA phase is bound by shared-memory bandwidth (operand
+  // reads of the MMAs + TMA stage writes ~ 2.0 MB per layer per SM at ~64 B/clk), not by staging depth.
+  const char* kw_env = getenv("BCNF_TC_KW");
+  td.kw = kw_env ? atoi(kw_env) : 64;
+  if (td.kw != 32 && td.kw != 64) td.kw = 64;
   for (int s = 0; s < 2; ++s) {
     const HalfLayout& hl = sd.half[s];
     if (hl.din > 64) return "own-half width > 64";
@@ -275,16 +282,16 @@ static const char* tc_plan(bcnf_flow& f, int npass) {
       if (hl.h[l] < 48) return "hidden width < 48: the row-per-thread / tiled FMA kernels are the better fit";
       if (hl.hp[l] > 1024) return "hidden width > 1024";
     }
-    tc_build_half(td.half[s], hl);
+    tc_build_half(td.half[s], hl, td.kw);
     for (int l = 0; l <= hl.L; ++l) {
       const TcLayer& ly = td.half[s].layer[l];
-      if (l >= 1) a_chunks = std::max(a_chunks, ly.kc);
+      if (l >= 1) a_chunks = std::max(a_chunks, (hl.h[l - 1] + 63) / 64);
       for (int nc = 0; nc < ly.n_chunks; ++nc) max_half_rows = std::max(max_half_rows, ly.chunk_n[nc] / 2);
     }
     max_doh = std::max(max_doh, td.half[s].doh);
   }
   td.a_chunks = a_chunks;
-  td.stage_bytes = max_half_rows * 128 * (npass == 3 ? 2 : 1);
+  td.stage_bytes = round_up(max_half_rows * 2 * td.kw * (npass == 3 ? 2 : 1), 1024);
   td.off_alo = npass == 3 ? a_chunks * kTcATile : 0;
   td.off_stage = (npass == 3 ? 2 : 1) * a_chunks * kTcATile;
   td.yp = sd.DP;
@@ -297,6 +304,8 @@ static const char* tc_plan(bcnf_flow& f, int npass) {
   td.off_ts = td.off_y + round_up(kTcRows * td.yp * 4, 16);
   td.off_misc = td.off_ts + round_up(kTcRows * td.tsp * 4, 16);
   td.smem_bytes = td.off_misc + 2048;
+  td.n_halfops = f.n_half;
+  td.two_way = f.desc.two_way ? 1 : 0;
   return nullptr;
 }
 
@@ -477,16 +486,21 @@ extern "C" int bcnf_flow_create(const bcnf_flow_desc_t* desc, const int32_t* op_
     // ---- tensor-core projection: tile streams of the h-columns of every first Linear ----
     ProjTcDims& pd = f->pd;
     memset(&pd, 0, sizeof(pd));
-    pd.C = sd.C; pd.PW = sd.PW;
+    pd.C = sd.C; pd.PW = sd.PW; pd.two_way = desc->two_way ? 1 : 0;
     const int kc_total = (sd.C + 63) / 64;
     for (int s = 0; s < 2; ++s) {
-      pd.layer[s] = f->td.half[s].layer[0];
+      pd.layer[s] = f->td.half[s].layer[0];      // N chunking of the first Linear; K = C in 64-wide tiles
       pd.layer[s].kc = kc_total;
       long long b = 0;
       for (int nc = 0; nc < pd.layer[s].n_chunks; ++nc) b += (long long)4 * (pd.layer[s].chunk_n[nc] / 2) * 128;
       pd.stream_bytes[s] = b * kc_total;
     }
-    pd.stage_bytes = f->td.stage_bytes;
+    {
+      int mhr = 8;
+      for (int s = 0; s < 2; ++s)
+        for (int nc = 0; nc < pd.layer[s].n_chunks; ++nc) mhr = std::max(mhr, pd.layer[s].chunk_n[nc] / 2);
+      pd.stage_bytes = mhr * 128 * (f->npass == 3 ? 2 : 1);
+    }
     pd.a_stages = 3;
     const int a_bytes = pd.a_stages * (f->npass == 3 ? 2 : 1) * kTcATile;
     pd.off_b = a_bytes;
@@ -585,9 +599,9 @@ static void emit_tc_half(const bcnf_flow& f, int s, const float* const* w, long 
     for (int kc = 0; kc < ly.kc; ++kc) {          // K-major stream order, as the kernel consumes it
       int coff = 0;
       for (int nc = 0; nc < ly.n_chunks; ++nc) {
-        d.dst = dst; d.chunk_off = coff; d.chunk_n = ly.chunk_n[nc]; d.kc = kc;
+        d.dst = dst; d.chunk_off = coff; d.chunk_n = ly.chunk_n[nc]; d.kc = kc; d.kw = f.td.kw;
         v.push_back(d);
-        dst += (size_t)4 * (ly.chunk_n[nc] / 2) * 128;
+        dst += (size_t)4 * (ly.chunk_n[nc] / 2) * (2 * f.td.kw);
         coff += ly.chunk_n[nc];
       }
     }
@@ -669,7 +683,7 @@ extern "C" int bcnf_flow_set_params(bcnf_flow_t* f, const bcnf_op_params_t* ops,
       for (int kc = 0; kc < ly.kc; ++kc) {
         int coff = 0;
         for (int nc = 0; nc < ly.n_chunks; ++nc) {
-          d.dst = dst; d.chunk_off = coff; d.chunk_n = ly.chunk_n[nc]; d.kc = kc;
+          d.dst = dst; d.chunk_off = coff; d.chunk_n = ly.chunk_n[nc]; d.kc = kc; d.kw = 64;
           tv.push_back(d);
           dst += (size_t)4 * (ly.chunk_n[nc] / 2) * 128;
           coff += ly.chunk_n[nc];

@@ -46,8 +46,8 @@ struct TcLayer {
   int np;            // padded N (multiple of 16)
   int n_chunks;      // N is processed in chunks of <= 256 columns
   int chunk_n[4];
-  int kc;            // number of 64-wide K chunks
-  int last_ksteps;   // K=16 steps that carry data in the last chunk (1..4)
+  int kc;            // number of K chunks of the WEIGHT tiles (TcDims::kw columns each)
+  int last_ksteps;   // K=16 steps that carry data in the last chunk (1..kw/16)
 };
 
 struct TcHalfLayout {
@@ -59,12 +59,17 @@ struct TcHalfLayout {
 
 struct TcDims {
   TcHalfLayout half[2];
+  int kw;              // K columns per weight tile: 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B: half-size stages, so the
+                       // 3-pass mode can double-buffer every issuing warp within the same shared memory)
   int a_chunks;        // 64-column activation tiles per part
   int stage_bytes;     // bytes of one weight stage (hi [+ lo] of the largest half tile)
   int n_stages;
   int off_alo, off_stage, off_y, off_ts, off_misc;   // shared-memory carve-up (bytes)
   int yp, tsp;         // pitches (floats) of y_s and ts_s
   int smem_bytes;
+  int n_halfops;       // conditioner networks per pass over the stack (same in both directions)
+  int two_way;         // their nn_a / nn_b pattern: a,b,a,b,... (two_way) or a,a,a,... -- kept in the kernel
+                       // parameters so that the MMA issuers never depend on values loaded from global memory
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
@@ -108,6 +113,16 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset
   d |= (uint64_t)1 << 46;                 // descriptor version (sm_100)
   d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ uint64_t make_smem_desc_b(uint32_t saddr, int kw) {
+  // weight tiles: 128-byte rows / SWIZZLE_128B (kw = 64) or 64-byte rows / SWIZZLE_64B (kw = 32)
+  if (kw == 64) return make_smem_desc(saddr);
+  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;        // 8 rows x 64 bytes
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;                 // SWIZZLE_64B
   return d;
 }
 __device__ __forceinline__ uint32_t make_idesc(int n) {
@@ -202,7 +217,10 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
   float* ld_s = reinterpret_cast<float*>(tmem_ptr_s + 2);            // [64]
   const float** prow_s = reinterpret_cast<const float**>(ld_s + kTcRows);   // [64]
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // warp index and TMEM base as lane-0 broadcasts: provably warp-uniform, so ptxas keeps the MMA operands in
+  // uniform registers instead of wrapping every tcgen05.mma in a uniformisation loop (tools/mma_probe.cu:
+  // 139 -> 106 cycles per issue)
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const uint32_t cta = cluster_ctarank();         // rank in the cluster
   const uint32_t csize = cluster_nctarank();
   const uint32_t n_pairs = csize >> 1, pair = cta >> 1, prank = cta & 1u, lead_rank = cta & ~1u;
@@ -232,7 +250,7 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
   __syncthreads();
   cluster_sync_all();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_s;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_s, 0);
 
   if (warp == 0) {
     // ===================== weight producer (each CTA streams its half of every tile) =====================
@@ -249,7 +267,7 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
             // K-major tile order: (kc, nc); issuer nc consumes every n_chunks-th tile
             for (int kc = 0; kc < ly.kc; ++kc) {
               for (int nc = 0; nc < ly.n_chunks; ++nc, ++it) {
-                const uint32_t rows_b = (uint32_t)(ly.chunk_n[nc] >> 1) * 128u;
+                const uint32_t rows_b = (uint32_t)(ly.chunk_n[nc] >> 1) * (uint32_t)(2 * td.kw);
                 const int s = it % n_stages;
                 const uint32_t use = it / n_stages;
                 if (use > 0) mbar_wait_cluster(&w_empty[s], (use - 1) & 1);
@@ -296,10 +314,8 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
       int s = 0;            // ring position of the next tile of the stream (all chunks)
       uint32_t par = 0;
       for (long long iter = 0; iter < n_iter; ++iter)
-        for (int oi = 0; oi < a.n_ops; ++oi) {
-          const DevOp op = a.ops[oi];
-          if (op.type != DOP_HALF) continue;
-          const TcHalfLayout& hl = td.half[op.src];
+        for (int hi = 0; hi < td.n_halfops; ++hi) {
+          const TcHalfLayout& hl = td.half[td.two_way ? (hi & 1) : 0];
           for (int l = 0; l <= hl.L; ++l) {
             const TcLayer& ly = hl.layer[l];
             const int nch = ly.n_chunks;
@@ -318,7 +334,8 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
             for (int c = 0; c < j; ++c) col += (uint32_t)(ly.chunk_n[c] >> 1);
             const int cn = ly.chunk_n[j];
             const uint32_t idesc = make_idesc(cn);
-            const uint32_t rows_b = (uint32_t)(cn >> 1) * 128u;
+            const uint32_t rows_b = (uint32_t)(cn >> 1) * (uint32_t)(2 * td.kw);
+            const int steps_per_tile = td.kw >> 4;
             for (int kc = 0; kc < ly.kc; ++kc) {
               // my tile of this K step sits j positions further in the ring
               int sj = s + j; uint32_t pj = par;
@@ -327,11 +344,12 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
               mbar_wait_cluster(&w_peer[sj], pj);
               tc_fence_after();
               if (tr && kc == 0) a.trace[(a_cnt - 1) * 8 + 1] = clock64();
-              const int ksteps = kc == ly.kc - 1 ? ly.last_ksteps : 4;
-              const uint64_t ah = make_smem_desc(a_hi_addr + kc * kTcATile);
-              const uint64_t al = make_smem_desc(a_lo_addr + kc * kTcATile);
-              const uint64_t wh = make_smem_desc(st_addr + sj * td.stage_bytes);
-              const uint64_t wl = make_smem_desc(st_addr + sj * td.stage_bytes + rows_b);
+              const int ksteps = kc == ly.kc - 1 ? ly.last_ksteps : steps_per_tile;
+              const int g0 = kc * steps_per_tile;                 // first K=16 step of this weight tile
+              const uint64_t ah = make_smem_desc(a_hi_addr + (g0 >> 2) * kTcATile) + 2 * (g0 & 3);
+              const uint64_t al = make_smem_desc(a_lo_addr + (g0 >> 2) * kTcATile) + 2 * (g0 & 3);
+              const uint64_t wh = make_smem_desc_b(st_addr + sj * td.stage_bytes, td.kw);
+              const uint64_t wl = make_smem_desc_b(st_addr + sj * td.stage_bytes + rows_b, td.kw);
               for (int k = 0; k < ksteps; ++k) {
                 const uint32_t first = (kc | k) == 0 ? 0u : 1u;
                 umma_2sm(tmem_base + col, ah + 2 * k, wh + 2 * k, idesc, first);
@@ -405,7 +423,7 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
         // ---- input of the first Linear: own half of y, zero padded to the K=16 steps in use ----
         if (et < kTcRows) {
           const float* yr = y_s + et * td.yp + in0;
-          const int kcols = tl.layer[0].last_ksteps * 16;
+          const int kcols = ((hl.din + 15) >> 4) << 4;
           for (int n0 = 0; n0 < kcols; n0 += 8) {
             float v[8];
 #pragma unroll
@@ -542,15 +560,17 @@ struct TcPackDesc {
   int out_mode;         // 1: last Linear, rows [0,dout) -> n in [0,doh), rows [dout,2dout) -> n in [doh, 2doh)
   int doh;
   int chunk_off, chunk_n, kc;
-  int pad;
+  int kw;               // K columns per tile: 64 or 32
 };
 
 __global__ void tc_pack_kernel(const TcPackDesc* __restrict__ descs) {
   const TcPackDesc d = descs[blockIdx.x];
   const int half_rows = d.chunk_n >> 1;
-  const uint32_t rows_b = (uint32_t)half_rows * 128u;
-  for (int e = threadIdx.x; e < d.chunk_n * 8; e += blockDim.x) {
-    const int nl_all = e >> 3, c16 = e & 7;
+  const int row_bytes = 2 * d.kw;                 // 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
+  const int cpr = d.kw >> 3;                      // 16-byte chunks per row
+  const uint32_t rows_b = (uint32_t)half_rows * (uint32_t)row_bytes;
+  for (int e = threadIdx.x; e < d.chunk_n * cpr; e += blockDim.x) {
+    const int nl_all = e / cpr, c16 = e - nl_all * cpr;
     const int r = nl_all / half_rows, nl = nl_all - r * half_rows;
     const int n = d.chunk_off + nl_all;
     int src_row = -1;
@@ -563,14 +583,16 @@ __global__ void tc_pack_kernel(const TcPackDesc* __restrict__ descs) {
       float v[2];
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
-        const int k = d.kc * 64 + c16 * 8 + p * 2 + t;
+        const int k = d.kc * d.kw + c16 * 8 + p * 2 + t;
         v[t] = (src_row >= 0 && k < d.k_valid) ? d.w[(size_t)src_row * d.pitch + d.col0 + k] : 0.f;
       }
       const float h0 = __bfloat162float(__float2bfloat16_rn(v[0])), h1 = __bfloat162float(__float2bfloat16_rn(v[1]));
       hi[p] = pack_bf16x2(h0, h1);
       lo[p] = pack_bf16x2(v[0] - h0, v[1] - h1);
     }
-    unsigned char* base = d.dst + (size_t)r * 2u * rows_b + (size_t)nl * 128 + ((c16 ^ (nl & 7)) << 4);
+    // hardware swizzle: 16-byte chunk index XOR row-in-atom (128B mode: row & 7; 64B mode: (row >> 1) & 3)
+    const int sw = d.kw == 64 ? (nl & 7) : ((nl >> 1) & 3);
+    unsigned char* base = d.dst + (size_t)r * 2u * rows_b + (size_t)nl * row_bytes + ((c16 ^ sw) << 4);
     *reinterpret_cast<uint4*>(base) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(base + rows_b) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }

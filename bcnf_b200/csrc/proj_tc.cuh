@@ -25,6 +25,7 @@ struct ProjTcDims {
   int off_b, off_misc, smem_bytes;
   int C;                   // number of condition features (K)
   int PW;
+  int two_way;             // networks alternate nn_a, nn_b (else all nn_a): lets the issuers stay on kernel parameters
 };
 
 struct ProjNet {           // one conditioner network of the stack
@@ -52,7 +53,10 @@ proj_tc_kernel(const float* __restrict__ h, float* __restrict__ P, const float* 
   uint64_t* tmem_free = acc_full + 4;                     // [1] leader, count 2
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tmem_free + 1);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // warp index and TMEM base as lane-0 broadcasts: provably warp-uniform, so ptxas keeps the MMA operands in
+  // uniform registers instead of wrapping every tcgen05.mma in a uniformisation loop (tools/mma_probe.cu:
+  // 139 -> 106 cycles per issue)
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const uint32_t cta = cluster_ctarank();
   const bool leader = cta == 0;
   const int nbs = pd.b_stages, nas = pd.a_stages;
@@ -76,7 +80,7 @@ proj_tc_kernel(const float* __restrict__ h, float* __restrict__ P, const float* 
   __syncthreads();
   cluster_sync_all();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_s;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_s, 0);
 
   if (warp == 0) {
     // ===================== W1h tile producer =====================
@@ -119,8 +123,7 @@ proj_tc_kernel(const float* __restrict__ h, float* __restrict__ P, const float* 
       int s = 0; uint32_t par = 0;           // B ring position of the next K step's first tile
       uint32_t a_it = 0, item_cnt = 0;
       for (long long item = cluster_id; item < n_items; item += n_clusters, ++item_cnt) {
-        const ProjNet net = nets[item / n_mt];
-        const TcLayer& ly = pd.layer[net.src];
+        const TcLayer& ly = pd.layer[pd.two_way ? (int)((item / n_mt) & 1) : 0];
         const int nch = ly.n_chunks;
         if (item_cnt > 0) mbar_wait_cluster(tmem_free, (item_cnt - 1) & 1);   // previous item's accumulators drained
         tc_fence_after();
