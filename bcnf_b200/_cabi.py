@@ -53,7 +53,7 @@ class GemmArgs(C.Structure):
                 ("K", C.c_int32), ("as0", C.c_int64), ("as1", C.c_int64), ("bs0", C.c_int64), ("bs1", C.c_int64),
                 ("cs0", C.c_int64), ("beta", C.c_float), ("epilogue", C.c_int32), ("bias", C.c_void_p),
                 ("save", C.c_void_p), ("saved", C.c_void_p), ("seed", C.c_uint64), ("layer_uid", C.c_uint32),
-                ("p_drop", C.c_float)]
+                ("p_drop", C.c_float), ("seed_ptr", C.c_void_p)]
 
 
 def nvcc_command(out_path: str = LIB_PATH) -> list[str]:
@@ -106,7 +106,7 @@ def lib() -> C.CDLL:
     L.bcnf_train_gemm.argtypes = [C.POINTER(GemmArgs), C.c_int32, C.c_void_p]
     L.bcnf_train_colsum.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_float, C.c_int32, C.c_void_p]
     L.bcnf_train_dropout_mask.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_uint64, C.c_uint32, C.c_float,
-                                          C.c_int32, C.c_void_p]
+                                          C.c_void_p, C.c_int32, C.c_void_p]
     for name in EXPORTS:
         if name not in ("bcnf_last_error",):
             getattr(L, name).restype = C.c_int if name != "bcnf_last_error" else C.c_char_p

@@ -920,13 +920,14 @@ extern "C" int bcnf_train_colsum(const float* X, int32_t M, int32_t N, int64_t l
 }
 
 extern "C" int bcnf_train_dropout_mask(float* out, int32_t M, int32_t N, uint64_t seed, uint32_t layer_uid, float p_drop,
-                                       int32_t device, void* stream_) {
+                                       const uint64_t* seed_ptr, int32_t device, void* stream_) {
   if (!out) return fail(BCNF_E_ARG, "bcnf_train_dropout_mask: null argument");
   if (M < 0 || N < 0 || p_drop < 0.f || p_drop >= 1.f) return fail(BCNF_E_ARG, "bcnf_train_dropout_mask: bad argument");
   const long long n = (long long)M * N;
   if (n == 0) return BCNF_OK;
   CUDA_TRY(cudaSetDevice(device));
-  dropout_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(out, M, N, seed, layer_uid, p_drop);
+  dropout_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(out, M, N, seed, layer_uid, p_drop,
+                                                                                            (const unsigned long long*)seed_ptr);
   CUDA_TRY(cudaGetLastError());
   return BCNF_OK;
 }

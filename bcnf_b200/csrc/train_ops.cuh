@@ -34,6 +34,7 @@ struct GemmArgs {
   unsigned long long seed;
   unsigned int layer_uid;
   float p_drop;
+  const unsigned long long* seed_ptr;   // optional device-resident seed word, XORed into `seed` (CUDA-graph replays)
 };
 
 // uniform [0,1) from (seed, layer, element): two rounds of a 64-bit mix (splitmix64 finaliser)
@@ -56,12 +57,14 @@ __device__ __forceinline__ float dgelu_erf(float x) {
 template <int BM, int BN>
 __global__ void __launch_bounds__(256)
 train_gemm_kernel(const GemmArgs g) {
-  constexpr int BK = 16;
+  constexpr int BK = 32;
   constexpr int TM = BM / 16, TN = BN / 16;     // per-thread micro tile (16 x 16 threads)
-  __shared__ float As[BK][BM + 4];
-  __shared__ float Bs[BK][BN + 4];
+  constexpr int LA = BM * BK / 256, LB = BN * BK / 256;   // global loads per thread and tile
+  __shared__ float As[2][BK][BM + 4];
+  __shared__ float Bs[2][BK][BN + 4];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int i0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
+  const unsigned long long seed = g.seed_ptr ? (g.seed ^ *g.seed_ptr) : g.seed;
   float acc[TM][TN];
 #pragma unroll
   for (int a = 0; a < TM; ++a)
@@ -70,33 +73,67 @@ train_gemm_kernel(const GemmArgs g) {
 
   const bool a_r_fast = g.as1 == 1;   // r contiguous in A
   const bool b_j_fast = g.bs1 == 1;   // j contiguous in B
-  for (int k0 = 0; k0 < g.K; k0 += BK) {
-    for (int e = tid; e < BM * BK; e += 256) {
+  float ra[LA], rb[LB];
+  auto load_tile = [&](int k0) {
+#pragma unroll
+    for (int t = 0; t < LA; ++t) {
+      const int e = tid + t * 256;
       int i, r;
       if (a_r_fast) { i = e / BK; r = e % BK; } else { r = e / BM; i = e % BM; }
       const int gi = i0 + i, gr = k0 + r;
-      As[r][i] = (gi < g.M && gr < g.K) ? __ldg(g.A + gi * g.as0 + gr * g.as1) : 0.f;
+      ra[t] = (gi < g.M && gr < g.K) ? __ldg(g.A + gi * g.as0 + gr * g.as1) : 0.f;
     }
-    for (int e = tid; e < BN * BK; e += 256) {
+#pragma unroll
+    for (int t = 0; t < LB; ++t) {
+      const int e = tid + t * 256;
       int j, r;
       if (b_j_fast) { r = e / BN; j = e % BN; } else { j = e / BK; r = e % BK; }
       const int gj = j0 + j, gr = k0 + r;
-      Bs[r][j] = (gj < g.N && gr < g.K) ? __ldg(g.B + gr * g.bs0 + gj * g.bs1) : 0.f;
+      rb[t] = (gj < g.N && gr < g.K) ? __ldg(g.B + gr * g.bs0 + gj * g.bs1) : 0.f;
     }
-    __syncthreads();
+  };
+  auto store_tile = [&](int buf) {
+#pragma unroll
+    for (int t = 0; t < LA; ++t) {
+      const int e = tid + t * 256;
+      int i, r;
+      if (a_r_fast) { i = e / BK; r = e % BK; } else { r = e / BM; i = e % BM; }
+      As[buf][r][i] = ra[t];
+    }
+#pragma unroll
+    for (int t = 0; t < LB; ++t) {
+      const int e = tid + t * 256;
+      int j, r;
+      if (b_j_fast) { r = e / BN; j = e % BN; } else { j = e / BK; r = e % BK; }
+      Bs[buf][r][j] = rb[t];
+    }
+  };
+
+  // double-buffered K loop: the global loads of tile k+1 are in flight while tile k is multiplied
+  load_tile(0);
+  store_tile(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < g.K; k0 += BK) {
+    const bool more = k0 + BK < g.K;
+    if (more) load_tile(k0 + BK);
 #pragma unroll
     for (int r = 0; r < BK; ++r) {
       float av[TM], bv[TN];
 #pragma unroll
-      for (int a = 0; a < TM; ++a) av[a] = As[r][ty * TM + a];
+      for (int a = 0; a < TM; ++a) av[a] = As[buf][r][ty * TM + a];
 #pragma unroll
-      for (int b = 0; b < TN; ++b) bv[b] = Bs[r][tx * TN + b];
+      for (int b = 0; b < TN; ++b) bv[b] = Bs[buf][r][tx * TN + b];
 #pragma unroll
       for (int a = 0; a < TM; ++a)
 #pragma unroll
         for (int b = 0; b < TN; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
     }
-    __syncthreads();
+    if (more) {
+      store_tile(buf ^ 1);     // the other buffer was last read one iteration ago, before the previous barrier
+      __syncthreads();
+      buf ^= 1;
+    }
   }
 
   const float keep_scale = g.p_drop > 0.f ? 1.0f / (1.0f - g.p_drop) : 1.0f;
@@ -117,12 +154,12 @@ train_gemm_kernel(const GemmArgs g) {
         g.save[idx] = v;
         v = gelu_erf(v);
         if (g.p_drop > 0.f)
-          v = dropout_uniform(g.seed, g.layer_uid, (unsigned long long)i * (unsigned)g.N + (unsigned)j) >= g.p_drop
+          v = dropout_uniform(seed, g.layer_uid, (unsigned long long)i * (unsigned)g.N + (unsigned)j) >= g.p_drop
                   ? v * keep_scale : 0.f;
       } else if (g.epi == TEPI_DGELU_DROP) {
         v *= dgelu_erf(__ldg(g.saved + idx));
         if (g.p_drop > 0.f)
-          v = dropout_uniform(g.seed, g.layer_uid, (unsigned long long)i * (unsigned)g.N + (unsigned)j) >= g.p_drop
+          v = dropout_uniform(seed, g.layer_uid, (unsigned long long)i * (unsigned)g.N + (unsigned)j) >= g.p_drop
                   ? v * keep_scale : 0.f;
       }
       if (g.beta != 0.f) v += g.beta * g.C[idx];
@@ -140,7 +177,9 @@ __global__ void colsum_kernel(const float* __restrict__ X, int M, int N, long lo
   out[j] = beta != 0.f ? fmaf(beta, out[j], s) : s;
 }
 
-__global__ void dropout_mask_kernel(float* __restrict__ out, int M, int N, unsigned long long seed, unsigned int layer_uid, float p) {
+__global__ void dropout_mask_kernel(float* __restrict__ out, int M, int N, unsigned long long seed, unsigned int layer_uid, float p,
+                                    const unsigned long long* __restrict__ seed_ptr) {
+  if (seed_ptr) seed ^= *seed_ptr;
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (long long)M * N) return;
   const float scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;

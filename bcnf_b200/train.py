@@ -30,7 +30,7 @@ def _stream(dev: torch.device) -> int:
 
 
 def _gemm(A, a_strides, B, b_strides, Cm, M, N, K, *, beta=0.0, epi=_cabi.EPI_NONE, bias=None, save=None,
-          saved=None, seed=0, uid=0, p=0.0) -> None:
+          saved=None, seed=0, uid=0, p=0.0, seed_ptr=None) -> None:
     g = _cabi.GemmArgs()
     g.A, g.B, g.C = A.data_ptr(), B.data_ptr(), Cm.data_ptr()
     g.M, g.N, g.K = M, N, K
@@ -42,6 +42,7 @@ def _gemm(A, a_strides, B, b_strides, Cm, M, N, K, *, beta=0.0, epi=_cabi.EPI_NO
     g.save = save.data_ptr() if save is not None else None
     g.saved = saved.data_ptr() if saved is not None else None
     g.seed, g.layer_uid, g.p_drop = seed, uid, p
+    g.seed_ptr = seed_ptr
     dev = Cm.device
     _cabi.check(_cabi.lib().bcnf_train_gemm(C.byref(g), dev.index or 0, _stream(dev)), "bcnf_train_gemm")
 
@@ -52,11 +53,13 @@ def _colsum(X: torch.Tensor, out: torch.Tensor) -> None:
                                               dev.index or 0, _stream(dev)), "bcnf_train_colsum")
 
 
-def dropout_mask(rows: int, cols: int, seed: int, uid: int, p: float, device: Any) -> torch.Tensor:
+def dropout_mask(rows: int, cols: int, seed: int, uid: int, p: float, device: Any,
+                 seed_word: torch.Tensor | None = None) -> torch.Tensor:
     """The multiplicative mask (0 or 1/(1-p)) the fused epilogues apply for (seed, uid) -- for tests."""
     dev = torch.device(device)
     out = torch.empty(rows, cols, device=dev)
-    _cabi.check(_cabi.lib().bcnf_train_dropout_mask(out.data_ptr(), rows, cols, seed, uid, p, dev.index or 0, _stream(dev)),
+    sp = seed_word.data_ptr() if seed_word is not None else None
+    _cabi.check(_cabi.lib().bcnf_train_dropout_mask(out.data_ptr(), rows, cols, seed, uid, p, sp, dev.index or 0, _stream(dev)),
                 "bcnf_train_dropout_mask")
     return out
 
@@ -70,9 +73,11 @@ class _Spec:
     """Static description of the stack handed to the autograd function (not a tensor)."""
 
     def __init__(self, kinds: list[str], n_lin: int, two_way: bool, size: int, n_conditions: int, p_drop: float,
-                 seed: int) -> None:
+                 seed: int, seed_word: torch.Tensor | None = None) -> None:
         self.kinds, self.n_lin, self.two_way = kinds, n_lin, two_way
         self.size, self.n_conditions, self.p_drop, self.seed = size, n_conditions, p_drop, seed
+        self.seed_word = seed_word          # device int64 word XORed into the seed by the kernels (CUDA-graph replays)
+        self.seed_ptr = seed_word.data_ptr() if seed_word is not None else None
 
 
 def _mlp_forward(u: torch.Tensor, ws: Sequence[torch.Tensor], bs: Sequence[torch.Tensor], spec: _Spec, li: int,
@@ -87,7 +92,7 @@ def _mlp_forward(u: torch.Tensor, ws: Sequence[torch.Tensor], bs: Sequence[torch
         x = acts[-1]
         # out = dropout(gelu(x W^T + b)): nn.Linear, nn.GELU, nn.Dropout (cnf.py:79-83)
         _gemm(x, (x.stride(0), 1), ws[l], (1, ws[l].stride(0)), out, B, n_out, n_in, epi=_cabi.EPI_BIAS_GELU_DROP,
-              bias=bs[l], save=pre, seed=spec.seed, uid=layer_uid(li, net, l), p=spec.p_drop)
+              bias=bs[l], save=pre, seed=spec.seed, uid=layer_uid(li, net, l), p=spec.p_drop, seed_ptr=spec.seed_ptr)
         pres.append(pre)
         acts.append(out)
     n_out, n_in = ws[-1].shape
@@ -115,7 +120,8 @@ def _mlp_backward(do: torch.Tensor, ws, bs, acts, pres, spec: _Spec, li: int, ne
         d_in = torch.empty(B, n_in, device=do.device)
         if l > 0:
             _gemm(d_out, (d_out.stride(0), 1), ws[l], (ws[l].stride(0), 1), d_in, B, n_in, n_out,
-                  epi=_cabi.EPI_DGELU_DROP, saved=pres[l - 1], seed=spec.seed, uid=layer_uid(li, net, l - 1), p=spec.p_drop)
+                  epi=_cabi.EPI_DGELU_DROP, saved=pres[l - 1], seed=spec.seed, uid=layer_uid(li, net, l - 1), p=spec.p_drop,
+                  seed_ptr=spec.seed_ptr)
         else:
             _gemm(d_out, (d_out.stride(0), 1), ws[l], (ws[l].stride(0), 1), d_in, B, n_in, n_out)
         d_out = d_in
@@ -219,8 +225,13 @@ class _StackFn(torch.autograd.Function):
         return (None, dz if needs[1] else None, dh if needs[2] else None, *out_params)
 
 
-def stack_forward_train(model: Any, y: torch.Tensor, h: torch.Tensor, seed: int | None = None):
-    """Training-mode forward of ``model.layers``: returns (z, log|det J|), both with autograd history."""
+def stack_forward_train(model: Any, y: torch.Tensor, h: torch.Tensor, seed: int | None = None,
+                        seed_word: torch.Tensor | None = None):
+    """Training-mode forward of ``model.layers``: returns (z, log|det J|), both with autograd history.
+
+    ``seed_word``: optional device int64 tensor whose value is XORed into the dropout seed inside the kernels;
+    a CUDA-graph-captured step bumps it on the device so that every replay draws fresh masks.
+    """
     from .cnf import ActNorm, ConditionalAffineCouplingLayer, OrthonormalTransformation
     kinds, params = [], []
     n_lin = len(model.nested_sizes) + 1
@@ -238,10 +249,13 @@ def stack_forward_train(model: Any, y: torch.Tensor, h: torch.Tensor, seed: int 
                 params += [m.weight for m in lin] + [m.bias for m in lin]
         else:
             raise ValueError(f"Layer must be an instance of ConditionalInvertibleLayer or InvertibleLayer, but got {type(layer)}")
+    if seed_word is None:
+        seed_word = getattr(model, "_dropout_seed_word", None)
     if seed is None:
-        seed = int(torch.randint(0, 2 ** 62, (1,)).item())    # consumes the CPU generator, like nn.Dropout would
+        # eager mode consumes the CPU generator, like nn.Dropout would; under graph capture the base seed is fixed
+        seed = 0x5EED if seed_word is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
     p = float(model.dropout) if model.training else 0.0
-    spec = _Spec(kinds, n_lin, model.two_way, model.size, model.n_conditions, p, seed)
+    spec = _Spec(kinds, n_lin, model.two_way, model.size, model.n_conditions, p, seed, seed_word)
     dev = torch.device(model.device)
     if dev.type != "cuda":
         raise RuntimeError(f"bcnf_b200 runs on CUDA devices only (got {dev}); there is no CPU path. "
@@ -261,33 +275,88 @@ class Trainer:
     ``train_batch`` = zero_grad -> forward(log_det_J, return_features) -> [hybrid MSE head] -> NLL ->
     backward -> optimizer.step -> clip_grad_norm_ (after the step, as the reference does: it never
     affects an update, trainer.py:273-275).  Returns Python floats like the reference (3 syncs).
+
+    ``cuda_graph=True`` captures zero_grad + forward + backward + optimizer.step of one batch shape into a CUDA
+    graph and replays it (the step is launch-bound at the reference's batch size of 256); it needs a
+    capturable optimizer (``torch.optim.Adam(..., capturable=True)``) and a single process (no DDP).
     """
 
-    def __init__(self, model: Any, optimizer: torch.optim.Optimizer, hybrid_weight: float = 0.0) -> None:
+    def __init__(self, model: Any, optimizer: torch.optim.Optimizer, hybrid_weight: float = 0.0,
+                 cuda_graph: bool = False) -> None:
         from .utils import inn_nll_loss
         self.model, self.optimizer, self.hybrid_weight = model, optimizer, hybrid_weight
         self.loss_function = inn_nll_loss
         self.mse_loss = torch.nn.MSELoss()
+        self.cuda_graph = cuda_graph
+        self._graph: Any = None
+        self._static: Any = None
+        if cuda_graph:
+            if hasattr(model, "module"):
+                raise NotImplementedError("cuda_graph=True with DistributedDataParallel is not supported")
+            if not all(g.get("capturable", False) for g in optimizer.param_groups):
+                raise ValueError("cuda_graph=True needs a capturable optimizer, e.g. torch.optim.Adam(..., capturable=True)")
+
+    def _net(self) -> Any:
+        return self.model.module if hasattr(self.model, "module") else self.model
 
     def _losses(self, y: torch.Tensor, *conditions: torch.Tensor):
-        net = self.model.module if hasattr(self.model, "module") else self.model
+        net = self._net()
         dev = net.device
         z, h = self.model(y.to(dev), *[c.to(dev) for c in conditions], log_det_J=True, return_features=True)
         if self.hybrid_weight > 0:
             mse = self.mse_loss(net.prediction_head(h), y.to(dev))
         else:
-            mse = torch.tensor(0.0)
+            mse = torch.zeros((), device=z.device)
         nll = self.loss_function(z, net.log_det_J)
         loss = (nll + mse * self.hybrid_weight) / (1 + self.hybrid_weight)
         return loss, nll, mse, z
 
+    def _graphed_step(self, y: torch.Tensor, *conditions: torch.Tensor):
+        net = self._net()
+        dev = torch.device(net.device)
+        shapes = (tuple(y.shape),) + tuple(tuple(c.shape) for c in conditions)
+        if self._graph is None or self._static["shapes"] != shapes:
+            net._dropout_seed_word = torch.zeros(1, dtype=torch.int64, device=dev)
+            st = {"shapes": shapes, "y": torch.empty_like(y, device=dev),
+                  "c": [torch.empty_like(c, device=dev) for c in conditions]}
+            st["y"].copy_(y)
+            for d, c in zip(st["c"], conditions):
+                d.copy_(c)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):              # warm-up off the capture stream (allocator, lazy inits)
+                for _ in range(3):
+                    self.optimizer.zero_grad(set_to_none=True)
+                    loss, _, _, _ = self._losses(st["y"], *st["c"])
+                    loss.backward()
+                    self.optimizer.step()
+                    net._dropout_seed_word.add_(1)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            self.optimizer.zero_grad(set_to_none=True)
+            with torch.cuda.graph(graph):
+                loss, nll, mse, _ = self._losses(st["y"], *st["c"])
+                loss.backward()
+                self.optimizer.step()
+                net._dropout_seed_word.add_(1)          # fresh dropout masks on every replay
+            st.update(loss=loss, nll=nll, mse=mse)
+            self._graph, self._static = graph, st
+        st = self._static
+        st["y"].copy_(y, non_blocking=True)
+        for d, c in zip(st["c"], conditions):
+            d.copy_(c, non_blocking=True)
+        self._graph.replay()
+        return st["loss"], st["nll"], st["mse"]
+
     def train_batch(self, y: torch.Tensor, *conditions: torch.Tensor) -> tuple[float, float, float]:
+        if self.cuda_graph:
+            loss, nll, mse = self._graphed_step(y, *conditions)
+            return loss.item(), nll.item(), mse.item()
         self.optimizer.zero_grad()
         loss, nll, mse, _ = self._losses(y, *conditions)
         loss.backward()
         self.optimizer.step()
-        net = self.model.module if hasattr(self.model, "module") else self.model
-        torch.nn.utils.clip_grad_norm_(net.parameters(), max_norm=1.0)
+        torch.nn.utils.clip_grad_norm_(self._net().parameters(), max_norm=1.0)
         return loss.item(), nll.item(), mse.item()
 
     def validate_batch(self, y: torch.Tensor, *conditions: torch.Tensor):

@@ -157,6 +157,7 @@ typedef struct {
   uint64_t seed;         /* dropout: mask(i, j) = hash(seed, layer_uid, i*N + j) >= p_drop */
   uint32_t layer_uid;
   float p_drop;
+  const uint64_t* seed_ptr;  /* optional DEVICE word XORed into seed: lets a captured CUDA graph draw new masks per replay */
 } bcnf_gemm_args_t;
 
 int bcnf_train_gemm(const bcnf_gemm_args_t* args, int32_t device, void* stream);
@@ -164,7 +165,7 @@ int bcnf_train_gemm(const bcnf_gemm_args_t* args, int32_t device, void* stream);
 int bcnf_train_colsum(const float* X, int32_t M, int32_t N, int64_t ldx, float* out, float beta, int32_t device, void* stream);
 /* the multiplicative dropout mask (0 or 1/(1-p)) the fused epilogues apply, materialised for tests */
 int bcnf_train_dropout_mask(float* out, int32_t M, int32_t N, uint64_t seed, uint32_t layer_uid, float p_drop,
-                            int32_t device, void* stream);
+                            const uint64_t* seed_ptr, int32_t device, void* stream);
 
 #ifdef __cplusplus
 }

@@ -181,3 +181,17 @@ def test_ddp_wraps_the_model_single_rank_nccl():
         assert all(np.isfinite(out))
     finally:
         dist.destroy_process_group()
+
+
+def test_cuda_graph_trainer_matches_eager_statistics():
+    # the captured step (zero_grad + forward + backward + Adam) replays with fresh dropout masks and learns
+    model = _model(19, [32, 32], 3, 8, dropout=0.3).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True)
+    trainer = bcnf_b200.Trainer(model, opt, cuda_graph=True)
+    g = torch.Generator().manual_seed(9)
+    y, c = torch.randn(128, 19, generator=g), torch.randn(128, 8, generator=g)
+    losses = [trainer.train_batch(y, c)[0] for _ in range(40)]
+    assert all(np.isfinite(losses)) and np.mean(losses[-5:]) < np.mean(losses[:5])
+    assert len({round(l, 6) for l in losses[:6]}) > 1          # replays are not identical: masks and weights change
+    with pytest.raises(ValueError):
+        bcnf_b200.Trainer(model, torch.optim.Adam(model.parameters(), lr=1e-3), cuda_graph=True)
