@@ -87,14 +87,18 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // default semantics (.release.cta), as CUTLASS' ClusterBarrier::arrive(cta_id): the data the arrival
+  // announces lives in the arriving CTA's own shared memory and is only ever read there (by its half of
+  // the 2-CTA MMA), after this thread's fence.proxy.async + CTA barrier; a cluster-scope release costs a
+  // few thousand cycles per hand-off (measured) and orders nothing more that matters here
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "WAITC_%=:\n"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
       "@p bra DONEC_%=;\n"
       "bra WAITC_%=;\n"
       "DONEC_%=:\n"
