@@ -92,6 +92,60 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return fmaf(hx, erf_v, hx);
 }
 
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2 process two fp32 lanes per instruction) ----------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// gelu_erf_fast on two values at once: the Horner chain, the products and the final fma run packed
+// (about 10.5 instructions per value instead of 17).  Same polynomial, same results bit for bit.
+__device__ __forceinline__ f32x2 gelu_erf_fast2(f32x2 x) {
+  float x0, x1;
+  unpack2(x, x0, x1);
+  const float t0 = fminf(fabsf(x0) * 0.70710678118654752440f, 4.0f);
+  const float t1 = fminf(fabsf(x1) * 0.70710678118654752440f, 4.0f);
+  const f32x2 t = pack2(t0, t1);
+  f32x2 p = pack2(-7.638800192e-07f, -7.638800192e-07f);
+  p = fma2(p, t, pack2(1.656447655e-05f, 1.656447655e-05f));
+  p = fma2(p, t, pack2(-1.540620985e-04f, -1.540620985e-04f));
+  p = fma2(p, t, pack2(7.796742463e-04f, 7.796742463e-04f));
+  p = fma2(p, t, pack2(-2.041655680e-03f, -2.041655680e-03f));
+  p = fma2(p, t, pack2(-2.589820766e-04f, -2.589820766e-04f));
+  p = fma2(p, t, pack2(2.797563118e-02f, 2.797563118e-02f));
+  p = fma2(p, t, pack2(-1.483925716e-01f, -1.483925716e-01f));
+  p = fma2(p, t, pack2(-9.184330629e-01f, -9.184330629e-01f));
+  p = fma2(p, t, pack2(-1.627907331e+00f, -1.627907331e+00f));
+  float a0, a1;
+  unpack2(mul2(p, t), a0, a1);
+  float e0, e1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+  const f32x2 erf_v = pack2(copysignf(1.0f - e0, x0), copysignf(1.0f - e1, x1));
+  const f32x2 hx = mul2(x, pack2(0.5f, 0.5f));
+  return fma2(hx, erf_v, hx);
+}
+
 // Launch arguments common to the flow kernels.
 struct FlowArgs {
   const float* in;        // (n_rows, D)

@@ -106,6 +106,15 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
       "r"(parity)
       : "memory");
 }
+// spin on test_wait (no hardware suspend): lowest wake-up latency, for the single hot hand-off per layer
+__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiThreads) : "memory"); }
@@ -201,6 +210,35 @@ __device__ __forceinline__ void store_act8(unsigned char* a_hi, unsigned char* a
 // Launched with a cluster of CS = 2, 4 or 8 CTAs = CS/2 CTA pairs.  Each pair owns its own 128-row tile;
 // the pairs of a cluster walk the same weight stream in lockstep, and every weight half-tile is fetched
 // from L2 once per cluster and multicast to the same-rank CTA of every pair.
+// (+ add) -> GELU -> bf16 hi/lo split of 8 accumulator columns, packed two values per instruction, stored as
+// one 16-byte chunk per part into the swizzled activation tiles
+template <int NPASS>
+__device__ __forceinline__ void gelu_store8(unsigned char* a_hi, unsigned char* a_lo, int row, int n0,
+                                            const uint32_t (&r)[8], const float4& b0, const float4& b1) {
+  const int tile = n0 >> 6, c16 = (n0 & 63) >> 3;
+  const int off = tile * kTcATile + row * 128 + ((c16 ^ (row & 7)) << 4);
+  f32x2 v[4];
+  v[0] = gelu_erf_fast2(add2(pack2(__uint_as_float(r[0]), __uint_as_float(r[1])), pack2(b0.x, b0.y)));
+  v[1] = gelu_erf_fast2(add2(pack2(__uint_as_float(r[2]), __uint_as_float(r[3])), pack2(b0.z, b0.w)));
+  v[2] = gelu_erf_fast2(add2(pack2(__uint_as_float(r[4]), __uint_as_float(r[5])), pack2(b1.x, b1.y)));
+  v[3] = gelu_erf_fast2(add2(pack2(__uint_as_float(r[6]), __uint_as_float(r[7])), pack2(b1.z, b1.w)));
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float x0, x1;
+    unpack2(v[i], x0, x1);
+    hi[i] = pack_bf16x2(x0, x1);                                        // cvt.rn.bf16x2.f32
+    if (NPASS == 3) {
+      const f32x2 h = pack2(__uint_as_float(hi[i] << 16), __uint_as_float(hi[i] & 0xffff0000u));
+      float l0, l1;
+      unpack2(add2(v[i], h ^ 0x8000000080000000ull), l0, l1);           // v - hi, both lanes
+      lo[i] = pack_bf16x2(l0, l1);
+    }
+  }
+  *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  if (NPASS == 3) *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
 template <int NPASS>
 __global__ void __launch_bounds__(kTcThreads, 1)
 flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsigned char* __restrict__ tc_blob,
@@ -324,7 +362,7 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
             const TcLayer& ly = hl.layer[l];
             const int nch = ly.n_chunks;
             // every issuer observes every phase of a_ready (a parity wait must not skip phases)
-            mbar_wait_cluster(a_ready, a_cnt & 1);    // activations of layer l written by both CTAs
+            mbar_spin(a_ready, a_cnt & 1);            // activations of layer l written by both CTAs
             ++a_cnt;
             tc_fence_after();
             if (j >= nch) {                    // not my layer: only keep the ring position in step
@@ -334,6 +372,7 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
             }
             const bool tr = a.trace && j == 0 && blockIdx.x == 0 && iter == 0 && a_cnt <= 32;
             if (tr) a.trace[(a_cnt - 1) * 8 + 0] = clock64();
+            if (tr) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); a.trace[(a_cnt - 1) * 8 + 6] = (long long)gt; }
             uint32_t col = 0;
             for (int c = 0; c < j; ++c) col += (uint32_t)(ly.chunk_n[c] >> 1);
             const int cn = ly.chunk_n[j];
@@ -448,7 +487,7 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
           ++acc_cnt;
           tc_fence_after();
           const bool tr = a.trace && blockIdx.x == 0 && iter == 0 && acc_cnt <= 32 && et == 0;
-          if (tr) a.trace[(acc_cnt - 1) * 8 + 3] = clock64();
+          const long long t_acc = tr ? clock64() : 0;
           const float* add = l == 0 ? prow_s[row] + op.proj_off : w + hl.off_b[l];
           uint32_t col = 0;
           int coff = 0;
@@ -472,29 +511,23 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
               tmem_ld8_issue(lane_addr + col + g * 8, r0);
               if (two) tmem_ld8_issue(lane_addr + col + g * 8 + 8, r1);
               tmem_ld_wait();
-              float v[8];
-              v[0] = gelu_erf_fast(__uint_as_float(r0[0]) + b[0].x); v[1] = gelu_erf_fast(__uint_as_float(r0[1]) + b[0].y);
-              v[2] = gelu_erf_fast(__uint_as_float(r0[2]) + b[0].z); v[3] = gelu_erf_fast(__uint_as_float(r0[3]) + b[0].w);
-              v[4] = gelu_erf_fast(__uint_as_float(r0[4]) + b[1].x); v[5] = gelu_erf_fast(__uint_as_float(r0[5]) + b[1].y);
-              v[6] = gelu_erf_fast(__uint_as_float(r0[6]) + b[1].z); v[7] = gelu_erf_fast(__uint_as_float(r0[7]) + b[1].w);
-              store_act8<NPASS>(a_hi, a_lo, row, n0, v);
-              if (two) {
-                v[0] = gelu_erf_fast(__uint_as_float(r1[0]) + b[2].x); v[1] = gelu_erf_fast(__uint_as_float(r1[1]) + b[2].y);
-                v[2] = gelu_erf_fast(__uint_as_float(r1[2]) + b[2].z); v[3] = gelu_erf_fast(__uint_as_float(r1[3]) + b[2].w);
-                v[4] = gelu_erf_fast(__uint_as_float(r1[4]) + b[3].x); v[5] = gelu_erf_fast(__uint_as_float(r1[5]) + b[3].y);
-                v[6] = gelu_erf_fast(__uint_as_float(r1[6]) + b[3].z); v[7] = gelu_erf_fast(__uint_as_float(r1[7]) + b[3].w);
-                store_act8<NPASS>(a_hi, a_lo, row, n0 + 8, v);
-              }
+              gelu_store8<NPASS>(a_hi, a_lo, row, n0, r0, b[0], b[1]);
+              if (two) gelu_store8<NPASS>(a_hi, a_lo, row, n0 + 8, r1, b[2], b[3]);
             }
             col += (uint32_t)(cn >> 1);
             coff += cn;
           }
-          if (tr) a.trace[(acc_cnt - 1) * 8 + 4] = clock64();
+          const long long t_own = tr ? clock64() : 0;
           tc_fence_before();
           fence_proxy_async();
           epi_bar_sync();
-          if (tr) a.trace[(acc_cnt - 1) * 8 + 5] = clock64();
+          const long long t_bar = tr ? clock64() : 0;
           if (et == 0) mbar_arrive_remote(a_ready_leader);
+          if (tr) {   // stamps are written after the arrival so that the trace's global stores do not delay its release
+            a.trace[(acc_cnt - 1) * 8 + 3] = t_acc;
+            a.trace[(acc_cnt - 1) * 8 + 4] = t_own;
+            a.trace[(acc_cnt - 1) * 8 + 5] = t_bar;
+          }
         }
 
         // ---- last Linear: (t | s) from TMEM, then the affine update on the row-owner threads ----

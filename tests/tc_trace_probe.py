@@ -23,7 +23,3 @@ for i in range(8):
     nxt = t[i+1,0]
     print(i, int(r[1]-r[0]), int(r[2]-r[1]), int(r[3]-r[2]), int(r[4]-r[3]), int(r[5]-r[4]), int(nxt-r[5]), " | layer period", int(nxt-r[0]))
 
-print("tile | wait_full | wait_peer | issue+commit | gap to next tile start")
-for i in range(27):
-    r = t[32+i]; nx = t[33+i,0] if i < 26 else r[3]
-    print(i, int(r[1]-r[0]), int(r[2]-r[1]), int(r[3]-r[2]), int(nx-r[3]))
