@@ -304,6 +304,16 @@ static const char* tc_plan(bcnf_flow& f, int npass) {
   td.off_ts = td.off_y + round_up(kTcRows * td.yp * 4, 16);
   td.off_misc = td.off_ts + round_up(kTcRows * td.tsp * 4, 16);
   td.smem_bytes = td.off_misc + 2048;
+  {
+    int max_half_cols = 8;
+    for (int s2 = 0; s2 < 2; ++s2)
+      for (int l = 0; l <= td.half[s2].L; ++l)
+        for (int nc = 0; nc < td.half[s2].layer[l].n_chunks; ++nc)
+          max_half_cols = std::max(max_half_cols, td.half[s2].layer[l].chunk_n[nc] / 2);
+    td.region_cols = max_half_cols;
+    td.regions = std::min(8, 512 / max_half_cols);
+    if (td.regions < 4) return "accumulator slots do not fit in TMEM";     // every layer has <= 4 N chunks
+  }
   td.n_halfops = f.n_half;
   td.two_way = f.desc.two_way ? 1 : 0;
   return nullptr;

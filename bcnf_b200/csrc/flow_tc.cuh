@@ -67,6 +67,9 @@ struct TcDims {
   int off_alo, off_stage, off_y, off_ts, off_misc;   // shared-memory carve-up (bytes)
   int yp, tsp;         // pitches (floats) of y_s and ts_s
   int smem_bytes;
+  int regions;         // TMEM is cut into `regions` slots of `region_cols` columns; the accumulator of N chunk c of the
+  int region_cols;     // i-th layer executed lives in slot (sum of chunks of earlier layers + c) mod regions, so that
+                       // the next layer's MMAs can start while this layer's accumulators are still being drained
   int n_halfops;       // conditioner networks per pass over the stack (same in both directions)
   int two_way;         // their nn_a / nn_b pattern: a,b,a,b,... (two_way) or a,a,a,... -- kept in the kernel
                        // parameters so that the MMA issuers never depend on values loaded from global memory
@@ -254,8 +257,9 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
   uint64_t* w_peer = w_full + 8;                                     // [8] leader only
   uint64_t* w_empty = w_peer + 8;                                    // [8]
   uint64_t* acc_full = w_empty + 8;                                  // [4] one per N chunk / issuer
-  uint64_t* a_ready = acc_full + 4;                                  // [1] leader only
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(a_ready + 1);
+  uint64_t* a_ready = acc_full + 4;                                  // [1] leader only: input of a first Linear written
+  uint64_t* a_chunk = a_ready + 1;                                   // [4] leader only: N chunk c of a hidden layer's output written
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(a_chunk + 4);
   float* ld_s = reinterpret_cast<float*>(tmem_ptr_s + 2);            // [64]
   const float** prow_s = reinterpret_cast<const float**>(ld_s + kTcRows);   // [64]
 
@@ -282,6 +286,7 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
     for (int s = 0; s < n_stages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_peer[s], 1); mbar_init(&w_empty[s], (int)n_pairs); }
     for (int j = 0; j < kTcIssuers; ++j) mbar_init(&acc_full[j], 1);
     mbar_init(a_ready, 2);
+    for (int j = 0; j < kTcIssuers; ++j) mbar_init(&a_chunk[j], 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -352,61 +357,89 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
       // descriptors; chunks write disjoint TMEM columns, so their relative order does not matter.
       const int j = warp - 1;
       const uint32_t a_hi_addr = smem_u32(a_hi), a_lo_addr = smem_u32(a_lo), st_addr = smem_u32(stage0);
-      uint32_t a_cnt = 0;
+      // Hand-offs from the epilogue: `a_ready` once per conditioner network (input of its first Linear), and
+      // `a_chunk[c]` once per hidden layer and N chunk c of its output.  Each barrier completes at most once
+      // between two waits of every issuer (the next completion needs this layer's MMAs), so parities never alias.
+      uint32_t xin_use = 0, chunk_use[kTcIssuers] = {0, 0, 0, 0}, lay_cnt = 0;
       int s = 0;            // ring position of the next tile of the stream (all chunks)
       uint32_t par = 0;
+      uint32_t reg0 = 0;    // TMEM slot of chunk 0 of the current layer
       for (long long iter = 0; iter < n_iter; ++iter)
         for (int hi = 0; hi < td.n_halfops; ++hi) {
           const TcHalfLayout& hl = td.half[td.two_way ? (hi & 1) : 0];
+          int n_prev = 1;                // hand-offs that make up the input of the current layer (1 for the first Linear)
           for (int l = 0; l <= hl.L; ++l) {
             const TcLayer& ly = hl.layer[l];
             const int nch = ly.n_chunks;
-            // every issuer observes every phase of a_ready (a parity wait must not skip phases)
-            mbar_spin(a_ready, a_cnt & 1);            // activations of layer l written by both CTAs
-            ++a_cnt;
-            tc_fence_after();
-            if (j >= nch) {                    // not my layer: only keep the ring position in step
+            ++lay_cnt;
+            int got = 0;                       // hand-offs of this layer's input consumed so far
+            auto wait_inputs = [&](int target) {
+              while (got < target) {
+                if (l == 0) { mbar_wait(a_ready, xin_use & 1); ++xin_use; }
+                else { mbar_wait(&a_chunk[got], chunk_use[got] & 1); ++chunk_use[got]; }
+                ++got;
+              }
+            };
+            if (j >= nch) {
+              // not my layer: nothing to wait for -- only keep the hand-off, ring and slot counters in step (an idle
+              // issuer must not sit on a parity wait while the barrier can complete twice)
+              if (l == 0) ++xin_use;
+              else for (int c = 0; c < n_prev; ++c) ++chunk_use[c];
               int adv = nch * ly.kc;
               while (adv > 0) { const int d = adv < n_stages - s ? adv : n_stages - s; s += d; adv -= d; if (s == n_stages) { s = 0; par ^= 1; } }
-              continue;
-            }
-            const bool tr = a.trace && j == 0 && blockIdx.x == 0 && iter == 0 && a_cnt <= 32;
-            if (tr) a.trace[(a_cnt - 1) * 8 + 0] = clock64();
-            if (tr) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); a.trace[(a_cnt - 1) * 8 + 6] = (long long)gt; }
-            uint32_t col = 0;
-            for (int c = 0; c < j; ++c) col += (uint32_t)(ly.chunk_n[c] >> 1);
-            const int cn = ly.chunk_n[j];
-            const uint32_t idesc = make_idesc(cn);
-            const uint32_t rows_b = (uint32_t)(cn >> 1) * (uint32_t)(2 * td.kw);
-            const int steps_per_tile = td.kw >> 4;
-            for (int kc = 0; kc < ly.kc; ++kc) {
-              // my tile of this K step sits j positions further in the ring
-              int sj = s + j; uint32_t pj = par;
-              while (sj >= n_stages) { sj -= n_stages; pj ^= 1; }
-              mbar_wait(&w_full[sj], pj);
-              mbar_wait_cluster(&w_peer[sj], pj);
-              tc_fence_after();
-              if (tr && kc == 0) a.trace[(a_cnt - 1) * 8 + 1] = clock64();
-              const int ksteps = kc == ly.kc - 1 ? ly.last_ksteps : steps_per_tile;
-              const int g0 = kc * steps_per_tile;                 // first K=16 step of this weight tile
-              const uint64_t ah = make_smem_desc(a_hi_addr + (g0 >> 2) * kTcATile) + 2 * (g0 & 3);
-              const uint64_t al = make_smem_desc(a_lo_addr + (g0 >> 2) * kTcATile) + 2 * (g0 & 3);
-              const uint64_t wh = make_smem_desc_b(st_addr + sj * td.stage_bytes, td.kw);
-              const uint64_t wl = make_smem_desc_b(st_addr + sj * td.stage_bytes + rows_b, td.kw);
-              for (int k = 0; k < ksteps; ++k) {
-                const uint32_t first = (kc | k) == 0 ? 0u : 1u;
-                umma_2sm(tmem_base + col, ah + 2 * k, wh + 2 * k, idesc, first);
-                if (NPASS == 3) {
-                  umma_2sm(tmem_base + col, al + 2 * k, wh + 2 * k, idesc, 1u);
-                  umma_2sm(tmem_base + col, ah + 2 * k, wl + 2 * k, idesc, 1u);
+            } else {
+              // my accumulator slot; it may still hold chunk c_shared of the previous layer (not yet drained)
+              const uint32_t col = ((reg0 + (uint32_t)j) % (uint32_t)td.regions) * (uint32_t)td.region_cols;
+              const int c_shared = l == 0 ? -1 : n_prev + j - td.regions;
+              const TcLayer& lp = hl.layer[l > 0 ? l - 1 : 0];
+              const bool tr = a.trace && j == 0 && blockIdx.x == 0 && iter == 0 && lay_cnt <= 32;
+              const int cn = ly.chunk_n[j];
+              const uint32_t idesc = make_idesc(cn);
+              const uint32_t rows_b = (uint32_t)(cn >> 1) * (uint32_t)(2 * td.kw);
+              const int steps_per_tile = td.kw >> 4;
+              for (int kc = 0; kc < ly.kc; ++kc) {
+                // phases needed: every output chunk of the previous layer that overlaps A columns of this K tile
+                int need = 0;
+                if (l > 0) {
+                  const int col_end = min((kc + 1) * td.kw, lp.np);
+                  int pre = 0;
+                  for (int c = 0; c < n_prev; ++c) { pre += lp.chunk_n[c]; if (pre >= col_end) { need = c; break; } need = c; }
+                  if (kc == 0 && c_shared > need) need = c_shared;
                 }
+                wait_inputs(need + 1);
+                tc_fence_after();
+                if (tr && kc == 0) a.trace[(lay_cnt - 1) * 8 + 0] = clock64();
+                // my tile of this K step sits j positions further in the ring
+                int sj = s + j; uint32_t pj = par;
+                while (sj >= n_stages) { sj -= n_stages; pj ^= 1; }
+                mbar_wait(&w_full[sj], pj);
+                mbar_wait_cluster(&w_peer[sj], pj);
+                tc_fence_after();
+                if (tr && kc == 0) a.trace[(lay_cnt - 1) * 8 + 1] = clock64();
+                const int ksteps = kc == ly.kc - 1 ? ly.last_ksteps : steps_per_tile;
+                const int g0 = kc * steps_per_tile;                 // first K=16 step of this weight tile
+                const uint64_t ah = make_smem_desc(a_hi_addr + (g0 >> 2) * kTcATile) + 2 * (g0 & 3);
+                const uint64_t al = make_smem_desc(a_lo_addr + (g0 >> 2) * kTcATile) + 2 * (g0 & 3);
+                const uint64_t wh = make_smem_desc_b(st_addr + sj * td.stage_bytes, td.kw);
+                const uint64_t wl = make_smem_desc_b(st_addr + sj * td.stage_bytes + rows_b, td.kw);
+                for (int k = 0; k < ksteps; ++k) {
+                  const uint32_t first = (kc | k) == 0 ? 0u : 1u;
+                  umma_2sm(tmem_base + col, ah + 2 * k, wh + 2 * k, idesc, first);
+                  if (NPASS == 3) {
+                    umma_2sm(tmem_base + col, al + 2 * k, wh + 2 * k, idesc, 1u);
+                    umma_2sm(tmem_base + col, ah + 2 * k, wl + 2 * k, idesc, 1u);
+                  }
+                }
+                umma_commit_2sm(&w_empty[sj], mask_all);   // one of n_pairs arrivals that free the stage cluster-wide
+                s += nch;
+                while (s >= n_stages) { s -= n_stages; par ^= 1; }
               }
-              umma_commit_2sm(&w_empty[sj], mask_all);   // one of n_pairs arrivals that free the stage cluster-wide
-              s += nch;
-              while (s >= n_stages) { s -= n_stages; par ^= 1; }
+              wait_inputs(n_prev);                         // (already true after the last K tile)
+              umma_commit_2sm(&acc_full[j], mask_pair);    // chunk j of the layer output complete in TMEM of both CTAs
+              if (tr) a.trace[(lay_cnt - 1) * 8 + 2] = clock64();
             }
-            umma_commit_2sm(&acc_full[j], mask_pair);  // chunk j of the layer output complete in TMEM of both CTAs
-            if (tr) a.trace[(a_cnt - 1) * 8 + 2] = clock64();
+            reg0 = (reg0 + (uint32_t)nch) % (uint32_t)td.regions;
+            n_prev = nch;                // the epilogue of this layer hands over one N chunk at a time
           }
         }
     }
@@ -419,9 +452,11 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
     const int nhalf = q >> 1;                      // 2x2 layout: lanes 64..127 hold the second N half of a chunk
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const int D = sd.D;
+    uint32_t reg0 = 0;                             // TMEM slot of chunk 0 of the current layer (same walk as the issuers)
     uint32_t acc_cnt = 0;                          // layers seen (trace index)
     uint32_t acc_use[kTcIssuers] = {0, 0, 0, 0};   // phase counters of the per-chunk accumulator barriers
     const uint32_t a_ready_leader = mapa_u32(smem_u32(a_ready), lead_rank);
+    const uint32_t a_chunk_leader = mapa_u32(smem_u32(a_chunk), lead_rank);
 
     for (long long iter = 0; iter < n_iter; ++iter) {
       const long long tile = (iter * n_clusters + cluster_id) * n_pairs + pair;   // >= n_tiles: padding iteration
@@ -489,10 +524,11 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
           const bool tr = a.trace && blockIdx.x == 0 && iter == 0 && acc_cnt <= 32 && et == 0;
           const long long t_acc = tr ? clock64() : 0;
           const float* add = l == 0 ? prow_s[row] + op.proj_off : w + hl.off_b[l];
-          uint32_t col = 0;
           int coff = 0;
+          long long t_own = 0, t_bar = 0;
           for (int nc = 0; nc < ly.n_chunks; ++nc) {
             const int cn = ly.chunk_n[nc];
+            const uint32_t col = ((reg0 + (uint32_t)nc) % (uint32_t)td.regions) * (uint32_t)td.region_cols;
             const int groups = cn >> 4;                 // 8-column groups in this thread's half chunk
             const int g0 = (groups * part) >> 2, g1 = (groups * (part + 1)) >> 2;
             const int nbase = coff + nhalf * (cn >> 1);
@@ -514,16 +550,17 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
               gelu_store8<NPASS>(a_hi, a_lo, row, n0, r0, b[0], b[1]);
               if (two) gelu_store8<NPASS>(a_hi, a_lo, row, n0 + 8, r1, b[2], b[3]);
             }
-            col += (uint32_t)(cn >> 1);
             coff += cn;
+            // this N chunk of the next layer's input is complete (and its accumulator slot drained): one a_ready phase
+            if (tr && nc == ly.n_chunks - 1) t_own = clock64();
+            tc_fence_before();
+            fence_proxy_async();
+            epi_bar_sync();
+            if (tr && nc == ly.n_chunks - 1) t_bar = clock64();
+            if (et == 0) mbar_arrive_remote(a_chunk_leader + 8u * (uint32_t)nc);
           }
-          const long long t_own = tr ? clock64() : 0;
-          tc_fence_before();
-          fence_proxy_async();
-          epi_bar_sync();
-          const long long t_bar = tr ? clock64() : 0;
-          if (et == 0) mbar_arrive_remote(a_ready_leader);
-          if (tr) {   // stamps are written after the arrival so that the trace's global stores do not delay its release
+          reg0 = (reg0 + (uint32_t)ly.n_chunks) % (uint32_t)td.regions;
+          if (tr) {   // stamps are written after the arrivals so that the trace's global stores do not delay them
             a.trace[(acc_cnt - 1) * 8 + 3] = t_acc;
             a.trace[(acc_cnt - 1) * 8 + 4] = t_own;
             a.trace[(acc_cnt - 1) * 8 + 5] = t_bar;
@@ -540,7 +577,7 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
           const int groups = doh >> 3;                  // 8-column groups per half (t or s)
           for (int g = part; g < groups; g += 4) {
             float v[8];
-            tmem_ld8(lane_addr + g * 8, v);
+            tmem_ld8(lane_addr + (reg0 % (uint32_t)td.regions) * (uint32_t)td.region_cols + g * 8, v);
             const int j0 = g * 8;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -549,6 +586,7 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
               ts_s[row * td.tsp + nhalf * doh + j] = v[i] + b;
             }
           }
+          reg0 = (reg0 + 1u) % (uint32_t)td.regions;
           tc_fence_before();
           epi_bar_sync();
           if (et < kTcRows) {
