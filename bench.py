@@ -427,8 +427,16 @@ def main() -> None:
     achieved_tf = flops_launch / (ms_kernel * 1e-3) / 1e12
     peak_tf = float(peaks.get("bf16_tflops_sustained" if ms_kernel > 500 else "bf16_tflops"))
     fma_peak_tf = 148 * 128 * 2 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12
+    # DRAM bytes per row of the flow kernel from the committed ncu --set full captures (profiles/r01_*), scaled to
+    # this launch; for the tensor-core kernel almost all of it is the weight tile stream (re-read once per wave)
+    ncu_bytes_per_row = {("tcgen05", "trajectory_FC_large"): 1.588e9 / 1.0e5,
+                         ("rowthread", "trajectory_FC_small"): 40.8e6 / 5.0e5}.get((flow.kernel, cfg_key))
+    traffic = ncu_bytes_per_row * rows_step if ncu_bytes_per_row else None
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf, "traffic": None, "peak_source": f"{peak_src} bf16 dense",
+                "frac": achieved_tf / peak_tf, "traffic": traffic,
+                "traffic_source": "ncu dram__bytes_read+write per row (profiles/r01_tcgen05_v3.txt, r01_rowthread_lds.txt) x rows"
+                                  if traffic else None,
+                "peak_source": f"{peak_src} bf16 dense",
                 "kernel": f"flow_{flow.kernel}", "kernel_ms": ms_kernel,
                 "fp32_fma_peak_tflops": fma_peak_tf, "fp32_fma_frac": achieved_tf / fma_peak_tf,
                 "algorithmic_bytes_per_row": 4 * d * 2 + 4, "flops_per_row": 2 * int(flow.info.macs_per_row)}
