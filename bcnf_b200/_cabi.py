@@ -108,9 +108,7 @@ def lib() -> C.CDLL:
     L.bcnf_train_dropout_mask.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_uint64, C.c_uint32, C.c_float,
                                           C.c_void_p, C.c_int32, C.c_void_p]
     for name in EXPORTS:
-        if name not in ("bcnf_last_error",):
-            getattr(L, name).restype = C.c_int if name != "bcnf_last_error" else C.c_char_p
-    L.bcnf_last_error.restype = C.c_char_p
+        getattr(L, name).restype = C.c_char_p if name == "bcnf_last_error" else C.c_int
     _lib = L
     return L
 

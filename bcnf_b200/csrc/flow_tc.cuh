@@ -11,15 +11,19 @@
 //     shared-memory tile images the MMA wants, so the producer warp streams them with plain
 //     TMA bulk copies (cp.async.bulk + mbarrier) through a ring of stages; each CTA of the pair
 //     loads its half of the N rows of every tile, so a weight byte crosses L2->SM once per 128 rows;
-//   * one elected thread of the leader CTA issues tcgen05.mma.cta_group::2 (M = 128 over the pair,
-//     N <= 256 per instruction, K = 16), accumulating fp32 in TMEM: the whole layer output
-//     (64 rows x N per CTA = N/2 TMEM columns) stays there until the epilogue drains it;
-//   * eight epilogue warps per CTA read TMEM (tcgen05.ld), add the bias (or the hoisted
-//     condition projection P for the first layer), apply exact-erf GELU in fp32, split to bf16
-//     hi/lo and write the next layer's activation tiles in place;
+//   * one warp per N chunk of the leader CTA issues tcgen05.mma.cta_group::2 (M = 128 over the pair,
+//     N <= 256 per instruction, K = 16; a single thread needs ~106 cycles per issue, more than such an MMA
+//     lasts), accumulating fp32 in TMEM: 64 rows x N per CTA = N/2 columns; the accumulators of successive
+//     layers rotate through a ring of TMEM slots;
+//   * sixteen epilogue warps per CTA read TMEM (tcgen05.ld), add the bias (or the hoisted condition
+//     projection P for the first layer), apply exact-erf GELU in fp32 (packed f32x2 arithmetic), split to
+//     bf16 hi/lo and write the next layer's activation tiles in place, handing them to the issuers one
+//     N chunk at a time so that the next layer's MMAs overlap the rest of the epilogue;
 //   * the last Linear (N = 2 x 16) leaves t and s in TMEM; the row-owner threads apply
 //     tanh/exp, the affine update, the log-det row sum, ActNorm and the orthonormal mixing in
 //     fp32 on y kept in shared memory.
+// Cross-CTA hand-offs are mbarrier arrivals with CTA-scope semantics (see mbar_arrive_remote): what they
+// announce is only read by the arriving CTA's own half of the 2-CTA MMA.
 //
 // Arithmetic: NPASS = 3 computes a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (fp32-class accuracy),
 // NPASS = 1 only a_hi*w_hi (plain bf16 inputs).  Accumulation, bias, GELU, tanh, exp, the

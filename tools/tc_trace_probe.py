@@ -1,5 +1,5 @@
 import os, sys, json, torch, numpy as np
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import bench
 from bcnf_b200 import CondRealNVP_v2
 prec = sys.argv[1]
