@@ -76,6 +76,22 @@ __device__ __forceinline__ void axpy_row(float (&acc)[N], float x, uint32_t w) {
   }
 }
 
+// Packed variant: acc holds N/2 fp32 pairs; one FFMA2 updates two output columns with the same input x.
+__device__ __forceinline__ void lds2x2(uint32_t addr, f32x2& a, f32x2& b) {
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+}
+template <int N>
+__device__ __forceinline__ void axpy_row2(f32x2 (&acc)[N / 2], float x, uint32_t w) {
+  const f32x2 xx = pack2(x, x);
+#pragma unroll
+  for (int j = 0; j < N; j += 4) {
+    f32x2 w01, w23;
+    lds2x2(w + 4 * j, w01, w23);
+    acc[j / 2] = fma2(xx, w01, acc[j / 2]);
+    acc[j / 2 + 1] = fma2(xx, w23, acc[j / 2 + 1]);
+  }
+}
+
 // One conditioner network + affine update of the other half (cnf.py:98-107, :178-190, :203-204).
 template <int D, int HP, int SRC>
 __device__ __forceinline__ void half_coupling(float (&y)[D], float& ld, uint32_t w,
@@ -88,35 +104,37 @@ __device__ __forceinline__ void half_coupling(float (&y)[D], float& ld, uint32_t
   constexpr int OUT0 = SRC == 0 ? DA : 0;
   constexpr int DOP = (DOUT + 3) / 4 * 4;
 
-  float acc[HP];
+  f32x2 acc[HP / 2];
   // first Linear: the condition part (W1h.h + b1) was hoisted into P (bcnf_cond_project)
 #pragma unroll
   for (int j = 0; j < HP; j += 4) {
-    float4 v = __ldg(reinterpret_cast<const float4*>(prow + j));
-    acc[j] = v.x; acc[j + 1] = v.y; acc[j + 2] = v.z; acc[j + 3] = v.w;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(prow + j));
+    acc[j / 2] = pack2(v.x, v.y);
+    acc[j / 2 + 1] = pack2(v.z, v.w);
   }
   {
     const uint32_t w1 = w + 4u * hl.off_w[0];
 #pragma unroll
-    for (int i = 0; i < DIN; ++i) axpy_row<HP>(acc, y[IN0 + i], w1 + 4u * (i * HP));
+    for (int i = 0; i < DIN; ++i) axpy_row2<HP>(acc, y[IN0 + i], w1 + 4u * (i * HP));
   }
   const int L = hl.L;
   for (int l = 1;; ++l) {
     float hcur[HP];
 #pragma unroll
-    for (int j = 0; j < HP; ++j) hcur[j] = gelu_erf_fast(acc[j]);   // nn.GELU() (exact-erf form); Dropout = identity in eval
+    for (int j = 0; j < HP; j += 2)      // nn.GELU() (exact-erf form), two columns per instruction; Dropout = identity in eval
+      unpack2(gelu_erf_fast2(acc[j / 2]), hcur[j], hcur[j + 1]);
     if (l >= L) {
       // last Linear -> (t, s); t = first DOUT outputs, s = last DOUT (chunk(2, dim=1), cnf.py:104)
-      float ts[2 * DOP];
+      f32x2 ts2[DOP];
       const uint32_t wo = w + 4u * hl.off_wout;
       const uint32_t bo = w + 4u * hl.off_bout;
 #pragma unroll
-      for (int j = 0; j < 2 * DOP; j += 4) {
-        float4 v = lds4(bo + 4 * j);
-        ts[j] = v.x; ts[j + 1] = v.y; ts[j + 2] = v.z; ts[j + 3] = v.w;
-      }
+      for (int j = 0; j < 2 * DOP; j += 4) lds2x2(bo + 4 * j, ts2[j / 2], ts2[j / 2 + 1]);
 #pragma unroll
-      for (int k = 0; k < HP; ++k) axpy_row<2 * DOP>(ts, hcur[k], wo + 4u * (k * (2 * DOP)));
+      for (int k = 0; k < HP; ++k) axpy_row2<2 * DOP>(ts2, hcur[k], wo + 4u * (k * (2 * DOP)));
+      float ts[2 * DOP];
+#pragma unroll
+      for (int j = 0; j < 2 * DOP; j += 2) unpack2(ts2[j / 2], ts[j], ts[j + 1]);
       float ls_sum = 0.f;
 #pragma unroll
       for (int j = 0; j < DOUT; ++j) {
@@ -131,12 +149,9 @@ __device__ __forceinline__ void half_coupling(float (&y)[D], float& ld, uint32_t
     const uint32_t wl = w + 4u * hl.off_w[l];
     const uint32_t bl = w + 4u * hl.off_b[l];
 #pragma unroll
-    for (int j = 0; j < HP; j += 4) {
-      float4 v = lds4(bl + 4 * j);
-      acc[j] = v.x; acc[j + 1] = v.y; acc[j + 2] = v.z; acc[j + 3] = v.w;
-    }
+    for (int j = 0; j < HP; j += 4) lds2x2(bl + 4 * j, acc[j / 2], acc[j / 2 + 1]);
 #pragma unroll
-    for (int k = 0; k < HP; ++k) axpy_row<HP>(acc, hcur[k], wl + 4u * (k * HP));
+    for (int k = 0; k < HP; ++k) axpy_row2<HP>(acc, hcur[k], wl + 4u * (k * HP));
   }
 }
 
@@ -201,11 +216,14 @@ flow_rowthread_kernel(const FlowArgs a, const StackDims sd, const int chunk_cap_
           else             half_coupling<D, HP, 1>(y, ld, w, sd.half[1], prow + op.proj_off, op.inverse);
         } else if (op.type == DOP_MIX) {
           // y <- y @ M, M = Q (forward, cnf.py:335) or Q^T (inverse, cnf.py:339)
+          f32x2 o2[DP / 2];
+#pragma unroll
+          for (int j = 0; j < DP / 2; ++j) o2[j] = 0ull;
+#pragma unroll
+          for (int i = 0; i < D; ++i) axpy_row2<DP>(o2, y[i], w + 4u * (i * DP));
           float o[DP];
 #pragma unroll
-          for (int j = 0; j < DP; ++j) o[j] = 0.f;
-#pragma unroll
-          for (int i = 0; i < D; ++i) axpy_row<DP>(o, y[i], w + 4u * (i * DP));
+          for (int j = 0; j < DP; j += 2) unpack2(o2[j / 2], o[j], o[j + 1]);
 #pragma unroll
           for (int j = 0; j < D; ++j) y[j] = o[j];
         } else if (op.type == DOP_ACTNORM_FWD) {
