@@ -24,7 +24,9 @@ KERNEL_NAMES = {0: "rowthread", 1: "tiled", 2: "tcgen05"}
 
 EXPORTS = ["bcnf_abi_version", "bcnf_last_error", "bcnf_flow_create", "bcnf_flow_destroy",
            "bcnf_flow_info", "bcnf_flow_set_params", "bcnf_cond_project", "bcnf_flow_forward",
-           "bcnf_flow_inverse", "bcnf_train_gemm", "bcnf_train_colsum", "bcnf_train_dropout_mask"]
+           "bcnf_flow_inverse", "bcnf_train_gemm", "bcnf_train_colsum", "bcnf_train_dropout_mask",
+           "bcnf_train_set_gemm_mode", "bcnf_train_gemm_trace", "bcnf_train_pre", "bcnf_train_post",
+           "bcnf_train_post_bwd", "bcnf_train_pre_bwd", "bcnf_img_pack"]
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU_DROP, EPI_DGELU_DROP = 0, 1, 2, 3
 
 
@@ -53,7 +55,53 @@ class GemmArgs(C.Structure):
                 ("K", C.c_int32), ("as0", C.c_int64), ("as1", C.c_int64), ("bs0", C.c_int64), ("bs1", C.c_int64),
                 ("cs0", C.c_int64), ("beta", C.c_float), ("epilogue", C.c_int32), ("bias", C.c_void_p),
                 ("save", C.c_void_p), ("saved", C.c_void_p), ("seed", C.c_uint64), ("layer_uid", C.c_uint32),
-                ("p_drop", C.c_float), ("seed_ptr", C.c_void_p)]
+                ("p_drop", C.c_float), ("seed_ptr", C.c_void_p), ("colsum", C.c_void_p), ("ws", C.c_void_p),
+                ("counters", C.c_void_p), ("ws_floats", C.c_int64), ("n_counters", C.c_int32), ("split_k", C.c_int32),
+                ("a_img", C.c_void_p), ("a_plane", C.c_int64), ("a_rpad", C.c_int32), ("pad0", C.c_int32),
+                ("b_img", C.c_void_p), ("b_plane", C.c_int64), ("b_rpad", C.c_int32), ("pad1", C.c_int32),
+                ("c_img", C.c_void_p), ("c_plane", C.c_int64), ("c_rpad", C.c_int32), ("pad2", C.c_int32)]
+
+
+class ImgPackDesc(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("s_row", C.c_int64), ("s_k", C.c_int64), ("rows", C.c_int32), ("k", C.c_int32),
+                ("dst", C.c_void_p), ("plane", C.c_int64), ("rpad", C.c_int32), ("chunks", C.c_int32)]
+
+
+GLUE_ORTHO, GLUE_ACTNORM = 0, 1
+
+
+class GlueOp(C.Structure):
+    _fields_ = [("type", C.c_int32), ("p0", C.c_void_p), ("p1", C.c_void_p), ("save", C.c_void_p), ("g0", C.c_void_p),
+                ("g1", C.c_void_p)]
+
+
+class TrainPreArgs(C.Structure):
+    _fields_ = [("y", C.c_void_p), ("y_pitch", C.c_int64), ("B", C.c_int32), ("D", C.c_int32), ("src0", C.c_int32),
+                ("din", C.c_int32), ("W1", C.c_void_p), ("w1_pitch", C.c_int64), ("P", C.c_void_p), ("p_pitch", C.c_int64),
+                ("H", C.c_int32), ("pre", C.c_void_p), ("act", C.c_void_p), ("pitch", C.c_int64), ("seed", C.c_uint64),
+                ("layer_uid", C.c_uint32), ("p_drop", C.c_float), ("seed_ptr", C.c_void_p), ("act_img", C.c_void_p),
+                ("img_plane", C.c_int64), ("img_rpad", C.c_int32)]
+
+
+class TrainPostArgs(C.Structure):
+    _fields_ = [("a", C.c_void_p), ("a_pitch", C.c_int64), ("Wout", C.c_void_p), ("bout", C.c_void_p), ("B", C.c_int32),
+                ("D", C.c_int32), ("H", C.c_int32), ("dst0", C.c_int32), ("dout", C.c_int32), ("y_in", C.c_void_p),
+                ("y_out", C.c_void_p), ("ld", C.c_void_p), ("ls_save", C.c_void_p), ("ydst_save", C.c_void_p),
+                ("n_ops", C.c_int32), ("ops", GlueOp * 4)]
+
+
+class TrainPostBwdArgs(C.Structure):
+    _fields_ = [("dz_in", C.c_void_p), ("dz_out", C.c_void_p), ("dld", C.c_void_p), ("B", C.c_int32), ("D", C.c_int32),
+                ("H", C.c_int32), ("dst0", C.c_int32), ("dout", C.c_int32), ("ls_save", C.c_void_p),
+                ("ydst_save", C.c_void_p), ("Wout", C.c_void_p), ("pre", C.c_void_p), ("pitch", C.c_int64),
+                ("d_o", C.c_void_p), ("d_pre", C.c_void_p), ("seed", C.c_uint64), ("layer_uid", C.c_uint32),
+                ("p_drop", C.c_float), ("seed_ptr", C.c_void_p), ("n_ops", C.c_int32), ("ops", GlueOp * 4),
+                ("dpre_img", C.c_void_p), ("img_plane", C.c_int64), ("img_rpad", C.c_int32)]
+
+
+class TrainPreBwdArgs(C.Structure):
+    _fields_ = [("d_pre", C.c_void_p), ("pitch", C.c_int64), ("W1", C.c_void_p), ("w1_pitch", C.c_int64), ("B", C.c_int32),
+                ("D", C.c_int32), ("H", C.c_int32), ("src0", C.c_int32), ("din", C.c_int32), ("dz", C.c_void_p)]
 
 
 def nvcc_command(out_path: str = LIB_PATH) -> list[str]:
@@ -104,6 +152,13 @@ def lib() -> C.CDLL:
     L.bcnf_flow_forward.argtypes = flow_args
     L.bcnf_flow_inverse.argtypes = flow_args
     L.bcnf_train_gemm.argtypes = [C.POINTER(GemmArgs), C.c_int32, C.c_void_p]
+    L.bcnf_train_set_gemm_mode.argtypes = [C.c_int32]
+    L.bcnf_img_pack.argtypes = [C.POINTER(ImgPackDesc), C.c_int32, C.c_int32, C.c_void_p]
+    L.bcnf_train_pre.argtypes = [C.POINTER(TrainPreArgs), C.c_int32, C.c_void_p]
+    L.bcnf_train_post.argtypes = [C.POINTER(TrainPostArgs), C.c_int32, C.c_void_p]
+    L.bcnf_train_post_bwd.argtypes = [C.POINTER(TrainPostBwdArgs), C.c_int32, C.c_void_p]
+    L.bcnf_train_pre_bwd.argtypes = [C.POINTER(TrainPreBwdArgs), C.c_int32, C.c_void_p]
+    L.bcnf_train_gemm_trace.argtypes = [C.POINTER(GemmArgs), C.c_int32, C.c_void_p, C.POINTER(C.c_int64)]
     L.bcnf_train_colsum.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_float, C.c_int32, C.c_void_p]
     L.bcnf_train_dropout_mask.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_uint64, C.c_uint32, C.c_float,
                                           C.c_void_p, C.c_int32, C.c_void_p]

@@ -17,6 +17,8 @@
 #include "flow_tiled.cuh"
 #include "proj_tc.cuh"
 #include "train_ops.cuh"
+#include "train_tc.cuh"
+#include "train_glue.cuh"
 
 using namespace bcnf;
 
@@ -891,8 +893,146 @@ extern "C" int bcnf_flow_inverse(bcnf_flow_t* f, const float* z, const float* P,
 // ----------------------------------------------------------------------------------------------
 static_assert(sizeof(bcnf_gemm_args_t) == sizeof(GemmArgs), "bcnf_gemm_args_t and GemmArgs must match");
 
+static int g_train_gemm_mode = 0;
+static long long* g_train_trace = nullptr;   // debug: device buffer of 64 clock64 stamps (bcnf_train_gemm_trace)
+
+// Debug aid (tools/tc_gemm_check.py): run one tensor-core GEMM with the pipeline stamps of CTA (0,0,0) recorded.
+extern "C" int bcnf_train_gemm_trace(const bcnf_gemm_args_t* args, int32_t device, void* stream, int64_t* out64) {
+  CUDA_TRY(cudaSetDevice(device));
+  long long* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, 64 * sizeof(long long)));
+  CUDA_TRY(cudaMemset(d, 0, 64 * sizeof(long long)));
+  g_train_trace = d;
+  const int rc = bcnf_train_gemm(args, device, stream);
+  g_train_trace = nullptr;
+  if (rc == BCNF_OK) {
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    CUDA_TRY(cudaMemcpy(out64, d, 64 * sizeof(long long), cudaMemcpyDeviceToHost));
+  }
+  cudaFree(d);
+  return rc;
+}
+
+extern "C" int bcnf_train_set_gemm_mode(int32_t mode) {
+  const int old = g_train_gemm_mode;
+  g_train_gemm_mode = mode;
+  return old;
+}
+
+template <int BN>
+static int launch_train_tc_bn(const GemmArgs& g, cudaStream_t stream) {
+  using Cfg = TgCfg<BN>;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 64 && !attr_set[dev]) {
+    CUDA_TRY(cudaFuncSetAttribute(train_tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem));
+    attr_set[dev] = true;
+  }
+  const int tiles_m = (g.M + kTgBM - 1) / kTgBM, tiles_n = (g.N + BN - 1) / BN;
+  const long long tiles = (long long)tiles_m * tiles_n;
+  const int n_kc = (g.K + 63) / 64;
+  // split K over gridDim.z when the tiles alone leave most SMs idle: at batch 256 a CTA's time is the L2 -> SM
+  // transfer of its operand panels (about 64 B/clk per SM), so spreading K over more SMs is what shortens it
+  int split = 1;
+  if (g.split_k != 1 && g.ws && g.counters && tiles <= g.n_counters && tiles * kTgBM * BN <= g.ws_floats && tiles < 120) {
+    split = (int)(148 / tiles);
+    if (g.split_k > 1 && split > g.split_k) split = g.split_k;
+    if (split > n_kc) split = n_kc;
+    if (split < 1) split = 1;
+  }
+  TgExtra x;
+  x.ws = g.ws;
+  x.counters = g.counters;
+  x.colsum = g.colsum;
+  x.trace = g_train_trace;
+  x.chunks_per_split = (n_kc + split - 1) / split;
+  split = (n_kc + x.chunks_per_split - 1) / x.chunks_per_split;
+  dim3 grid(tiles_n, tiles_m, split);
+  train_tc_gemm_kernel<BN><<<grid, kTgThreads, Cfg::smem, stream>>>(g, x);
+  CUDA_TRY(cudaGetLastError());
+  return BCNF_OK;
+}
+
+template <int BN>
+static int launch_train_tc2_bn(const GemmArgs& g, cudaStream_t stream) {
+  using Cfg = T2Cfg<BN>;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 64 && !attr_set[dev]) {
+    CUDA_TRY(cudaFuncSetAttribute(train_tc2_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem));
+    attr_set[dev] = true;
+  }
+  const int tiles_m = (g.M + kTgBM - 1) / kTgBM, tiles_n = (g.N + BN - 1) / BN;
+  const int n_kc = (g.K + 63) / 64;
+  if (g.a_rpad % 128 || g.a_rpad < tiles_m * kTgBM || g.a_plane < (long long)n_kc * g.a_rpad * 128)
+    return fail(BCNF_E_ARG, "bcnf_train_gemm: A image too small (rpad=%d plane=%lld for M=%d K=%d)", g.a_rpad, g.a_plane, g.M, g.K);
+  if (g.b_rpad < tiles_n * BN || g.b_plane < (long long)n_kc * g.b_rpad * 128)
+    return fail(BCNF_E_ARG, "bcnf_train_gemm: B image too small (rpad=%d plane=%lld for N=%d K=%d)", g.b_rpad, g.b_plane, g.N, g.K);
+  if (g.c_img && (g.c_rpad <= 0 || g.c_plane % ((long long)g.c_rpad * 128)))
+    return fail(BCNF_E_ARG, "bcnf_train_gemm: bad C image (rpad=%d plane=%lld)", g.c_rpad, g.c_plane);
+  ImgArgs im;
+  im.a_img = g.a_img; im.a_plane = g.a_plane; im.a_rpad = g.a_rpad;
+  im.b_img = g.b_img; im.b_plane = g.b_plane; im.b_rpad = g.b_rpad;
+  im.c_img = g.c_img; im.c_plane = g.c_plane; im.c_rpad = g.c_rpad;
+  im.colsum = g.colsum;
+  dim3 grid(tiles_n, tiles_m);
+  train_tc2_gemm_kernel<BN><<<grid, kT2Threads, Cfg::smem, stream>>>(g, im);
+  CUDA_TRY(cudaGetLastError());
+  return BCNF_OK;
+}
+
+static int launch_train_tc2(const GemmArgs& g, int force_bn, cudaStream_t stream) {
+  const long long tm = (g.M + kTgBM - 1) / kTgBM;
+  int bn = force_bn;
+  // at a few hundred rows the CTA's time is the L2 -> SM transfer of its operand panels: narrow tiles, more SMs
+  if (bn == 0) bn = tm * ((g.N + 127) / 128) >= 148 ? 128 : (tm * ((g.N + 63) / 64) >= 148 ? 64 : 32);
+  if (bn == 128) return launch_train_tc2_bn<128>(g, stream);
+  if (bn == 64) return launch_train_tc2_bn<64>(g, stream);
+  if (bn == 32) return launch_train_tc2_bn<32>(g, stream);
+  return fail(BCNF_E_ARG, "bcnf_train_gemm: tile width %d (32, 64 or 128)", bn);
+}
+
+static_assert(sizeof(bcnf_img_pack_desc_t) == sizeof(ImgPackDesc), "bcnf_img_pack_desc_t and ImgPackDesc must match");
+
+extern "C" int bcnf_img_pack(const bcnf_img_pack_desc_t* descs, int32_t n, int32_t device, void* stream) {
+  if (n < 0 || (n > 0 && !descs)) return fail(BCNF_E_ARG, "bcnf_img_pack: bad argument");
+  CUDA_TRY(cudaSetDevice(device));
+  for (int b0 = 0; b0 < n; b0 += kImgPackMax) {
+    ImgPackBatch batch;
+    const int nb = n - b0 < kImgPackMax ? n - b0 : kImgPackMax;
+    int max_blocks = 0;
+    for (int i = 0; i < nb; ++i) {
+      const bcnf_img_pack_desc_t& d = descs[b0 + i];
+      if (!d.src || !d.dst || d.rpad <= 0 || d.rpad % 32 || d.chunks <= 0 || d.plane < (long long)d.chunks * d.rpad * 128 ||
+          d.rows < 0 || d.rows > d.rpad || d.k < 0 || d.k > d.chunks * 64)
+        return fail(BCNF_E_ARG, "bcnf_img_pack: bad descriptor %d", b0 + i);
+      memcpy(&batch.d[i], &d, sizeof(ImgPackDesc));
+      if (d.rpad / 32 > max_blocks) max_blocks = d.rpad / 32;
+    }
+    img_pack_kernel<<<dim3(max_blocks, nb), kTgGroupThreads, 0, (cudaStream_t)stream>>>(batch);
+    CUDA_TRY(cudaGetLastError());
+  }
+  return BCNF_OK;
+}
+
+static int launch_train_tc(const GemmArgs& g, int force_bn, cudaStream_t stream) {
+  const long long tm = (g.M + kTgBM - 1) / kTgBM;
+  int bn = force_bn;
+  if (bn == 0) {
+    if (tm * ((g.N + 127) / 128) >= 148) bn = 128;
+    else bn = 64;
+  }
+  if (bn == 128) return launch_train_tc_bn<128>(g, stream);
+  if (bn == 64) return launch_train_tc_bn<64>(g, stream);
+  if (bn == 32) return launch_train_tc_bn<32>(g, stream);
+  return fail(BCNF_E_ARG, "bcnf_train_gemm: tile width %d (32, 64 or 128)", bn);
+}
+
 extern "C" int bcnf_train_gemm(const bcnf_gemm_args_t* args, int32_t device, void* stream_) {
-  if (!args || !args->A || !args->B || !args->C) return fail(BCNF_E_ARG, "bcnf_train_gemm: null argument");
+  const bool images = args && args->a_img && args->b_img;
+  if (!args || !args->C || (!images && (!args->A || !args->B))) return fail(BCNF_E_ARG, "bcnf_train_gemm: null argument");
   if (args->M < 0 || args->N < 0 || args->K < 0) return fail(BCNF_E_ARG, "bcnf_train_gemm: negative size");
   if (args->epilogue < 0 || args->epilogue > 3) return fail(BCNF_E_ARG, "bcnf_train_gemm: unknown epilogue %d", args->epilogue);
   if ((args->epilogue == BCNF_EPI_BIAS || args->epilogue == BCNF_EPI_BIAS_GELU_DROP) && !args->bias)
@@ -905,6 +1045,16 @@ extern "C" int bcnf_train_gemm(const bcnf_gemm_args_t* args, int32_t device, voi
   GemmArgs g;
   memcpy(&g, args, sizeof(g));
   cudaStream_t stream = (cudaStream_t)stream_;
+  const int mode = g_train_gemm_mode & 0xF, force_bn = (g_train_gemm_mode >> 4) & 0xFF;
+  if (images) {
+    if (g.K < 1) return fail(BCNF_E_ARG, "bcnf_train_gemm: K = 0 with operand images");
+    return launch_train_tc2(g, force_bn, stream);
+  }
+  // tensor cores when the problem fills a 128-row tile reasonably; slivers (K = 10 own-half inputs, the 18-wide last
+  // Linear and its gradients) stay on the FMA kernel
+  const bool tc_legal = g.K >= 16;
+  const bool tc_auto = g.M >= 64 && g.N >= 32 && g.K >= 64;
+  if (tc_legal && (mode == 2 || (mode == 0 && tc_auto))) return launch_train_tc(g, force_bn, stream);
   // small problems: 32x32 tiles put more CTAs in flight (a 256-row batch is 4 tiles of 64)
   const long long ctas64 = (long long)((g.M + 63) / 64) * ((g.N + 63) / 64);
   if (ctas64 >= 296) {
@@ -915,6 +1065,10 @@ extern "C" int bcnf_train_gemm(const bcnf_gemm_args_t* args, int32_t device, voi
     train_gemm_kernel<32, 32><<<grid, 256, 0, stream>>>(g);
   }
   CUDA_TRY(cudaGetLastError());
+  if (g.colsum) {   // same contract as the tensor-core epilogue: column sums of the values just written
+    colsum_kernel<<<(g.N + 31) / 32, 256, 0, stream>>>(g.C, g.M, g.N, g.cs0, g.colsum, 1.0f);
+    CUDA_TRY(cudaGetLastError());
+  }
   return BCNF_OK;
 }
 
@@ -924,7 +1078,7 @@ extern "C" int bcnf_train_colsum(const float* X, int32_t M, int32_t N, int64_t l
   if (M < 0 || N < 0) return fail(BCNF_E_ARG, "bcnf_train_colsum: negative size");
   if (N == 0) return BCNF_OK;
   CUDA_TRY(cudaSetDevice(device));
-  colsum_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream_>>>(X, M, N, ldx, out, beta);
+  colsum_kernel<<<(N + 31) / 32, 256, 0, (cudaStream_t)stream_>>>(X, M, N, ldx, out, beta);
   CUDA_TRY(cudaGetLastError());
   return BCNF_OK;
 }
@@ -938,6 +1092,77 @@ extern "C" int bcnf_train_dropout_mask(float* out, int32_t M, int32_t N, uint64_
   CUDA_TRY(cudaSetDevice(device));
   dropout_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(out, M, N, seed, layer_uid, p_drop,
                                                                                             (const unsigned long long*)seed_ptr);
+  CUDA_TRY(cudaGetLastError());
+  return BCNF_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// fused training kernels around the hidden-layer GEMMs
+// ----------------------------------------------------------------------------------------------
+static_assert(sizeof(bcnf_train_pre_args_t) == sizeof(TrainPreArgs), "bcnf_train_pre_args_t / TrainPreArgs");
+static_assert(sizeof(bcnf_train_post_args_t) == sizeof(TrainPostArgs), "bcnf_train_post_args_t / TrainPostArgs");
+static_assert(sizeof(bcnf_train_post_bwd_args_t) == sizeof(TrainPostBwdArgs), "bcnf_train_post_bwd_args_t / TrainPostBwdArgs");
+static_assert(sizeof(bcnf_train_pre_bwd_args_t) == sizeof(TrainPreBwdArgs), "bcnf_train_pre_bwd_args_t / TrainPreBwdArgs");
+
+static int check_glue_dims(const char* what, int B, int D, int H, int half0, int half_n, int n_ops) {
+  if (B < 0 || D < 1 || D > 64 || H < 0) return fail(BCNF_E_ARG, "%s: bad size (B=%d D=%d H=%d; D <= 64)", what, B, D, H);
+  if (half_n < 0 || half_n > 32 || half0 < 0 || half0 + half_n > D) return fail(BCNF_E_ARG, "%s: bad half [%d, %d) of %d", what, half0, half0 + half_n, D);
+  if (n_ops < 0 || n_ops > kGlueMaxOps) return fail(BCNF_E_ARG, "%s: %d glue ops (max %d)", what, n_ops, kGlueMaxOps);
+  return BCNF_OK;
+}
+
+extern "C" int bcnf_train_pre(const bcnf_train_pre_args_t* args, int32_t device, void* stream) {
+  if (!args || !args->y || !args->W1 || !args->P || !args->pre || !args->act) return fail(BCNF_E_ARG, "bcnf_train_pre: null argument");
+  if (int rc = check_glue_dims("bcnf_train_pre", args->B, args->D, args->H, args->src0, args->din, 0)) return rc;
+  if (args->p_drop < 0.f || args->p_drop >= 1.f) return fail(BCNF_E_ARG, "bcnf_train_pre: p_drop=%f", args->p_drop);
+  if (args->B == 0 || args->H == 0) return BCNF_OK;
+  CUDA_TRY(cudaSetDevice(device));
+  TrainPreArgs a;
+  memcpy(&a, args, sizeof(a));
+  dim3 grid((a.H + 127) / 128, (a.B + kPreRows - 1) / kPreRows);
+  train_pre_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  return BCNF_OK;
+}
+
+extern "C" int bcnf_train_post(const bcnf_train_post_args_t* args, int32_t device, void* stream) {
+  if (!args || !args->y_in || !args->y_out || !args->ld) return fail(BCNF_E_ARG, "bcnf_train_post: null argument");
+  if (args->a && (!args->Wout || !args->bout || !args->ls_save || !args->ydst_save)) return fail(BCNF_E_ARG, "bcnf_train_post: null argument");
+  if (int rc = check_glue_dims("bcnf_train_post", args->B, args->D, args->H, args->dst0, args->dout, args->n_ops)) return rc;
+  if (args->B == 0) return BCNF_OK;
+  CUDA_TRY(cudaSetDevice(device));
+  TrainPostArgs a;
+  memcpy(&a, args, sizeof(a));
+  train_post_kernel<<<(a.B + kGlueWarps - 1) / kGlueWarps, 32 * kGlueWarps, 0, (cudaStream_t)stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  return BCNF_OK;
+}
+
+extern "C" int bcnf_train_post_bwd(const bcnf_train_post_bwd_args_t* args, int32_t device, void* stream) {
+  if (!args || !args->dz_in || !args->dz_out || !args->dld) return fail(BCNF_E_ARG, "bcnf_train_post_bwd: null argument");
+  if (args->Wout && (!args->ls_save || !args->ydst_save || !args->pre || !args->d_o || !args->d_pre))
+    return fail(BCNF_E_ARG, "bcnf_train_post_bwd: null argument");
+  if (int rc = check_glue_dims("bcnf_train_post_bwd", args->B, args->D, args->H, args->dst0, args->dout, args->n_ops)) return rc;
+  for (int o = 0; o < args->n_ops; ++o)
+    if (args->ops[o].type == GLUE_ACTNORM && (!args->ops[o].save || !args->ops[o].g0 || !args->ops[o].g1))
+      return fail(BCNF_E_ARG, "bcnf_train_post_bwd: ActNorm op %d lacks save / gradient buffers", o);
+  if (args->B == 0) return BCNF_OK;
+  CUDA_TRY(cudaSetDevice(device));
+  TrainPostBwdArgs a;
+  memcpy(&a, args, sizeof(a));
+  train_post_bwd_kernel<<<(a.B + kGlueWarps - 1) / kGlueWarps, 32 * kGlueWarps, 0, (cudaStream_t)stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  return BCNF_OK;
+}
+
+extern "C" int bcnf_train_pre_bwd(const bcnf_train_pre_bwd_args_t* args, int32_t device, void* stream) {
+  if (!args || !args->d_pre || !args->W1 || !args->dz) return fail(BCNF_E_ARG, "bcnf_train_pre_bwd: null argument");
+  if (int rc = check_glue_dims("bcnf_train_pre_bwd", args->B, args->D, args->H, args->src0, args->din, 0)) return rc;
+  if (args->B == 0) return BCNF_OK;
+  CUDA_TRY(cudaSetDevice(device));
+  TrainPreBwdArgs a;
+  memcpy(&a, args, sizeof(a));
+  train_pre_bwd_kernel<<<(a.B + kGlueWarps - 1) / kGlueWarps, 32 * kGlueWarps, 0, (cudaStream_t)stream>>>(a);
   CUDA_TRY(cudaGetLastError());
   return BCNF_OK;
 }

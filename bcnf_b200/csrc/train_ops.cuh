@@ -35,6 +35,16 @@ struct GemmArgs {
   unsigned int layer_uid;
   float p_drop;
   const unsigned long long* seed_ptr;   // optional device-resident seed word, XORed into `seed` (CUDA-graph replays)
+  float* colsum;           // optional [N]: colsum[j] += sum_i C(i, j) of the values written (bias gradient of the layer below)
+  float* ws;               // optional split-K workspace (fp32, zero on entry, left zero) and its size in floats
+  unsigned int* counters;  // optional split-K tile counters (zero on entry, left zero) and their number
+  long long ws_floats;
+  int n_counters;
+  int split_k;             // 0: library decides (needs ws / counters); 1: never split; n > 1: at most n splits
+  // operand images (train_tc.cuh): when a_img and b_img are given the TMA-fed kernel runs and A / B are not read
+  const unsigned char* a_img; long long a_plane; int a_rpad; int pad0;
+  const unsigned char* b_img; long long b_plane; int b_rpad; int pad1;
+  unsigned char* c_img; long long c_plane; int c_rpad; int pad2;     // optional: image of the values written to C
 };
 
 // uniform [0,1) from (seed, layer, element): two rounds of a 64-bit mix (splitmix64 finaliser)
@@ -168,13 +178,30 @@ train_gemm_kernel(const GemmArgs g) {
   }
 }
 
-// out[j] = sum_i X[i*ldx + j] (+ beta * out[j]): bias gradients and ActNorm reductions
-__global__ void colsum_kernel(const float* __restrict__ X, int M, int N, long long ldx, float* __restrict__ out, float beta) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= N) return;
-  float s = 0.f;
-  for (int i = 0; i < M; ++i) s += X[i * ldx + j];
-  out[j] = beta != 0.f ? fmaf(beta, out[j], s) : s;
+// out[j] = sum_i X[i*ldx + j] (+ beta * out[j]): bias gradients and ActNorm reductions.
+// Block = 32 columns x 8 row groups; each thread sums every 8th row (coalesced across the 32 columns), then the 8
+// partial sums of a column meet in shared memory.
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, int M, int N, long long ldx,
+                                                     float* __restrict__ out, float beta) {
+  __shared__ float part[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + tx;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (j < N) {
+    int i = ty;
+    for (; i + 24 < M; i += 32) {
+      s0 += X[i * ldx + j]; s1 += X[(i + 8) * ldx + j]; s2 += X[(i + 16) * ldx + j]; s3 += X[(i + 24) * ldx + j];
+    }
+    for (; i < M; i += 8) s0 += X[i * ldx + j];
+  }
+  part[ty][tx] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (ty == 0 && j < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) s += part[r][tx];
+    out[j] = beta != 0.f ? fmaf(beta, out[j], s) : s;
+  }
 }
 
 __global__ void dropout_mask_kernel(float* __restrict__ out, int M, int N, unsigned long long seed, unsigned int layer_uid, float p,

@@ -29,14 +29,79 @@ def _stream(dev: torch.device) -> int:
     return torch.cuda.current_stream(dev).cuda_stream
 
 
+_WS: dict[int, tuple[torch.Tensor, torch.Tensor]] = {}
+_WS_FLOATS = 148 * 128 * 128        # one 128 x 128 fp32 tile per SM: split-K only runs when the tiles alone leave SMs idle
+_WS_COUNTERS = 1024
+
+
+def _workspace(dev: torch.device) -> tuple[torch.Tensor, torch.Tensor]:
+    """Split-K scratch of the tensor-core GEMM (zero on entry, left zero by every launch); one per device, shared by
+    all GEMMs of that device -- they are ordered on one stream (the step runs on the current stream)."""
+    key = dev.index or 0
+    if key not in _WS:
+        _WS[key] = (torch.zeros(_WS_FLOATS, device=dev), torch.zeros(_WS_COUNTERS, dtype=torch.int32, device=dev))
+    return _WS[key]
+
+
+class _Img:
+    """Operand image of a (rows x k) matrix for the TMA-fed tensor-core GEMM (include/bcnf_b200.h): bf16 hi and lo
+    planes, [ceil(k/64)][rows padded to 128][128 bytes] each; zero outside the valid extent (allocated zeroed, and
+    producers only ever write inside rows x tiles)."""
+
+    def __init__(self, dev: torch.device, rows: int, k: int) -> None:
+        self.rows, self.k = rows, k
+        self.rpad = (rows + 127) // 128 * 128
+        self.chunks = (k + 63) // 64
+        self.plane = self.chunks * self.rpad * 128
+        self.buf = torch.zeros(2 * self.plane, dtype=torch.uint8, device=dev)
+
+    @property
+    def ptr(self) -> int:
+        return self.buf.data_ptr()
+
+
+_IMGS: dict[tuple, _Img] = {}
+
+
+def _img(dev: torch.device, tag: Any, rows: int, k: int) -> _Img:
+    """Cached scratch image: (device, tag, shape) -> buffer.  Scratch images are reused in stream order."""
+    key = (dev.index or 0, tag, rows, k)
+    im = _IMGS.get(key)
+    if im is None:
+        im = _IMGS[key] = _Img(dev, rows, k)
+    return im
+
+
+def _pack_images(descs: list[tuple[torch.Tensor, int, int, int, int, int, _Img]], dev: torch.device) -> None:
+    """descs: (tensor, element offset, s_row, s_k, rows, k, image).  One launch per 64 descriptors."""
+    arr = (_cabi.ImgPackDesc * len(descs))()
+    for d, (t, off, s_row, s_k, rows, k, im) in zip(arr, descs):
+        d.src, d.s_row, d.s_k, d.rows, d.k = t.data_ptr() + 4 * off, s_row, s_k, rows, k
+        d.dst, d.plane, d.rpad, d.chunks = im.ptr, im.plane, im.rpad, im.chunks
+    _cabi.check(_cabi.lib().bcnf_img_pack(arr, len(descs), dev.index or 0, _stream(dev)), "bcnf_img_pack")
+
+
 def _gemm(A, a_strides, B, b_strides, Cm, M, N, K, *, beta=0.0, epi=_cabi.EPI_NONE, bias=None, save=None,
-          saved=None, seed=0, uid=0, p=0.0, seed_ptr=None) -> None:
+          saved=None, seed=0, uid=0, p=0.0, seed_ptr=None, colsum=None, split_k=0, c_stride=None,
+          a_img: _Img | None = None, b_img: _Img | None = None, c_img: _Img | None = None) -> None:
     g = _cabi.GemmArgs()
-    g.A, g.B, g.C = A.data_ptr(), B.data_ptr(), Cm.data_ptr()
+    if split_k != 1:
+        ws, counters = _workspace(Cm.device)
+        g.ws, g.counters, g.ws_floats, g.n_counters = ws.data_ptr(), counters.data_ptr(), ws.numel(), counters.numel()
+    g.split_k = split_k
+    g.colsum = colsum.data_ptr() if colsum is not None else None
+    if a_img is not None and b_img is not None:
+        g.a_img, g.a_plane, g.a_rpad = a_img.ptr, a_img.plane, a_img.rpad
+        g.b_img, g.b_plane, g.b_rpad = b_img.ptr, b_img.plane, b_img.rpad
+    else:
+        g.A, g.B = A.data_ptr(), B.data_ptr()
+        g.as0, g.as1 = a_strides
+        g.bs0, g.bs1 = b_strides
+    if c_img is not None:
+        g.c_img, g.c_plane, g.c_rpad = c_img.ptr, c_img.plane, c_img.rpad
+    g.C = Cm.data_ptr()
     g.M, g.N, g.K = M, N, K
-    g.as0, g.as1 = a_strides
-    g.bs0, g.bs1 = b_strides
-    g.cs0 = Cm.stride(0)
+    g.cs0 = Cm.stride(0) if c_stride is None else c_stride
     g.beta, g.epilogue = beta, epi
     g.bias = bias.data_ptr() if bias is not None else None
     g.save = save.data_ptr() if save is not None else None
@@ -47,9 +112,10 @@ def _gemm(A, a_strides, B, b_strides, Cm, M, N, K, *, beta=0.0, epi=_cabi.EPI_NO
     _cabi.check(_cabi.lib().bcnf_train_gemm(C.byref(g), dev.index or 0, _stream(dev)), "bcnf_train_gemm")
 
 
-def _colsum(X: torch.Tensor, out: torch.Tensor) -> None:
+def _colsum(X: torch.Tensor, out: torch.Tensor, cols: int | None = None) -> None:
     dev = X.device
-    _cabi.check(_cabi.lib().bcnf_train_colsum(X.data_ptr(), X.shape[0], X.shape[1], X.stride(0), out.data_ptr(), 0.0,
+    _cabi.check(_cabi.lib().bcnf_train_colsum(X.data_ptr(), X.shape[0], X.shape[1] if cols is None else cols, X.stride(0),
+                                              out.data_ptr(), 0.0,
                                               dev.index or 0, _stream(dev)), "bcnf_train_colsum")
 
 
@@ -80,149 +146,293 @@ class _Spec:
         self.seed_ptr = seed_word.data_ptr() if seed_word is not None else None
 
 
-def _mlp_forward(u: torch.Tensor, ws: Sequence[torch.Tensor], bs: Sequence[torch.Tensor], spec: _Spec, li: int,
-                 net: int):
-    """u: (B, din + C) = cat([y_half, h]) (cnf.py:101).  Returns (o, saved activations)."""
-    B = u.shape[0]
-    acts, pres = [u], []
-    for l in range(len(ws) - 1):
-        n_out, n_in = ws[l].shape
-        pre = torch.empty(B, n_out, device=u.device)
-        out = torch.empty(B, n_out, device=u.device)
-        x = acts[-1]
-        # out = dropout(gelu(x W^T + b)): nn.Linear, nn.GELU, nn.Dropout (cnf.py:79-83)
-        _gemm(x, (x.stride(0), 1), ws[l], (1, ws[l].stride(0)), out, B, n_out, n_in, epi=_cabi.EPI_BIAS_GELU_DROP,
-              bias=bs[l], save=pre, seed=spec.seed, uid=layer_uid(li, net, l), p=spec.p_drop, seed_ptr=spec.seed_ptr)
-        pres.append(pre)
-        acts.append(out)
-    n_out, n_in = ws[-1].shape
-    o = torch.empty(B, n_out, device=u.device)
-    x = acts[-1]
-    _gemm(x, (x.stride(0), 1), ws[-1], (1, ws[-1].stride(0)), o, B, n_out, n_in, epi=_cabi.EPI_BIAS, bias=bs[-1])
-    return o, acts, pres
+_N_SIDE = 3      # a weight-gradient GEMM at batch 256 fills ~45 SMs: three of them run side by side
+_SIDE: dict[int, list[torch.cuda.Stream]] = {}
 
 
-def _mlp_backward(do: torch.Tensor, ws, bs, acts, pres, spec: _Spec, li: int, net: int):
-    """Returns (du, [dW...], [db...]) for one conditioner network."""
-    B = do.shape[0]
-    dws, dbs = [None] * len(ws), [None] * len(ws)
-    d_out = do.contiguous()
-    for l in range(len(ws) - 1, -1, -1):
-        n_out, n_in = ws[l].shape
-        x = acts[l]
-        # dW = d_out^T x   (A(i=n, r=m) = d_out[m, n];  B(r=m, j=k) = x[m, k])
-        dw = torch.empty_like(ws[l])
-        _gemm(d_out, (1, d_out.stride(0)), x, (x.stride(0), 1), dw, n_out, n_in, B)
-        db = torch.empty_like(bs[l])
-        _colsum(d_out, db)
-        dws[l], dbs[l] = dw, db
-        # d_in = d_out W  (* gelu'(pre) * mask of the layer below)
-        d_in = torch.empty(B, n_in, device=do.device)
-        if l > 0:
-            _gemm(d_out, (d_out.stride(0), 1), ws[l], (ws[l].stride(0), 1), d_in, B, n_in, n_out,
-                  epi=_cabi.EPI_DGELU_DROP, saved=pres[l - 1], seed=spec.seed, uid=layer_uid(li, net, l - 1), p=spec.p_drop,
-                  seed_ptr=spec.seed_ptr)
+def _side_streams(dev: torch.device) -> list[torch.cuda.Stream]:
+    key = dev.index or 0
+    if key not in _SIDE:
+        _SIDE[key] = [torch.cuda.Stream(device=dev) for _ in range(_N_SIDE)]
+    return _SIDE[key]
+
+
+def _side_stream(dev: torch.device) -> torch.cuda.Stream:
+    return _side_streams(dev)[0]
+
+
+class _Unit:
+    """One conditioner network + the half it transforms + the ActNorm / mixing layers that follow it."""
+
+    def __init__(self, li: int, net: int, w0: int, src0: int, din: int, dst0: int, dout: int) -> None:
+        self.li, self.net, self.w0 = li, net, w0          # w0: index of the network's first weight in the parameter list
+        self.src0, self.din, self.dst0, self.dout = src0, din, dst0, dout
+        self.ops: list[tuple[int, int]] = []              # (glue type, index of its first parameter)
+
+
+def _plan(spec: _Spec) -> tuple[list[tuple[int, int]], list[_Unit]]:
+    """Split model.layers into the glue ops before the first coupling and one _Unit per conditioner network."""
+    D = spec.size
+    da = (D + 1) // 2
+    lead: list[tuple[int, int]] = []
+    units: list[_Unit] = []
+    o = 0
+    for li, kind in enumerate(spec.kinds):
+        if kind == "actnorm":
+            (units[-1].ops if units else lead).append((_cabi.GLUE_ACTNORM, o))
+            o += 2
+        elif kind == "ortho":
+            (units[-1].ops if units else lead).append((_cabi.GLUE_ORTHO, o))
+            o += 1
         else:
-            _gemm(d_out, (d_out.stride(0), 1), ws[l], (ws[l].stride(0), 1), d_in, B, n_in, n_out)
-        d_out = d_in
-    return d_out, dws, dbs
+            # nn_a reads y_a and transforms y_b; nn_b reads z_b and transforms y_a (cnf.py:178-184)
+            units.append(_Unit(li, 0, o, 0, da, da, D - da))
+            o += 2 * spec.n_lin
+            if spec.two_way:
+                units.append(_Unit(li, 1, o, da, D - da, 0, da))
+                o += 2 * spec.n_lin
+    for u in [None] + units:
+        if len(lead if u is None else u.ops) > 4:
+            raise NotImplementedError("more than 4 ActNorm / mixing layers between two coupling layers")
+    return lead, units
+
+
+def _fill_ops(arr: Any, ops: list[tuple[int, int]], params: Sequence[torch.Tensor], saves: list[Any],
+              grads: list[Any] | None) -> int:
+    for k, (typ, po) in enumerate(ops):
+        arr[k].type = typ
+        arr[k].p0 = params[po].data_ptr()
+        if typ == _cabi.GLUE_ACTNORM:
+            arr[k].p1 = params[po + 1].data_ptr()
+            arr[k].save = saves[k].data_ptr()
+            if grads is not None:
+                arr[k].g0, arr[k].g1 = grads[po].data_ptr(), grads[po + 1].data_ptr()
+    return len(ops)
+
+
+def _call(name: str, args: Any, dev: torch.device) -> None:
+    _cabi.check(getattr(_cabi.lib(), name)(C.byref(args), dev.index or 0, _stream(dev)), name)
+
+
+def _pitch(n: int) -> int:
+    return (n + 3) // 4 * 4
 
 
 class _StackFn(torch.autograd.Function):
-    """z, log|det J| = stack(y, h; parameters) with a hand-written backward."""
+    """z, log|det J| = stack(y, h; parameters) with a hand-written backward.
+
+    Per conditioner network the dependency chain is  pre (first Linear on the own half + P) -> hidden GEMMs ->
+    post (last Linear, coupling, following ActNorm / mixing): L + 1 launches forward and backward.  Everything off
+    that chain -- the condition projections P = h W1h^T + b1 of all networks, the weight / bias gradients and the
+    gradient w.r.t. h -- runs on a second stream and only joins at the end.
+    """
 
     @staticmethod
     def forward(ctx, spec: _Spec, y: torch.Tensor, h: torch.Tensor, *params: torch.Tensor):
-        D = spec.size
-        da = (D + 1) // 2
+        D, L = spec.size, spec.n_lin - 1
         y = y.contiguous().float()
         h = h.contiguous().float()
-        B = y.shape[0]
-        ld = torch.zeros(B, device=y.device)
-        saved: list[Any] = []
-        it = iter(params)
-        nets = 2 if spec.two_way else 1
-        for li, kind in enumerate(spec.kinds):
-            if kind == "actnorm":
-                scale, bias = next(it), next(it)
-                saved.append((y,))
-                y = scale * y + bias                                   # cnf.py:349
-                ld = ld + torch.log(torch.abs(scale)).sum()            # cnf.py:350
-            elif kind == "ortho":
-                q = next(it)
-                saved.append(())
-                y = y @ q                                              # cnf.py:335
-            else:
-                per_net = []
-                for net in range(nets):
-                    ws = [next(it) for _ in range(spec.n_lin)]
-                    bs = [next(it) for _ in range(spec.n_lin)]
-                    src = slice(0, da) if net == 0 else slice(da, D)   # nn_a reads y_a, nn_b reads z_b (cnf.py:178, :183)
-                    dst = slice(da, D) if net == 0 else slice(0, da)
-                    u = torch.cat([y[:, src], h], dim=1)               # cnf.py:101
-                    o, acts, pres = _mlp_forward(u, ws, bs, spec, li, net)
-                    half = o.shape[1] // 2
-                    t, ls = o[:, :half], torch.tanh(o[:, half:])       # cnf.py:104, :107
-                    e = torch.exp(ls)
-                    y_dst = y[:, dst]
-                    new = e * y_dst + t                                # cnf.py:179 / :184
-                    ld = ld + ls.sum(dim=1)                            # cnf.py:190, :193
-                    y = torch.cat([y[:, :da], new], 1) if net == 0 else torch.cat([new, y[:, da:]], 1)
-                    per_net.append((acts, pres, ls, e, y_dst))
-                saved.append(tuple(per_net))
-        ctx.spec, ctx.saved_acts, ctx.params = spec, saved, params
-        ctx.h_cols = h.shape[1]
+        B, Cn = y.shape[0], h.shape[1]
+        dev = y.device
+        lead, units = _plan(spec)
+        main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+        ld = torch.zeros(B, device=dev)
+        new = lambda *shape: torch.empty(*shape, device=dev)
+
+        # off the chain, per network: operand images of its parameters (they changed in the last optimizer step), in
+        # the forward (rows = out) and the data-gradient (rows = in) orientation, then the condition projection P
+        side.wait_stream(main)
+        P, p_ready, wimg = [], [], []
+        with torch.cuda.stream(side):
+            h_img = _img(dev, "h", B, Cn)
+            _pack_images([(h, 0, h.stride(0), 1, B, Cn, h_img)], dev)
+            for u in units:
+                ws = params[u.w0: u.w0 + spec.n_lin]
+                w1, b1 = ws[0], params[u.w0 + spec.n_lin]
+                H1, pitch1 = w1.shape[0], w1.stride(0)
+                fwd = [_img(dev, ("wf", w1.data_ptr()), H1, Cn)] + [_img(dev, ("wf", w.data_ptr()), *w.shape) for w in ws[1:L]]
+                bwd = [_img(dev, ("wb", w1.data_ptr()), Cn, H1)] + [_img(dev, ("wb", w.data_ptr()), w.shape[1], w.shape[0]) for w in ws[1:L]]
+                descs = [(w1, u.din, pitch1, 1, H1, Cn, fwd[0]), (w1, u.din, 1, pitch1, Cn, H1, bwd[0])]
+                for l in range(1, L):
+                    w = ws[l]
+                    descs += [(w, 0, w.stride(0), 1, w.shape[0], w.shape[1], fwd[l]), (w, 0, 1, w.stride(0), w.shape[1], w.shape[0], bwd[l])]
+                _pack_images(descs, dev)
+                Pu = new(B, _pitch(H1))
+                _gemm(None, None, None, None, Pu, B, H1, Cn, epi=_cabi.EPI_BIAS, bias=b1, split_k=1, a_img=h_img, b_img=fwd[0])
+                ev = torch.cuda.Event()
+                ev.record(side)
+                P.append(Pu)
+                p_ready.append(ev)
+                wimg.append((fwd, bwd))
+
+        def glue_only(y_in, ops):
+            a = _cabi.TrainPostArgs()
+            y_out, saves = new(B, D), [new(B, D) if t == _cabi.GLUE_ACTNORM else None for t, _ in ops]
+            a.B, a.D = B, D
+            a.y_in, a.y_out, a.ld = y_in.data_ptr(), y_out.data_ptr(), ld.data_ptr()
+            a.n_ops = _fill_ops(a.ops, ops, params, saves, None)
+            _call("bcnf_train_post", a, dev)
+            return y_out, saves
+
+        lead_saves: list[Any] = []
+        if lead:
+            y, lead_saves = glue_only(y, lead)
+        saved_units = []
+        for ui, u in enumerate(units):
+            ws = params[u.w0: u.w0 + spec.n_lin]
+            bs = params[u.w0 + spec.n_lin: u.w0 + 2 * spec.n_lin]
+            widths = [w.shape[0] for w in ws[:-1]]
+            pre = [new(B, _pitch(n)) for n in widths]
+            act = [new(B, _pitch(n)) for n in widths]
+            main.wait_event(p_ready[ui])
+            a = _cabi.TrainPreArgs()
+            a.y, a.y_pitch, a.B, a.D, a.src0, a.din = y.data_ptr(), D, B, D, u.src0, u.din
+            a.W1, a.w1_pitch, a.P, a.p_pitch, a.H = ws[0].data_ptr(), ws[0].stride(0), P[ui].data_ptr(), P[ui].stride(0), widths[0]
+            a.pre, a.act, a.pitch = pre[0].data_ptr(), act[0].data_ptr(), pre[0].stride(0)
+            a.seed, a.layer_uid, a.p_drop, a.seed_ptr = spec.seed, layer_uid(u.li, u.net, 0), spec.p_drop, spec.seed_ptr
+            aimg = [_img(dev, ("act", l & 1), B, widths[l]) for l in range(L)]     # ping-pong scratch along the chain
+            if L > 1:
+                a.act_img, a.img_plane, a.img_rpad = aimg[0].ptr, aimg[0].plane, aimg[0].rpad
+            _call("bcnf_train_pre", a, dev)
+            for l in range(1, L):
+                # act[l] = dropout(gelu(act[l-1] W_l^T + b_l)): nn.Linear, nn.GELU, nn.Dropout (cnf.py:79-83)
+                _gemm(None, None, None, None, act[l], B, widths[l], widths[l - 1],
+                      epi=_cabi.EPI_BIAS_GELU_DROP, bias=bs[l], save=pre[l], seed=spec.seed, uid=layer_uid(u.li, u.net, l),
+                      p=spec.p_drop, seed_ptr=spec.seed_ptr, split_k=1, a_img=aimg[l - 1], b_img=wimg[ui][0][l],
+                      c_img=aimg[l] if l < L - 1 else None)
+            ls, ydst = new(B, u.dout), new(B, u.dout)
+            y_out = new(B, D)
+            op_saves = [new(B, D) if t == _cabi.GLUE_ACTNORM else None for t, _ in u.ops]
+            a = _cabi.TrainPostArgs()
+            a.a, a.a_pitch, a.Wout, a.bout = act[L - 1].data_ptr(), act[L - 1].stride(0), ws[L].data_ptr(), bs[L].data_ptr()
+            a.B, a.D, a.H, a.dst0, a.dout = B, D, widths[L - 1], u.dst0, u.dout
+            a.y_in, a.y_out, a.ld = y.data_ptr(), y_out.data_ptr(), ld.data_ptr()
+            a.ls_save, a.ydst_save = ls.data_ptr(), ydst.data_ptr()
+            a.n_ops = _fill_ops(a.ops, u.ops, params, op_saves, None)
+            _call("bcnf_train_post", a, dev)
+            saved_units.append((y, pre, act, ls, ydst, op_saves))
+            y = y_out
+        main.wait_stream(side)
+        ctx.spec, ctx.params, ctx.h = spec, params, h
+        ctx.plan = (lead, units, lead_saves, saved_units)
+        ctx.wimg = wimg
+        ctx.keep = P
         return y, ld
 
     @staticmethod
     def backward(ctx, dz: torch.Tensor, dld: torch.Tensor):
-        spec, saved, params = ctx.spec, ctx.saved_acts, ctx.params
-        D = spec.size
-        da = (D + 1) // 2
-        nets = 2 if spec.two_way else 1
+        spec, params, h = ctx.spec, ctx.params, ctx.h
+        lead, units, lead_saves, saved_units = ctx.plan
+        D, L = spec.size, spec.n_lin - 1
         dz = dz.contiguous().float()
-        B = dz.shape[0]
-        dld = dld.contiguous().float() if dld is not None else torch.zeros(B, device=dz.device)
-        dh = torch.zeros(B, ctx.h_cols, device=dz.device)
-        grads: list[Any] = [None] * len(params)
-        # parameter offsets per layer, in forward order
-        offs, o = [], 0
-        for kind in spec.kinds:
-            offs.append(o)
-            o += 2 if kind == "actnorm" else 1 if kind == "ortho" else 2 * spec.n_lin * nets
-        for li in range(len(spec.kinds) - 1, -1, -1):
-            kind, po = spec.kinds[li], offs[li]
-            if kind == "actnorm":
-                scale = params[po]
-                (x,) = saved[li]
-                grads[po] = (dz * x).sum(0) + dld.sum() / scale        # d/ds [s x + b] and d/ds sum log|s|
-                grads[po + 1] = dz.sum(0)
-                dz = dz * scale
-            elif kind == "ortho":
-                dz = dz @ params[po].t()                               # Q is frozen (requires_grad False)
-            else:
-                for net in range(nets - 1, -1, -1):
-                    acts, pres, ls, e, y_dst = saved[li][net]
-                    base = po + net * 2 * spec.n_lin
-                    ws = params[base: base + spec.n_lin]
-                    bs = params[base + spec.n_lin: base + 2 * spec.n_lin]
-                    src = slice(0, da) if net == 0 else slice(da, D)
-                    dst = slice(da, D) if net == 0 else slice(0, da)
-                    d_new = dz[:, dst]
-                    dt = d_new
-                    dls = d_new * y_dst * e + dld.unsqueeze(1)         # via z = e*y + t and via log-det
-                    do = torch.cat([dt, dls * (1.0 - ls * ls)], dim=1)  # tanh'
-                    du, dws, dbs = _mlp_backward(do, ws, bs, acts, pres, spec, li, net)
-                    for j in range(spec.n_lin):
-                        grads[base + j] = dws[j]
-                        grads[base + spec.n_lin + j] = dbs[j]
-                    d_src = dz[:, src] + du[:, : src.stop - src.start]
-                    d_dst = d_new * e
-                    dz = torch.cat([d_src, d_dst], 1) if net == 0 else torch.cat([d_dst, d_src], 1)
-                    dh = dh + du[:, src.stop - src.start:]
+        B, Cn = dz.shape[0], h.shape[1]
+        dev = dz.device
+        dld = dld.contiguous().float() if dld is not None else torch.zeros(B, device=dev)
+        main, sides = torch.cuda.current_stream(dev), _side_streams(dev)
+        new = lambda *shape: torch.empty(*shape, device=dev)
         needs = ctx.needs_input_grad
+        grads: list[Any] = [None] * len(params)
+        # every gradient that is accumulated with atomics (ActNorm parameters, fused bias column sums) starts from
+        # zero: one buffer, one fill
+        n_zero = sum(params[po].numel() + params[po + 1].numel() for ops in [lead] + [u.ops for u in units]
+                     for typ, po in ops if typ == _cabi.GLUE_ACTNORM)
+        n_zero += sum(params[u.w0 + spec.n_lin + j].numel() for u in units for j in range(spec.n_lin))
+        zero_buf, zero_at = torch.zeros(n_zero, device=dev), 0
+
+        def zeros_like(t):
+            nonlocal zero_at
+            v = zero_buf[zero_at: zero_at + t.numel()].view(t.shape)
+            zero_at += t.numel()
+            return v
+
+        for ops in [lead] + [u.ops for u in units]:
+            for typ, po in ops:
+                if typ == _cabi.GLUE_ACTNORM:
+                    grads[po], grads[po + 1] = zeros_like(params[po]), zeros_like(params[po + 1])
+        dh = new(B, Cn)
+        keep: list[Any] = []                                 # everything the side streams read stays alive until the join
+        for sd in sides:
+            sd.wait_stream(main)
+        first_dh = True
+        rr = 0
+        for ui in range(len(units) - 1, -1, -1):
+            u = units[ui]
+            y_in, pre, act, ls, ydst, op_saves = saved_units[ui]
+            ws = params[u.w0: u.w0 + spec.n_lin]
+            widths = [w.shape[0] for w in ws[:-1]]
+            no = 2 * u.dout
+            d_pre = [new(B, _pitch(n)) for n in widths]
+            d_o, dz_new = new(B, no), new(B, D)
+            dws = [torch.empty_like(w) for w in ws]
+            dbs = [zeros_like(params[u.w0 + spec.n_lin + j]) for j in range(spec.n_lin)]
+            a = _cabi.TrainPostBwdArgs()
+            a.dz_in, a.dz_out, a.dld = dz.data_ptr(), dz_new.data_ptr(), dld.data_ptr()
+            a.B, a.D, a.H, a.dst0, a.dout = B, D, widths[L - 1], u.dst0, u.dout
+            a.ls_save, a.ydst_save, a.Wout = ls.data_ptr(), ydst.data_ptr(), ws[L].data_ptr()
+            a.pre, a.pitch, a.d_o, a.d_pre = pre[L - 1].data_ptr(), pre[L - 1].stride(0), d_o.data_ptr(), d_pre[L - 1].data_ptr()
+            a.seed, a.layer_uid, a.p_drop, a.seed_ptr = spec.seed, layer_uid(u.li, u.net, L - 1), spec.p_drop, spec.seed_ptr
+            a.n_ops = _fill_ops(a.ops, u.ops, params, op_saves, grads)
+            # images of d pre[l] along the chain: ping-pong scratch, except d pre[0], which the other stream reads later
+            gimg = [_img(dev, ("dpre0", ui), B, widths[0])] + [_img(dev, ("dpre", l & 1), B, widths[l]) for l in range(1, L)]
+            a.dpre_img, a.img_plane, a.img_rpad = gimg[L - 1].ptr, gimg[L - 1].plane, gimg[L - 1].rpad
+            _call("bcnf_train_post_bwd", a, dev)
+            for l in range(L - 1, 0, -1):
+                # d pre[l-1] = (d pre[l] W_l) * gelu'(pre[l-1]) * mask[l-1]; its column sums are the bias gradient of Linear l-1
+                _gemm(None, None, None, None, d_pre[l - 1], B, widths[l - 1], widths[l],
+                      epi=_cabi.EPI_DGELU_DROP, saved=pre[l - 1], seed=spec.seed, uid=layer_uid(u.li, u.net, l - 1),
+                      p=spec.p_drop, seed_ptr=spec.seed_ptr, colsum=dbs[l - 1], split_k=1, a_img=gimg[l],
+                      b_img=ctx.wimg[ui][1][l], c_img=gimg[l - 1])
+            a = _cabi.TrainPreBwdArgs()
+            a.d_pre, a.pitch, a.W1, a.w1_pitch = d_pre[0].data_ptr(), d_pre[0].stride(0), ws[0].data_ptr(), ws[0].stride(0)
+            a.B, a.D, a.H, a.src0, a.din, a.dz = B, D, widths[0], u.src0, u.din, dz_new.data_ptr()
+            _call("bcnf_train_pre_bwd", a, dev)
+            done = torch.cuda.Event()
+            done.record(main)
+            # ---- off the chain: parameter gradients and d h, spread over the side streams ----
+            for sd in sides:
+                sd.wait_event(done)
+            for l in range(L - 1, 0, -1):
+                with torch.cuda.stream(sides[rr % _N_SIDE]):
+                    _gemm(d_pre[l], (1, d_pre[l].stride(0)), act[l - 1], (act[l - 1].stride(0), 1), dws[l], widths[l],
+                          widths[l - 1], B, split_k=1)
+                rr += 1
+            w1g = dws[0]
+            with torch.cuda.stream(sides[rr % _N_SIDE]):
+                # first Linear: columns [din, din + C) against h
+                _gemm(d_pre[0], (1, d_pre[0].stride(0)), h, (h.stride(0), 1), w1g[:, u.din:], widths[0], Cn, B, split_k=1,
+                      c_stride=w1g.stride(0))
+            rr += 1
+            with torch.cuda.stream(sides[0]):
+                _colsum(d_pre[L - 1], dbs[L - 1], cols=widths[L - 1])
+                _colsum(d_o, dbs[L])
+                # dW_L = d_o^T act[L-1]
+                _gemm(d_o, (1, no), act[L - 1], (act[L - 1].stride(0), 1), dws[L], no, widths[L - 1], B, split_k=1)
+                # first Linear: columns [0, din) against the own half of y
+                ys = y_in[:, u.src0:]
+                _gemm(d_pre[0], (1, d_pre[0].stride(0)), ys, (y_in.stride(0), 1), w1g, widths[0], u.din, B, split_k=1,
+                      c_stride=w1g.stride(0))
+                if needs[2]:
+                    _gemm(None, None, None, None, dh, B, Cn, widths[0], beta=0.0 if first_dh else 1.0, split_k=1,
+                          a_img=gimg[0], b_img=ctx.wimg[ui][1][0])
+                    first_dh = False
+            for j in range(spec.n_lin):
+                grads[u.w0 + j] = dws[j]
+                grads[u.w0 + spec.n_lin + j] = dbs[j]
+            keep += [d_pre, d_o, dz]
+            dz = dz_new
+        if lead:
+            dz_new = new(B, D)
+            a = _cabi.TrainPostBwdArgs()
+            a.dz_in, a.dz_out, a.dld, a.B, a.D = dz.data_ptr(), dz_new.data_ptr(), dld.data_ptr(), B, D
+            a.n_ops = _fill_ops(a.ops, lead, params, lead_saves, grads)
+            _call("bcnf_train_post_bwd", a, dev)
+            keep.append(dz)
+            dz = dz_new
+        for sd in sides:
+            main.wait_stream(sd)
+        del keep
         out_params = [g if needs[3 + i] else None for i, g in enumerate(grads)]
-        return (None, dz if needs[1] else None, dh if needs[2] else None, *out_params)
+        return (None, dz if needs[1] else None, dh if needs[2] and not first_dh else None, *out_params)
 
 
 def stack_forward_train(model: Any, y: torch.Tensor, h: torch.Tensor, seed: int | None = None,

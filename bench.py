@@ -228,7 +228,7 @@ def main_train(args, cfg, cfg_key, batch, rank, world, local_rank) -> None:
     if world > 1:
         model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank])
     use_graph = world == 1 and not os.environ.get("BCNF_NO_TRAIN_GRAPH")
-    opt = torch.optim.Adam(model.parameters(), lr=2e-4, capturable=use_graph)
+    opt = torch.optim.Adam(model.parameters(), lr=2e-4, capturable=use_graph, fused=True)
     trainer = bcnf_b200.Trainer(model, opt, cuda_graph=use_graph)
     g = torch.Generator().manual_seed(100 + rank)
     y_host = torch.randn(batch, mk["size"], generator=g).pin_memory()
@@ -275,7 +275,7 @@ def main_train(args, cfg, cfg_key, batch, rank, world, local_rank) -> None:
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload_name, "size": mk["size"], "nested_sizes": mk["nested_sizes"],
                            "n_blocks": mk["n_blocks"], "n_conditions": mk["n_conditions"], "kernel": "train_gemm (fp32 FMA)",
-                           "precision": "fp32", "optimizer": "torch.optim.Adam", "cuda_graph": use_graph, "l2": "weights (195 MB) exceed nothing; "
+                           "precision": "fp32", "optimizer": "torch.optim.Adam(fused=True)", "cuda_graph": use_graph, "l2": "weights (195 MB) exceed nothing; "
                            "each step touches every parameter, gradient and Adam moment",
                            "parallelism": f"data parallel over {world} GPU(s), NCCL all-reduce of gradients via DDP"},
                 "e2e": {"value": world * batch * e2e_steps / (ms_e2e * 1e-3), "unit": unit,

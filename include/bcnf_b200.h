@@ -158,14 +158,116 @@ typedef struct {
   uint32_t layer_uid;
   float p_drop;
   const uint64_t* seed_ptr;  /* optional DEVICE word XORed into seed: lets a captured CUDA graph draw new masks per replay */
+  float* colsum;         /* optional [N]: colsum[j] += sum_i C(i, j) of the values written (atomic; the caller zeroes it):
+                          * the bias gradient of the Linear whose output gradient this GEMM produces */
+  float* ws;             /* optional split-K workspace: ws_floats fp32, all zero on entry, left all zero */
+  uint32_t* counters;    /* optional split-K tile counters: n_counters words, all zero on entry, left all zero */
+  int64_t ws_floats;
+  int32_t n_counters;
+  int32_t split_k;       /* 0: the library decides (only splits when ws and counters are given); 1: never; n > 1: at most n */
+  /* Operand images.  An image of a matrix X (rows x k) is X split into bf16 hi / lo planes, each stored as
+   * [ceil(k/64) chunks][rpad rows][128 bytes], 16-byte units of a row XOR-swizzled by (row & 7), zero outside the
+   * valid extent: the shared-memory operand tile of tcgen05.mma, fetched by TMA bulk copies.  lo plane = base + plane.
+   * With a_img (rows = i, k = r; rpad multiple of 128, >= M rounded up) and b_img (rows = j, k = r; rpad >= N rounded
+   * up to 128) the TMA-fed kernel runs and A / B may be NULL.  c_img: the values written to C are also written as an
+   * image (rows = i, k = j) -- the A operand of the next GEMM of the chain.  Images come from bcnf_img_pack, the
+   * c_img of a previous GEMM, or the act_img / dpre_img outputs of bcnf_train_pre / bcnf_train_post_bwd. */
+  const void* a_img; int64_t a_plane; int32_t a_rpad; int32_t pad0;
+  const void* b_img; int64_t b_plane; int32_t b_rpad; int32_t pad1;
+  void* c_img; int64_t c_plane; int32_t c_rpad; int32_t pad2;
 } bcnf_gemm_args_t;
 
 int bcnf_train_gemm(const bcnf_gemm_args_t* args, int32_t device, void* stream);
+
+/* fp32 matrix -> operand image: X(row, k) = src[row*s_row + k*s_k] for row < rows, k < k (zero elsewhere). */
+typedef struct {
+  const float* src;
+  int64_t s_row, s_k;
+  int32_t rows, k;
+  void* dst;
+  int64_t plane;       /* chunks * rpad * 128 */
+  int32_t rpad;        /* multiple of 32 */
+  int32_t chunks;
+} bcnf_img_pack_desc_t;
+int bcnf_img_pack(const bcnf_img_pack_desc_t* descs, int32_t n, int32_t device, void* stream);
+/* Kernel selection of bcnf_train_gemm, for tests and A/B timing.  bits 0-3: 0 = automatic (tensor cores when the
+ * problem fills a 128-row tile, fp32 FMA for slivers), 1 = fp32 FMA kernel only, 2 = tcgen05 kernel wherever it
+ * is legal; bits 4-11: force the tensor-core tile width BN (32, 64 or 128; 0 = automatic).  Returns the old mode. */
+int bcnf_train_set_gemm_mode(int32_t mode);
+/* Debug aid: bcnf_train_gemm once, synchronously, returning 64 clock64 stamps of CTA (0,0,0) of the tensor-core kernel
+ * (layout: tools/tc_gemm_check.py). */
+int bcnf_train_gemm_trace(const bcnf_gemm_args_t* args, int32_t device, void* stream, int64_t* out64);
 /* out[j] = sum_i X[i*ldx + j] + beta*out[j]   (bias gradients: the sum(0) of autograd's Linear backward) */
 int bcnf_train_colsum(const float* X, int32_t M, int32_t N, int64_t ldx, float* out, float beta, int32_t device, void* stream);
 /* the multiplicative dropout mask (0 or 1/(1-p)) the fused epilogues apply, materialised for tests */
 int bcnf_train_dropout_mask(float* out, int32_t M, int32_t N, uint64_t seed, uint32_t layer_uid, float p_drop,
                             const uint64_t* seed_ptr, int32_t device, void* stream);
+
+/* ---- fused training kernels around the hidden-layer GEMMs (one launch per coupling block and direction) ----------
+ * Reference: ConditionalNestedNeuralNetwork.forward cnf.py:98-107, ConditionalAffineCouplingLayer.forward
+ * cnf.py:165-196, ActNorm.forward cnf.py:348-351, OrthonormalTransformation.forward cnf.py:333-336, and their autograd
+ * backward (trainer.py:268).  All pointers are device pointers, fp32; D <= 64. */
+typedef struct {
+  int32_t type;        /* 0: y = y @ Q (p0 = Q (D, D));  1: ActNorm y = p0 * y + p1, log-det += sum log|p0| */
+  const float* p0;
+  const float* p1;
+  float* save;         /* ActNorm: its input (B, D), written forward, read backward */
+  float* g0;           /* backward, ActNorm: gradient of scale (D), accumulated (the caller zeroes it) */
+  float* g1;           /* backward, ActNorm: gradient of bias (D) */
+} bcnf_glue_op_t;
+
+/* pre = y[:, src0:src0+din] . W1[:, :din]^T + P ;  act = dropout(gelu(pre))     (P = h . W1[:, din:]^T + b1) */
+typedef struct {
+  const float* y; int64_t y_pitch;
+  int32_t B, D, src0, din;
+  const float* W1; int64_t w1_pitch;
+  const float* P; int64_t p_pitch;
+  int32_t H;
+  float* pre; float* act; int64_t pitch;
+  uint64_t seed; uint32_t layer_uid; float p_drop; const uint64_t* seed_ptr;
+  void* act_img; int64_t img_plane; int32_t img_rpad;   /* optional: also write act as an operand image (see bcnf_img_*) */
+} bcnf_train_pre_args_t;
+
+/* o = a . Wout^T + bout; t, log s = o[:dout], tanh(o[dout:]); y[dst] = exp(log s) * y[dst] + t; ld += sum log s;
+ * then the n_ops glue ops that follow the coupling in model.layers.  a == NULL: glue ops only. */
+typedef struct {
+  const float* a; int64_t a_pitch;
+  const float* Wout; const float* bout;
+  int32_t B, D, H, dst0, dout;
+  const float* y_in; float* y_out;
+  float* ld;
+  float* ls_save; float* ydst_save;     /* (B, dout) each, for the backward */
+  int32_t n_ops; bcnf_glue_op_t ops[4];
+} bcnf_train_post_args_t;
+
+/* backward of bcnf_train_post: dz_in, dld -> dz_out (the conditioner path into y[src] is added by
+ * bcnf_train_pre_bwd), d_o (B, 2 dout) and d_pre = (d_o . Wout) * gelu'(pre) * dropout mask of the last hidden layer. */
+typedef struct {
+  const float* dz_in; float* dz_out;
+  const float* dld;
+  int32_t B, D, H, dst0, dout;
+  const float* ls_save; const float* ydst_save;
+  const float* Wout;                    /* NULL: glue ops only */
+  const float* pre; int64_t pitch;
+  float* d_o;
+  float* d_pre;
+  uint64_t seed; uint32_t layer_uid; float p_drop; const uint64_t* seed_ptr;
+  int32_t n_ops; bcnf_glue_op_t ops[4];
+  void* dpre_img; int64_t img_plane; int32_t img_rpad;  /* optional: also write d_pre as an operand image */
+} bcnf_train_post_bwd_args_t;
+
+/* dz[:, src0:src0+din] += d_pre . W1[:, :din] */
+typedef struct {
+  const float* d_pre; int64_t pitch;
+  const float* W1; int64_t w1_pitch;
+  int32_t B, D, H, src0, din;
+  float* dz;
+} bcnf_train_pre_bwd_args_t;
+
+int bcnf_train_pre(const bcnf_train_pre_args_t* args, int32_t device, void* stream);
+int bcnf_train_post(const bcnf_train_post_args_t* args, int32_t device, void* stream);
+int bcnf_train_post_bwd(const bcnf_train_post_bwd_args_t* args, int32_t device, void* stream);
+int bcnf_train_pre_bwd(const bcnf_train_pre_bwd_args_t* args, int32_t device, void* stream);
 
 #ifdef __cplusplus
 }

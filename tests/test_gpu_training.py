@@ -31,41 +31,96 @@ def _model(size, nested, n_blocks, n_cond, dropout, two_way=False, seed=0):
     return model.to(DEV)
 
 
-def test_fused_gemm_epilogues_match_torch():
+@pytest.mark.parametrize("mode,tol", [(1, 2e-6), (2, 2e-5), (2 | (32 << 4), 2e-5), (2 | (128 << 4), 2e-5)],
+                         ids=["fma", "tcgen05", "tcgen05_bn32", "tcgen05_bn128"])
+def test_fused_gemm_epilogues_match_torch(mode, tol):
+    """fp32 FMA kernel: fp32 rounding.  tcgen05 kernel: 3-pass bf16 split, ~2^-17 per product (stated tolerance 2e-5 of
+    max|ref|, fp64 reference)."""
     g = torch.Generator().manual_seed(0)
     B, K, N = 77, 90, 53
     x = torch.randn(B, K, generator=g).to(DEV)
     w = (torch.randn(N, K, generator=g) / 8).to(DEV)
     b = torch.randn(N, generator=g).to(DEV)
-    # forward: bias + gelu + dropout, pre-activation saved
-    pre, out = torch.empty(B, N, device=DEV), torch.empty(B, N, device=DEV)
-    train._gemm(x, (K, 1), w, (1, K), out, B, N, K, epi=_cabi.EPI_BIAS_GELU_DROP, bias=b, save=pre, seed=7, uid=3, p=0.4)
-    mask = train.dropout_mask(B, N, 7, 3, 0.4, DEV)
-    ref_pre = x @ w.t() + b
-    assert torch.allclose(pre, ref_pre, rtol=1e-5, atol=1e-5)
-    assert torch.allclose(out, torch.nn.functional.gelu(ref_pre) * mask, rtol=1e-5, atol=1e-5)
-    keep = (mask > 0).float().mean().item()
-    assert abs(keep - 0.6) < 0.05
-    assert all(v == 0.0 or abs(v - 1 / 0.6) < 1e-6 for v in mask.unique().tolist())
-    # data gradient: (d W) * gelu'(pre) * mask
-    d = torch.randn(B, N, generator=g).to(DEV)
-    pre_in = torch.randn(B, K, generator=g).to(DEV)
-    din = torch.empty(B, K, device=DEV)
-    train._gemm(d, (N, 1), w, (K, 1), din, B, K, N, epi=_cabi.EPI_DGELU_DROP, saved=pre_in, seed=7, uid=9, p=0.4)
-    xg = pre_in.clone().requires_grad_(True)
-    torch.nn.functional.gelu(xg).sum().backward()
-    mask_in = train.dropout_mask(B, K, 7, 9, 0.4, DEV)
-    assert torch.allclose(din, (d @ w) * xg.grad * mask_in, rtol=1e-5, atol=1e-5)
-    # weight gradient and bias gradient
-    dw = torch.empty(N, K, device=DEV)
-    train._gemm(d, (1, N), x, (K, 1), dw, N, K, B)
-    assert torch.allclose(dw, d.t() @ x, rtol=1e-5, atol=1e-4)
-    db = torch.empty(N, device=DEV)
-    train._colsum(d, db)
-    assert torch.allclose(db, d.sum(0), rtol=1e-5, atol=1e-5)
-    # beta = 1 accumulates
-    train._gemm(d, (1, N), x, (K, 1), dw, N, K, B, beta=1.0)
-    assert torch.allclose(dw, 2 * (d.t() @ x), rtol=1e-5, atol=2e-4)
+    close = lambda a, ref: rel_err(a.double().cpu().numpy(), ref.double().cpu().numpy()) < tol
+    old = _cabi.lib().bcnf_train_set_gemm_mode(mode)
+    try:
+        # forward: bias + gelu + dropout, pre-activation saved
+        pre, out = torch.empty(B, N, device=DEV), torch.empty(B, N, device=DEV)
+        train._gemm(x, (K, 1), w, (1, K), out, B, N, K, epi=_cabi.EPI_BIAS_GELU_DROP, bias=b, save=pre, seed=7, uid=3, p=0.4)
+        mask = train.dropout_mask(B, N, 7, 3, 0.4, DEV)
+        ref_pre = x.double() @ w.double().t() + b.double()
+        assert close(pre, ref_pre)
+        assert close(out, torch.nn.functional.gelu(ref_pre) * mask)
+        keep = (mask > 0).float().mean().item()
+        assert abs(keep - 0.6) < 0.05
+        assert all(v == 0.0 or abs(v - 1 / 0.6) < 1e-6 for v in mask.unique().tolist())
+        # data gradient: (d W) * gelu'(pre) * mask, with the column sums of the result (bias gradient of the layer below)
+        d = torch.randn(B, N, generator=g).to(DEV)
+        pre_in = torch.randn(B, K, generator=g).to(DEV)
+        din = torch.empty(B, K, device=DEV)
+        cs = torch.zeros(K, device=DEV)
+        train._gemm(d, (N, 1), w, (K, 1), din, B, K, N, epi=_cabi.EPI_DGELU_DROP, saved=pre_in, seed=7, uid=9, p=0.4, colsum=cs)
+        xg = pre_in.double().clone().requires_grad_(True)
+        torch.nn.functional.gelu(xg).sum().backward()
+        mask_in = train.dropout_mask(B, K, 7, 9, 0.4, DEV)
+        ref_din = (d.double() @ w.double()) * xg.grad * mask_in
+        assert close(din, ref_din)
+        assert close(cs, ref_din.sum(0))
+        # weight gradient and bias gradient
+        dw = torch.empty(N, K, device=DEV)
+        train._gemm(d, (1, N), x, (K, 1), dw, N, K, B)
+        assert close(dw, d.double().t() @ x.double())
+        db = torch.empty(N, device=DEV)
+        train._colsum(d, db)
+        assert close(db, d.double().sum(0))
+        # beta = 1 accumulates; split-K (tensor-core kernel) reduces through the workspace and leaves it zeroed
+        train._gemm(d, (1, N), x, (K, 1), dw, N, K, B, beta=1.0)
+        assert close(dw, 2 * (d.double().t() @ x.double()))
+        for _ in range(2):
+            train._gemm(d, (1, N), x, (K, 1), dw, N, K, B, split_k=0)
+            assert close(dw, d.double().t() @ x.double())
+        ws, counters = train._workspace(torch.device(DEV))
+        assert not ws.any() and not counters.any()
+    finally:
+        _cabi.lib().bcnf_train_set_gemm_mode(old)
+
+
+@pytest.mark.parametrize("bn", [32, 64, 128])
+@pytest.mark.parametrize("dims", [(77, 53, 90), (256, 526, 526), (300, 130, 1370)], ids=["ragged", "hidden_layer", "projection"])
+def test_image_gemm_chain_matches_fp64(dims, bn):
+    """TMA-fed tcgen05 GEMM on operand images (bcnf_img_pack -> GEMM with fused epilogue -> c_img -> next GEMM):
+    stated tolerance 2e-5 of max|ref| (3-pass bf16 split), fp64 reference."""
+    B, N, K = dims
+    g = torch.Generator().manual_seed(B + N + K)
+    x = torch.randn(B, K, generator=g).to(DEV)
+    w1 = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    b1 = torch.randn(N, generator=g).to(DEV)
+    w2 = (torch.randn(N, N, generator=g) / N ** 0.5).to(DEV)
+    dev = torch.device(DEV)
+    close = lambda a, ref: rel_err(a.double().cpu().numpy(), ref.double().cpu().numpy()) < 2e-5
+    x_img, w1_img, w2t_img = train._Img(dev, B, K), train._Img(dev, N, K), train._Img(dev, N, N)
+    h_img = train._Img(dev, B, N)
+    # w2t_img: rows = input index of w2, k = output index (the data-gradient orientation)
+    train._pack_images([(x, 0, K, 1, B, K, x_img), (w1, 0, K, 1, N, K, w1_img), (w2, 0, 1, N, N, N, w2t_img)], dev)
+    old = _cabi.lib().bcnf_train_set_gemm_mode(bn << 4)
+    try:
+        pre, act = torch.empty(B, N, device=DEV), torch.empty(B, N, device=DEV)
+        train._gemm(None, None, None, None, act, B, N, K, epi=_cabi.EPI_BIAS_GELU_DROP, bias=b1, save=pre, seed=11, uid=2, p=0.3,
+                    split_k=1, a_img=x_img, b_img=w1_img, c_img=h_img)
+        mask = train.dropout_mask(B, N, 11, 2, 0.3, DEV)
+        ref_pre = x.double() @ w1.double().t() + b1.double()
+        ref_act = torch.nn.functional.gelu(ref_pre) * mask
+        assert close(pre, ref_pre) and close(act, ref_act)
+        # second GEMM reads the image the first one wrote: d = act . w2 (rows of B = columns of w2), with column sums
+        d, cs = torch.empty(B, N, device=DEV), torch.zeros(N, device=DEV)
+        train._gemm(None, None, None, None, d, B, N, N, split_k=1, a_img=h_img, b_img=w2t_img, colsum=cs)
+        ref_d = ref_act @ w2.double()
+        assert close(d, ref_d) and close(cs, ref_d.sum(0))
+        # beta = 1
+        train._gemm(None, None, None, None, d, B, N, N, split_k=1, a_img=h_img, b_img=w2t_img, beta=1.0)
+        assert close(d, 2 * ref_d)
+    finally:
+        _cabi.lib().bcnf_train_set_gemm_mode(old)
 
 
 @pytest.mark.parametrize("shape", [(19, [16] * 3, 4, 24, False, 64), (21, [40, 40], 3, 12, True, 33),
