@@ -1104,6 +1104,24 @@ static_assert(sizeof(bcnf_train_post_args_t) == sizeof(TrainPostArgs), "bcnf_tra
 static_assert(sizeof(bcnf_train_post_bwd_args_t) == sizeof(TrainPostBwdArgs), "bcnf_train_post_bwd_args_t / TrainPostBwdArgs");
 static_assert(sizeof(bcnf_train_pre_bwd_args_t) == sizeof(TrainPreBwdArgs), "bcnf_train_pre_bwd_args_t / TrainPreBwdArgs");
 
+constexpr size_t kGlueSmemBudget = 96 * 1024;   // dynamic shared memory of a glue kernel (parameter tile)
+
+static int glue_allow_smem(const void* kernel, size_t bytes) {
+  if (bytes > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGlueSmemBudget));
+  return BCNF_OK;
+}
+
+// K tile of the last Linear staged in shared memory: the whole matrix when it fits the budget
+// (row_bufs: per-warp staging rows of kt floats next to the tile; pad: extra floats per tile row)
+static int glue_wout_tile(int no, int H, const void* kernel, int row_bufs, int pad, int* kt, size_t* smem) {
+  int t = (H + 31) / 32 * 32;
+  auto bytes = [&](int tt) { return ((size_t)no * (tt + pad) + (size_t)row_bufs * tt) * 4; };
+  while (bytes(t) > kGlueSmemBudget && t > 32) t = (t / 2 + 31) / 32 * 32;
+  *kt = t;
+  *smem = bytes(t);
+  return glue_allow_smem(kernel, *smem);
+}
+
 static int check_glue_dims(const char* what, int B, int D, int H, int half0, int half_n, int n_ops) {
   if (B < 0 || D < 1 || D > 64 || H < 0) return fail(BCNF_E_ARG, "%s: bad size (B=%d D=%d H=%d; D <= 64)", what, B, D, H);
   if (half_n < 0 || half_n > 32 || half0 < 0 || half0 + half_n > D) return fail(BCNF_E_ARG, "%s: bad half [%d, %d) of %d", what, half0, half0 + half_n, D);
@@ -1133,7 +1151,10 @@ extern "C" int bcnf_train_post(const bcnf_train_post_args_t* args, int32_t devic
   CUDA_TRY(cudaSetDevice(device));
   TrainPostArgs a;
   memcpy(&a, args, sizeof(a));
-  train_post_kernel<<<(a.B + kGlueWarps - 1) / kGlueWarps, 32 * kGlueWarps, 0, (cudaStream_t)stream>>>(a);
+  int kt = 0;
+  size_t smem = 0;
+  if (a.a) { if (int rc = glue_wout_tile(2 * a.dout, a.H, (const void*)train_post_kernel, kGlueWarps, 1, &kt, &smem)) return rc; }
+  train_post_kernel<<<(a.B + kGlueWarps - 1) / kGlueWarps, 32 * kGlueWarps, smem, (cudaStream_t)stream>>>(a, kt);
   CUDA_TRY(cudaGetLastError());
   return BCNF_OK;
 }
@@ -1150,7 +1171,10 @@ extern "C" int bcnf_train_post_bwd(const bcnf_train_post_bwd_args_t* args, int32
   CUDA_TRY(cudaSetDevice(device));
   TrainPostBwdArgs a;
   memcpy(&a, args, sizeof(a));
-  train_post_bwd_kernel<<<(a.B + kGlueWarps - 1) / kGlueWarps, 32 * kGlueWarps, 0, (cudaStream_t)stream>>>(a);
+  int kt = 0;
+  size_t smem = 0;
+  if (a.Wout) { if (int rc = glue_wout_tile(2 * a.dout, a.H, (const void*)train_post_bwd_kernel, 0, 0, &kt, &smem)) return rc; }
+  train_post_bwd_kernel<<<(a.B + kGlueWarps - 1) / kGlueWarps, 32 * kGlueWarps, smem, (cudaStream_t)stream>>>(a, kt);
   CUDA_TRY(cudaGetLastError());
   return BCNF_OK;
 }
@@ -1162,7 +1186,12 @@ extern "C" int bcnf_train_pre_bwd(const bcnf_train_pre_bwd_args_t* args, int32_t
   CUDA_TRY(cudaSetDevice(device));
   TrainPreBwdArgs a;
   memcpy(&a, args, sizeof(a));
-  train_pre_bwd_kernel<<<(a.B + kGlueWarps - 1) / kGlueWarps, 32 * kGlueWarps, 0, (cudaStream_t)stream>>>(a);
+  const int wp = a.din > 0 ? a.din : 1;    // lanes = consecutive columns: any pitch is conflict-free
+  int jt = (a.H + 31) / 32 * 32;
+  while (((size_t)jt * wp + (size_t)kGlueWarps * jt) * 4 > kGlueSmemBudget && jt > 32) jt = (jt / 2 + 31) / 32 * 32;
+  const size_t smem = ((size_t)jt * wp + (size_t)kGlueWarps * jt) * 4;
+  if (int rc = glue_allow_smem((const void*)train_pre_bwd_kernel, smem)) return rc;
+  train_pre_bwd_kernel<<<(a.B + kGlueWarps - 1) / kGlueWarps, 32 * kGlueWarps, smem, (cudaStream_t)stream>>>(a, jt, wp);
   CUDA_TRY(cudaGetLastError());
   return BCNF_OK;
 }

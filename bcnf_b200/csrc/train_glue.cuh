@@ -98,10 +98,14 @@ __global__ void __launch_bounds__(128) train_pre_kernel(const TrainPreArgs a) {
   for (int k = 0; k < 32; ++k) w[k] = k < a.din ? __ldg(a.W1 + j * a.w1_pitch + k) : 0.f;
   const unsigned long long seed = a.seed_ptr ? (a.seed ^ *a.seed_ptr) : a.seed;
   const float keep_scale = a.p_drop > 0.f ? 1.0f / (1.0f - a.p_drop) : 1.0f;
+  float pv[kPreRows];
+#pragma unroll
+  for (int r = 0; r < kPreRows; ++r) pv[r] = i0 + r < a.B ? __ldg(a.P + (i0 + r) * a.p_pitch + j) : 0.f;
+#pragma unroll
   for (int r = 0; r < kPreRows; ++r) {
     const int i = i0 + r;
     if (i >= a.B) break;
-    float s = __ldg(a.P + i * a.p_pitch + j);
+    float s = pv[r];
 #pragma unroll
     for (int k = 0; k < 32; ++k) s = fmaf(ys[r][k], w[k], s);
     a.pre[i * a.pitch + j] = s;
@@ -118,6 +122,7 @@ __device__ __forceinline__ void glue_forward(const GlueOp& op, float* yr, float*
   if (op.type == GLUE_ORTHO) {
     for (int j = lane; j < D; j += 32) {
       float s = 0.f;
+#pragma unroll 8
       for (int k = 0; k < D; ++k) s = fmaf(yr[k], __ldg(op.p0 + k * D + j), s);   // y @ Q, cnf.py:335
       tmp[j] = s;
     }
@@ -137,79 +142,88 @@ __device__ __forceinline__ void glue_forward(const GlueOp& op, float* yr, float*
   }
 }
 
-constexpr int kGlueKT = 128;     // K tile of the last Linear staged in shared memory
+// ---- asynchronous staging of small parameter blocks into shared memory: 4-byte cp.async (no alignment
+// requirement beyond the element), every copy of a thread in flight at once, zero fill where !valid ----
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src, bool valid) {
+  const int sz = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// cooperative load of Wout[m, k0 .. k0+KT) for m < no into w_s[m][kk] (zero past H)
-__device__ __forceinline__ void load_wout_tile(float (*w_s)[kGlueKT], const float* __restrict__ Wout, int no, int H, int k0) {
-  // thread = (column kk, row parity): all loads of a thread are independent and issued back to back (8 per batch)
-  const int kk = threadIdx.x & (kGlueKT - 1), m0 = threadIdx.x / kGlueKT;
-  constexpr int MS = 32 * kGlueWarps / kGlueKT;          // rows covered per pass (2)
-  const bool k_ok = k0 + kk < H;
-  const float* src = Wout + k0 + kk;
-#pragma unroll
-  for (int mb = 0; mb < 64; mb += 8 * MS) {
-    if (mb >= no) break;
-    float v[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int m = mb + u * MS + m0;
-      v[u] = (k_ok && m < no) ? __ldg(src + (long long)m * H) : 0.f;
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int m = mb + u * MS + m0;
-      if (m < no) w_s[m][kk] = v[u];
-    }
+// Wout[m, k0 .. k0+kt) for m < no  ->  w_s[m*kt + kk]   (whole matrix when kt >= H: the usual case)
+__device__ __forceinline__ void stage_wout(float* w_s, const float* __restrict__ Wout, int no, int H, int k0, int kt) {
+  for (int e = threadIdx.x; e < no * kt; e += 32 * kGlueWarps) {
+    const int m = e / kt, kk = e - m * kt;
+    const bool ok = k0 + kk < H;
+    cp_async4(w_s + e, Wout + (long long)m * H + (ok ? k0 + kk : 0), ok);
   }
 }
 
-__global__ void __launch_bounds__(32 * kGlueWarps) train_post_kernel(const TrainPostArgs a) {
+extern __shared__ float glue_dyn_smem[];
+
+// stage one row of a (B, pitch) matrix, columns [k0, k0 + kt), into shared memory (zero past H)
+__device__ __forceinline__ void stage_row(float* x_s, const float* __restrict__ row, int H, int k0, int kt, int lane) {
+  for (int kk = lane; kk < kt; kk += 32) {
+    const bool ok = k0 + kk < H;
+    cp_async4(x_s + kk, row + (ok ? k0 + kk : 0), ok);
+  }
+}
+
+// Dynamic shared memory of the post kernels: w_s[no][kt + 1] (odd pitch: lanes = output rows read conflict-free),
+// then one kt-float row buffer per warp.
+__global__ void __launch_bounds__(32 * kGlueWarps) train_post_kernel(const TrainPostArgs a, const int kt) {
   __shared__ float y_s[kGlueWarps][64], t_s[kGlueWarps][64];
-  __shared__ float w_s[64][kGlueKT];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long i = (long long)blockIdx.x * kGlueWarps + warp;
   const bool valid = i < a.B;
+  const int no = 2 * a.dout, wp = kt + 1;
+  float* w_s = glue_dyn_smem;
+  float* x_s = glue_dyn_smem + no * wp + warp * kt;
   float* yr = y_s[warp];
   float* tmp = t_s[warp];
   if (valid) for (int j = lane; j < a.D; j += 32) yr[j] = a.y_in[i * a.D + j];
   __syncwarp();
   float ld = 0.f;
   if (a.a) {
-    // o = a Wout^T + bout: Wout staged tile by tile in shared memory, lanes stride over k, butterfly reduction
-    const int no = 2 * a.dout;
-    float acc[64];
-#pragma unroll
-    for (int m = 0; m < 64; ++m) acc[m] = 0.f;
+    // o = a Wout^T + bout.  Lane m owns outputs m and m + 32: it walks k with x[k] broadcast from shared memory.
     const float* ar = a.a + (valid ? i : 0) * a.a_pitch;
-    for (int k0 = 0; k0 < a.H; k0 += kGlueKT) {
+    const int m0 = lane < no ? lane : 0, m1 = lane + 32 < no ? lane + 32 : 0;
+    float o0a = 0.f, o0b = 0.f, o1a = 0.f, o1b = 0.f;
+    for (int k0 = 0; k0 < a.H; k0 += kt) {
+      if (k0 > 0) __syncthreads();
+      for (int e = threadIdx.x; e < no * kt; e += 32 * kGlueWarps) {
+        const int m = e / kt, kk = e - m * kt;
+        const bool ok = k0 + kk < a.H;
+        cp_async4(w_s + m * wp + kk, a.Wout + (long long)m * a.H + (ok ? k0 + kk : 0), ok);
+      }
+      stage_row(x_s, ar, valid ? a.H : 0, k0, kt, lane);
+      cp_async_wait_all();
       __syncthreads();
-      load_wout_tile(w_s, a.Wout, no, a.H, k0);
-      float x[kGlueKT / 32];
-#pragma unroll
-      for (int t = 0; t < kGlueKT / 32; ++t) { const int k = k0 + lane + 32 * t; x[t] = (valid && k < a.H) ? ar[k] : 0.f; }
-      __syncthreads();
-#pragma unroll
-      for (int t = 0; t < kGlueKT / 32; ++t)
-#pragma unroll
-        for (int m = 0; m < 64; ++m)
-          if (m < no) acc[m] = fmaf(x[t], w_s[m][lane + 32 * t], acc[m]);
-    }
-#pragma unroll
-    for (int m = 0; m < 64; ++m)
-      if (m < no) acc[m] = warp_sum(acc[m]);
-    // lane m < dout owns element m of the transformed half: t = o[m], log s = tanh(o[dout + m])  (cnf.py:104-107)
-    float t = 0.f, s_raw = 0.f;
-#pragma unroll
-    for (int m = 0; m < 64; ++m) {
-      if (m < no) {
-        if (m == lane) t = acc[m];
-        if (m == lane + a.dout) s_raw = acc[m];
+      const float* w0 = w_s + m0 * wp;
+      const float* w1 = w_s + m1 * wp;
+      if (no <= 32) {
+#pragma unroll 4
+        for (int kk = 0; kk < kt; kk += 2) {
+          o0a = fmaf(x_s[kk], w0[kk], o0a);
+          o0b = fmaf(x_s[kk + 1], w0[kk + 1], o0b);
+        }
+      } else {
+#pragma unroll 4
+        for (int kk = 0; kk < kt; kk += 2) {
+          const float xa = x_s[kk], xb = x_s[kk + 1];
+          o0a = fmaf(xa, w0[kk], o0a); o0b = fmaf(xb, w0[kk + 1], o0b);
+          o1a = fmaf(xa, w1[kk], o1a); o1b = fmaf(xb, w1[kk + 1], o1b);
+        }
       }
     }
+    const float o0 = o0a + o0b, o1 = o1a + o1b;      // outputs lane and lane + 32
+    // lane m < dout owns element m of the transformed half: t = o[m], log s = tanh(o[dout + m])  (cnf.py:104-107)
+    const int si = a.dout + lane;                      // index of this lane's s output
+    const float s_lo = __shfl_sync(0xffffffffu, o0, si & 31), s_hi = __shfl_sync(0xffffffffu, o1, si & 31);
     float ls = 0.f;
     if (valid && lane < a.dout) {
-      t += __ldg(a.bout + lane);
-      ls = tanhf(s_raw + __ldg(a.bout + a.dout + lane));
+      const float t = o0 + __ldg(a.bout + lane);
+      ls = tanhf((si < 32 ? s_lo : s_hi) + __ldg(a.bout + si));
       const float yd = yr[a.dst0 + lane];
       a.ls_save[i * a.dout + lane] = ls;
       a.ydst_save[i * a.dout + lane] = yd;
@@ -224,17 +238,21 @@ __global__ void __launch_bounds__(32 * kGlueWarps) train_post_kernel(const Train
   if (lane == 0) a.ld[i] += ld;
 }
 
-__global__ void __launch_bounds__(32 * kGlueWarps) train_post_bwd_kernel(const TrainPostBwdArgs a) {
-  __shared__ float d_s[kGlueWarps][64], t_s[kGlueWarps][64];
+// Dynamic shared memory: w_s[no][kt] (lanes = consecutive k: conflict-free)
+__global__ void __launch_bounds__(32 * kGlueWarps) train_post_bwd_kernel(const TrainPostBwdArgs a, const int kt) {
+  __shared__ float d_s[kGlueWarps][64], t_s[kGlueWarps][64], do_s[kGlueWarps][64];
   __shared__ float red_s[2][kGlueMaxOps][64];       // block-level partial sums of the ActNorm parameter gradients
-  __shared__ float w_s[64][kGlueKT];
+  float* w_s = glue_dyn_smem;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long i = (long long)blockIdx.x * kGlueWarps + warp;
   const bool valid = i < a.B;
+  const int no = 2 * a.dout;
+  if (a.Wout) stage_wout(w_s, a.Wout, no, a.H, 0, kt);
   for (int e = threadIdx.x; e < 2 * kGlueMaxOps * 64; e += blockDim.x) (&red_s[0][0][0])[e] = 0.f;
   __syncthreads();
   float* dr = d_s[warp];
   float* tmp = t_s[warp];
+  float* dov = do_s[warp];
   const float dld = valid ? a.dld[i] : 0.f;
   if (valid) {
     for (int j = lane; j < a.D; j += 32) dr[j] = a.dz_in[i * a.D + j];
@@ -244,6 +262,7 @@ __global__ void __launch_bounds__(32 * kGlueWarps) train_post_bwd_kernel(const T
       if (op.type == GLUE_ORTHO) {
         for (int k = lane; k < a.D; k += 32) {
           float s = 0.f;
+#pragma unroll 8
           for (int j = 0; j < a.D; ++j) s = fmaf(dr[j], __ldg(op.p0 + k * a.D + j), s);   // dz @ Q^T
           tmp[k] = s;
         }
@@ -263,45 +282,50 @@ __global__ void __launch_bounds__(32 * kGlueWarps) train_post_bwd_kernel(const T
     }
   }
   if (a.Wout) {
-    const int no = 2 * a.dout;
-    // affine update and tanh backward; lane m < dout owns element m
-    float dt = 0.f, dso = 0.f;
+    // affine update and tanh backward; lane m < dout owns element m; d_o kept in shared memory for the broadcast below
     if (valid && lane < a.dout) {
       const float ls = a.ls_save[i * a.dout + lane], yd = a.ydst_save[i * a.dout + lane];
       const float e = expf(ls), dn = dr[a.dst0 + lane];
-      dt = dn;
-      dso = fmaf(dn * yd, e, dld) * (1.0f - ls * ls);
+      const float dso = fmaf(dn * yd, e, dld) * (1.0f - ls * ls);
       dr[a.dst0 + lane] = dn * e;
-      a.d_o[i * no + lane] = dt;
+      a.d_o[i * no + lane] = dn;
       a.d_o[i * no + a.dout + lane] = dso;
+      dov[lane] = dn;
+      dov[a.dout + lane] = dso;
     }
-    // d a = d_o Wout (Wout staged tile by tile), then gelu'(pre) * dropout mask of the last hidden layer
-    float dov[64];
-#pragma unroll
-    for (int m = 0; m < 64; ++m) {
-      dov[m] = 0.f;
-      if (m < no) dov[m] = m < a.dout ? __shfl_sync(0xffffffffu, dt, m & 31) : __shfl_sync(0xffffffffu, dso, (m - a.dout) & 31);
-    }
+    __syncwarp();
+    // d a = d_o Wout (Wout staged in shared memory), then gelu'(pre) * dropout mask of the last hidden layer
     const unsigned long long seed = a.seed_ptr ? (a.seed ^ *a.seed_ptr) : a.seed;
     const float keep_scale = a.p_drop > 0.f ? 1.0f / (1.0f - a.p_drop) : 1.0f;
-    for (int k0 = 0; k0 < a.H; k0 += kGlueKT) {
-      __syncthreads();
-      load_wout_tile(w_s, a.Wout, no, a.H, k0);
+    for (int k0 = 0; k0 < a.H; k0 += kt) {
+      if (k0 > 0) { __syncthreads(); stage_wout(w_s, a.Wout, no, a.H, k0, kt); }
+      cp_async_wait_all();
       __syncthreads();
       if (!valid) continue;
-#pragma unroll
-      for (int t = 0; t < kGlueKT / 32; ++t) {
-        const int k = k0 + lane + 32 * t;
-        if (k >= a.H) break;
-        float s = 0.f;
-#pragma unroll
-        for (int m = 0; m < 64; ++m)
-          if (m < no) s = fmaf(dov[m], w_s[m][lane + 32 * t], s);
-        s *= dgelu_erf(a.pre[i * a.pitch + k]);
-        if (a.p_drop > 0.f)
-          s = dropout_uniform(seed, a.layer_uid, (unsigned long long)i * (unsigned)a.H + (unsigned)k) >= a.p_drop ? s * keep_scale : 0.f;
-        a.d_pre[i * a.pitch + k] = s;
-        if (a.dpre_img) img_store1(a.dpre_img, a.img_plane, a.img_rpad, (int)i, k, s);
+      for (int kk = lane; kk < kt && k0 + kk < a.H; kk += 64) {
+        // two columns per pass: independent chains
+        const int k = k0 + kk, kb = kk + 32;
+        const bool second = kb < kt && k0 + kb < a.H;
+        const float pre0 = a.pre[i * a.pitch + k], pre1 = second ? a.pre[i * a.pitch + k + 32] : 0.f;
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll 2
+        for (int m = 0; m < no; ++m) {
+          const float dv = dov[m];
+          s0 = fmaf(dv, w_s[m * kt + kk], s0);
+          s1 = fmaf(dv, w_s[m * kt + (second ? kb : kk)], s1);
+        }
+        s0 *= dgelu_erf(pre0);
+        s1 *= dgelu_erf(pre1);
+        if (a.p_drop > 0.f) {
+          s0 = dropout_uniform(seed, a.layer_uid, (unsigned long long)i * (unsigned)a.H + (unsigned)k) >= a.p_drop ? s0 * keep_scale : 0.f;
+          s1 = dropout_uniform(seed, a.layer_uid, (unsigned long long)i * (unsigned)a.H + (unsigned)(k + 32)) >= a.p_drop ? s1 * keep_scale : 0.f;
+        }
+        a.d_pre[i * a.pitch + k] = s0;
+        if (a.dpre_img) img_store1(a.dpre_img, a.img_plane, a.img_rpad, (int)i, k, s0);
+        if (second) {
+          a.d_pre[i * a.pitch + k + 32] = s1;
+          if (a.dpre_img) img_store1(a.dpre_img, a.img_plane, a.img_rpad, (int)i, k + 32, s1);
+        }
       }
     }
   }
@@ -319,49 +343,34 @@ __global__ void __launch_bounds__(32 * kGlueWarps) train_post_bwd_kernel(const T
   }
 }
 
-constexpr int kGlueJT = 128;     // rows of W1[:, :din] staged per tile in train_pre_bwd_kernel
-__global__ void __launch_bounds__(32 * kGlueWarps) train_pre_bwd_kernel(const TrainPreBwdArgs a) {
-  __shared__ float w_s[kGlueJT][33];
+// dz[:, src] += d_pre . W1[:, :din].  Lane k < din owns column k: it walks j with d_pre[j] broadcast from shared memory.
+// Dynamic shared memory: w_s[jt][wp] (the first din columns of W1; lanes = consecutive k), then one jt-float row per warp.
+__global__ void __launch_bounds__(32 * kGlueWarps) train_pre_bwd_kernel(const TrainPreBwdArgs a, const int jt, const int wp) {
+  float* w_s = glue_dyn_smem;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* x_s = glue_dyn_smem + jt * wp + warp * jt;
   const long long i = (long long)blockIdx.x * kGlueWarps + warp;
   const bool valid = i < a.B;
-  float acc[32];
-#pragma unroll
-  for (int k = 0; k < 32; ++k) acc[k] = 0.f;
-  for (int j0 = 0; j0 < a.H; j0 += kGlueJT) {
-    __syncthreads();
-    {
-      // thread = (row jj of the tile, column parity): its loads are independent, issued back to back
-      const int jj = threadIdx.x & (kGlueJT - 1), kq = threadIdx.x / kGlueJT;    // kq in {0, 1}
-      const bool j_ok = j0 + jj < a.H;
-      const float* src = a.W1 + (long long)(j0 + jj) * a.w1_pitch;
-      float v[16];
-#pragma unroll
-      for (int u = 0; u < 16; ++u) { const int k = 2 * u + kq; v[u] = (j_ok && k < a.din) ? __ldg(src + k) : 0.f; }
-#pragma unroll
-      for (int u = 0; u < 16; ++u) w_s[jj][2 * u + kq] = v[u];
+  const float* dr = a.d_pre + (valid ? i : 0) * a.pitch;
+  const int kl = lane < a.din ? lane : 0;
+  float acc0 = 0.f, acc1 = 0.f;
+  for (int j0 = 0; j0 < a.H; j0 += jt) {
+    if (j0 > 0) __syncthreads();
+    for (int e = threadIdx.x; e < jt * a.din; e += 32 * kGlueWarps) {
+      const int jj = e / a.din, k = e - jj * a.din;
+      const bool ok = j0 + jj < a.H;
+      cp_async4(w_s + jj * wp + k, a.W1 + (long long)(ok ? j0 + jj : 0) * a.w1_pitch + k, ok);
     }
+    stage_row(x_s, dr, valid ? a.H : 0, j0, jt, lane);
+    cp_async_wait_all();
     __syncthreads();
-    if (!valid) continue;
-#pragma unroll
-    for (int t = 0; t < kGlueJT / 32; ++t) {
-      const int jj = lane + 32 * t, j = j0 + jj;
-      const float d = j < a.H ? a.d_pre[i * a.pitch + j] : 0.f;
-#pragma unroll
-      for (int k = 0; k < 32; ++k)
-        if (k < a.din) acc[k] = fmaf(d, w_s[jj][k], acc[k]);
+#pragma unroll 4
+    for (int jj = 0; jj < jt; jj += 2) {
+      acc0 = fmaf(x_s[jj], w_s[jj * wp + kl], acc0);
+      acc1 = fmaf(x_s[jj + 1], w_s[(jj + 1) * wp + kl], acc1);
     }
   }
-  if (!valid) return;
-  float mine = 0.f;
-#pragma unroll
-  for (int k = 0; k < 32; ++k) {
-    if (k < a.din) {
-      const float s = warp_sum(acc[k]);
-      if (k == lane) mine = s;
-    }
-  }
-  if (lane < a.din) a.dz[i * a.D + a.src0 + lane] += mine;
+  if (valid && lane < a.din) a.dz[i * a.D + a.src0 + lane] += acc0 + acc1;
 }
 
 }  // namespace bcnf

@@ -64,6 +64,26 @@ __device__ __forceinline__ float dgelu_erf(float x) {
   return fmaf(x, pdf, cdf);
 }
 
+// same derivative with the branch-free erf of gelu_erf_fast (|erf error| <= 1.1e-7) and an ex2-based Gaussian
+__device__ __forceinline__ float dgelu_erf_fast(float x) {
+  const float t = fminf(fabsf(x) * 0.70710678118654752440f, 4.0f);
+  float p = -7.638800192e-07f;
+  p = fmaf(p, t, 1.656447655e-05f);
+  p = fmaf(p, t, -1.540620985e-04f);
+  p = fmaf(p, t, 7.796742463e-04f);
+  p = fmaf(p, t, -2.041655680e-03f);
+  p = fmaf(p, t, -2.589820766e-04f);
+  p = fmaf(p, t, 2.797563118e-02f);
+  p = fmaf(p, t, -1.483925716e-01f);
+  p = fmaf(p, t, -9.184330629e-01f);
+  p = fmaf(p, t, -1.627907331e+00f);
+  float e, gs;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(p * t));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(gs) : "f"(-0.72134752044448170368f * x * x));   // exp(-x^2/2)
+  const float cdf = fmaf(0.5f, copysignf(1.0f - e, x), 0.5f);
+  return fmaf(x * 0.39894228040143267794f, gs, cdf);
+}
+
 template <int BM, int BN>
 __global__ void __launch_bounds__(256)
 train_gemm_kernel(const GemmArgs g) {

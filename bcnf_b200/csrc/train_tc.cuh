@@ -356,8 +356,8 @@ struct ImgArgs {
   float* colsum;
 };
 
-constexpr int kT2EpiWarps = 8;
-constexpr int kT2Threads = 32 * (4 + kT2EpiWarps);   // warp 0 producer, warps 1-3 issuers (one per pass), 8 epilogue warps
+constexpr int kT2EpiWarps = 16;
+constexpr int kT2Threads = 32 * (4 + kT2EpiWarps);   // warp 0 producer, warps 1-3 issuers (one per pass), 16 epilogue warps
 
 template <int BN>
 struct T2Cfg {
@@ -457,16 +457,27 @@ train_tc2_gemm_kernel(const GemmArgs g, const ImgArgs im) {
       umma_commit_1sm(acc_full);
     }
   } else {
-    // ===================== epilogue: lane quarter q = rows q*32.., two warps per quarter split the columns ==========
+    // ===================== epilogue: lane quarter q = rows q*32.., four warps per quarter split the columns ==========
     const int q = warp & 3, part = (warp - 4) >> 2;
-    constexpr int CPP = BN / 2;
+    constexpr int CPP = BN / 4;
     const int row = q * 32 + lane, i = i0 + row;
+    const int jbase = j0 + part * CPP;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(part * CPP);
     const unsigned long long seed = g.seed_ptr ? (g.seed ^ *g.seed_ptr) : g.seed;
     const float keep_scale = g.p_drop > 0.f ? 1.0f / (1.0f - g.p_drop) : 1.0f;
+    // operands of the epilogue are fetched while the main loop runs: bias / saved pre-activations / old C
+    float pf[CPP];
+#pragma unroll
+    for (int c = 0; c < CPP; ++c) {
+      const int j = jbase + c;
+      const bool ok = i < g.M && j < g.N;
+      pf[c] = 0.f;
+      if (g.epi == TEPI_BIAS || g.epi == TEPI_BIAS_GELU_DROP) { if (j < g.N) pf[c] = __ldg(g.bias + j); }
+      else if (g.epi == TEPI_DGELU_DROP) { if (ok) pf[c] = dgelu_erf_fast(__ldg(g.saved + (long long)i * g.cs0 + j)); }
+    }
     mbar_wait(acc_full, 0);
     tc_fence_after();
-#pragma unroll 1
+#pragma unroll
     for (int c = 0; c < CPP; c += 8) {
       uint32_t r0[8], r1[8], r2[8];
       tmem_ld8_issue(taddr + c, r0);
@@ -476,21 +487,21 @@ train_tc2_gemm_kernel(const GemmArgs g, const ImgArgs im) {
       float out[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const int j = j0 + part * CPP + c + e;
+        const int j = jbase + c + e;
         float val = (__uint_as_float(r0[e]) + __uint_as_float(r1[e])) + __uint_as_float(r2[e]);
         if (i < g.M && j < g.N) {
           const long long idx = (long long)i * g.cs0 + j;
           if (g.epi == TEPI_BIAS) {
-            val += __ldg(g.bias + j);
+            val += pf[c + e];
           } else if (g.epi == TEPI_BIAS_GELU_DROP) {
-            val += __ldg(g.bias + j);
+            val += pf[c + e];
             g.save[idx] = val;
-            val = gelu_erf(val);
+            val = gelu_erf_fast(val);
             if (g.p_drop > 0.f)
               val = dropout_uniform(seed, g.layer_uid, (unsigned long long)i * (unsigned)g.N + (unsigned)j) >= g.p_drop
                         ? val * keep_scale : 0.f;
           } else if (g.epi == TEPI_DGELU_DROP) {
-            val *= dgelu_erf(__ldg(g.saved + idx));
+            val *= pf[c + e];
             if (g.p_drop > 0.f)
               val = dropout_uniform(seed, g.layer_uid, (unsigned long long)i * (unsigned)g.N + (unsigned)j) >= g.p_drop
                         ? val * keep_scale : 0.f;
@@ -502,7 +513,7 @@ train_tc2_gemm_kernel(const GemmArgs g, const ImgArgs im) {
         }
         out[e] = val;
       }
-      const int n0 = j0 + part * CPP + c;
+      const int n0 = jbase + c;
       if (im.c_img && i < im.c_rpad && n0 < (im.c_plane / ((long long)im.c_rpad * 128)) * 64)
         img_store8(im.c_img, im.c_plane, im.c_rpad, i, n0, out);
       if (im.colsum) {
@@ -547,12 +558,18 @@ __global__ void __launch_bounds__(kTgGroupThreads) img_pack_kernel(const ImgPack
   const bool k_fast = d.s_k == 1;
   const float* base = d.src + (long long)r0 * d.s_row;
   const int vec = k_fast ? tg_vec_width(base, d.s_row) : 1;
-  for (int kc = 0; kc < d.chunks; ++kc) {
-    float v[1][8];
-    tg_load_regs<32>(v, base + (long long)kc * 64 * d.s_k, d.s_row, d.s_k, d.rows - r0, d.k - kc * 64, t, vec);
-    int row, grp;
-    if (k_fast) { grp = t & 7; row = t >> 3; } else { row = t & 31; grp = t >> 5; }
-    img_store8(d.dst, d.plane, d.rpad, r0 + row, kc * 64 + grp * 8, v[0]);
+  int row, grp;
+  if (k_fast) { grp = t & 7; row = t >> 3; } else { row = t & 31; grp = t >> 5; }
+  // four chunks of loads in flight per thread before the first store
+  for (int kc0 = 0; kc0 < d.chunks; kc0 += 4) {
+    float v[4][1][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (kc0 + u < d.chunks)
+        tg_load_regs<32>(v[u], base + (long long)(kc0 + u) * 64 * d.s_k, d.s_row, d.s_k, d.rows - r0, d.k - (kc0 + u) * 64, t, vec);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (kc0 + u < d.chunks) img_store8(d.dst, d.plane, d.rpad, r0 + row, (kc0 + u) * 64 + grp * 8, v[u][0]);
   }
 }
 

@@ -16,6 +16,7 @@ unchanged on top.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Any, Sequence
 
 import torch
@@ -146,11 +147,16 @@ class _Spec:
         self.seed_ptr = seed_word.data_ptr() if seed_word is not None else None
 
 
-_N_SIDE = 3      # a weight-gradient GEMM at batch 256 fills ~45 SMs: three of them run side by side
-_SIDE: dict[int, list[torch.cuda.Stream]] = {}
+# Work off the dependency chain (condition projections, weight / bias gradients, d h) runs on side streams.  A
+# weight-gradient GEMM at batch 256 fills ~45 SMs and a chain GEMM needs ~34 free ones, so two side streams leave the
+# chain room.  BCNF_TRAIN_SIDE_STREAMS=0 puts everything on the caller's stream (isolated kernel timings).
+_N_SIDE = int(os.environ.get("BCNF_TRAIN_SIDE_STREAMS", "2"))
+_SIDE: dict[int, list[Any]] = {}
 
 
-def _side_streams(dev: torch.device) -> list[torch.cuda.Stream]:
+def _side_streams(dev: torch.device) -> list[Any]:
+    if _N_SIDE <= 0:
+        return [torch.cuda.current_stream(dev)]
     key = dev.index or 0
     if key not in _SIDE:
         _SIDE[key] = [torch.cuda.Stream(device=dev) for _ in range(_N_SIDE)]
@@ -392,12 +398,12 @@ class _StackFn(torch.autograd.Function):
             for sd in sides:
                 sd.wait_event(done)
             for l in range(L - 1, 0, -1):
-                with torch.cuda.stream(sides[rr % _N_SIDE]):
+                with torch.cuda.stream(sides[rr % len(sides)]):
                     _gemm(d_pre[l], (1, d_pre[l].stride(0)), act[l - 1], (act[l - 1].stride(0), 1), dws[l], widths[l],
                           widths[l - 1], B, split_k=1)
                 rr += 1
             w1g = dws[0]
-            with torch.cuda.stream(sides[rr % _N_SIDE]):
+            with torch.cuda.stream(sides[rr % len(sides)]):
                 # first Linear: columns [din, din + C) against h
                 _gemm(d_pre[0], (1, d_pre[0].stride(0)), h, (h.stride(0), 1), w1g[:, u.din:], widths[0], Cn, B, split_k=1,
                       c_stride=w1g.stride(0))

@@ -12,6 +12,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--no-graph", action="store_true")
 ap.add_argument("--config", default="trajectory_TRF_large")
+ap.add_argument("--stack-only", action="store_true", help="coupling stack forward + backward only (no feature network, no optimizer)")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 cfg = bench.load_run_config(args.config)
@@ -25,6 +26,15 @@ trainer = bcnf_b200.Trainer(model, opt, cuda_graph=use_graph)
 mk = cfg["model"]["kwargs"]
 y = torch.randn(args.batch, mk["size"], device=dev)
 c = torch.randn(args.batch, 30, 3, device=dev)
+if args.stack_only:
+    from bcnf_b200 import train as _tr
+    h = torch.randn(args.batch, mk["n_conditions"], device=dev, requires_grad=True)
+
+    class _T:
+        def train_batch(self, y, c):
+            z, ld = _tr.stack_forward_train(model, y, h, seed=1)
+            (0.5 * (z ** 2).sum(1) - ld).mean().backward()
+    trainer = _T()
 for _ in range(4):
     trainer.train_batch(y, c)
 torch.cuda.synchronize()
