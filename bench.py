@@ -225,11 +225,15 @@ def main_train(args, cfg, cfg_key, batch, rank, world, local_rank) -> None:
     perturb_actnorm(model)
     model = model.to(device).train()
     net = model
-    if world > 1:
+    # default: the whole step (incl. the NCCL all-reduce of the flat gradient buffer) is one CUDA graph;
+    # BCNF_TRAIN_DDP=1: eager steps under torch's DistributedDataParallel; BCNF_NO_TRAIN_GRAPH=1: eager steps
+    use_ddp = world > 1 and bool(os.environ.get("BCNF_TRAIN_DDP"))
+    if use_ddp:
         model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank])
-    use_graph = world == 1 and not os.environ.get("BCNF_NO_TRAIN_GRAPH")
+    use_graph = not use_ddp and not os.environ.get("BCNF_NO_TRAIN_GRAPH")
     opt = torch.optim.Adam(model.parameters(), lr=2e-4, capturable=use_graph, fused=True)
-    trainer = bcnf_b200.Trainer(model, opt, cuda_graph=use_graph)
+    trainer = bcnf_b200.Trainer(model, opt, cuda_graph=use_graph,
+                                process_group=dist.group.WORLD if world > 1 and not use_ddp else None)
     g = torch.Generator().manual_seed(100 + rank)
     y_host = torch.randn(batch, mk["size"], generator=g).pin_memory()
     c_host = torch.randn(batch, 30, 3, generator=g).pin_memory()
@@ -274,23 +278,37 @@ def main_train(args, cfg, cfg_key, batch, rank, world, local_rank) -> None:
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload_name, "size": mk["size"], "nested_sizes": mk["nested_sizes"],
-                           "n_blocks": mk["n_blocks"], "n_conditions": mk["n_conditions"], "kernel": "train_gemm (fp32 FMA)",
-                           "precision": "fp32", "optimizer": "torch.optim.Adam(fused=True)", "cuda_graph": use_graph, "l2": "weights (195 MB) exceed nothing; "
+                           "n_blocks": mk["n_blocks"], "n_conditions": mk["n_conditions"],
+                           "kernel": "train_tc2_gemm (tcgen05, TMA-fed bf16 hi/lo operand images) + fused pre/post kernels; "
+                                     "weight gradients train_tc_gemm (tcgen05, fp32 operands)",
+                           "precision": "bf16x3 (3-pass split, fp32 accumulate: fp32-class)", "optimizer": "torch.optim.Adam(fused=True)", "cuda_graph": use_graph, "l2": "weights (195 MB) exceed nothing; "
                            "each step touches every parameter, gradient and Adam moment",
-                           "parallelism": f"data parallel over {world} GPU(s), NCCL all-reduce of gradients via DDP"},
+                           "parallelism": f"data parallel over {world} GPU(s), " + ("torch DistributedDataParallel (eager)" if use_ddp else
+                                           "one NCCL all-reduce of the flat gradient buffer inside the step's CUDA graph")},
                 "e2e": {"value": world * batch * e2e_steps / (ms_e2e * 1e-3), "unit": unit,
                         "h2d_bytes_per_step": (y_host.numel() + c_host.numel()) * 4, "d2h_bytes_per_step": 12,
                         "ms_per_step": ms_e2e / e2e_steps},
-                "gpu_launches": args.steps * n_coupling * (3 * n_lin + n_lin),
+                # per conditioner network: pre, hidden GEMMs, post; post_bwd, data-gradient GEMMs, pre_bwd; weight-gradient
+                # GEMMs, P and d h GEMMs, two column sums, the operand-image pack (bcnf_b200/train.py)
+                "gpu_launches": args.steps * (n_coupling * (4 * (n_lin - 2) + 8) + 3),
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": float(peaks["bf16_tflops"]), "unit": "TFLOP/s",
                              "frac": achieved / float(peaks["bf16_tflops"]), "traffic": None,
-                             "peak_source": f"{peak_src} bf16 dense", "kernel": "train_gemm_kernel (all launches of the step)",
-                             "note": "fp32 FMA GEMMs; at batch 256 the step is launch- and weight-traffic-bound (SURVEY 8d)"},
+                             "peak_source": f"{peak_src} bf16 dense", "kernel": "train_tc2_gemm_kernel / train_tc_gemm_kernel (all launches of the step)",
+                             "note": "algorithmic FLOPs (3 x forward) of the step / step time; at batch 256 the step is a chain of ~310 "
+                                     "dependent launches of ~10 us each plus the PyTorch feature network and Adam (SURVEY 8d: latency-, not "
+                                     "throughput-bound); --instances-per-step 4096 / 32768 shows the tensor-core rate"},
                 "clocks": clocks}
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = oracle_cpu_train_rate(cfg, batch)
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        # the step's CUDA graph holds kernels of the NCCL communicator: release it before the group goes away
+        trainer.close()
+        del trainer
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
 
 
