@@ -19,6 +19,7 @@
 #include "train_ops.cuh"
 #include "train_tc.cuh"
 #include "train_glue.cuh"
+#include "gemm_img2.cuh"
 
 using namespace bcnf;
 
@@ -122,6 +123,13 @@ struct bcnf_flow {
   ProjNet* d_proj_nets = nullptr;
   std::vector<ProjNet> proj_nets;
   std::vector<int> proj_net_layer;   // index in op_types of each conditioner network's coupling layer
+  // CTA-pair GEMM on operand images (gemm_img2.cuh): image of Wproj (rows = projection column, k = condition
+  // feature), rebuilt by set_params, and a scratch image of the h rows of one slice of instances
+  unsigned char* d_wproj_img = nullptr;
+  long long wproj_plane = 0;
+  int wproj_rpad = 0;
+  unsigned char* d_h_img = nullptr;
+  long long h_img_bytes = 0;
 };
 
 static const int kRowThreadChunkCap = 20 * 1024;  // bytes per streamed parameter chunk
@@ -231,6 +239,8 @@ extern "C" int bcnf_flow_destroy(bcnf_flow_t* f) {
   if (f->d_tc_pack) cudaFree(f->d_tc_pack);
   if (f->h_tc_pack) cudaFreeHost(f->h_tc_pack);
   if (f->d_proj_blob) cudaFree(f->d_proj_blob);
+  if (f->d_wproj_img) cudaFree(f->d_wproj_img);
+  if (f->d_h_img) cudaFree(f->d_h_img);
   if (f->d_proj_nets) cudaFree(f->d_proj_nets);
   delete f;
   return BCNF_OK;
@@ -708,9 +718,66 @@ extern "C" int bcnf_flow_set_params(bcnf_flow_t* f, const bcnf_op_params_t* ops,
     CUDA_TRY(cudaMemcpyAsync(f->d_tc_pack, f->h_tc_pack, tv.size() * sizeof(TcPackDesc), cudaMemcpyHostToDevice, stream));
     tc_pack_kernel<<<(unsigned)tv.size(), 256, 0, stream>>>(f->d_tc_pack);
     CUDA_TRY(cudaGetLastError());
+    // image of Wproj for the CTA-pair projection GEMM: rows = projection column j, k = condition feature
+    const int chunks = (sd.C + 63) / 64;
+    f->wproj_rpad = (sd.PW + 255) / 256 * 256;
+    f->wproj_plane = (long long)chunks * f->wproj_rpad * 128;
+    if (!f->d_wproj_img) CUDA_TRY(cudaMalloc(&f->d_wproj_img, (size_t)(2 * f->wproj_plane)));
+    ImgPackBatch batch;
+    ImgPackDesc& d = batch.d[0];
+    d.src = f->d_wproj; d.s_row = 1; d.s_k = sd.PW; d.rows = sd.PW; d.k = sd.C;
+    d.dst = f->d_wproj_img; d.plane = f->wproj_plane; d.rpad = f->wproj_rpad; d.chunks = chunks;
+    img_pack_kernel<<<dim3(f->wproj_rpad / 32, 1), kTgGroupThreads, 0, stream>>>(batch);
+    CUDA_TRY(cudaGetLastError());
   }
   f->params_set = true;
   return BCNF_OK;
+}
+
+template <int NPASS>
+static int launch_gemm_img2(const G2Args& g, int num_sms, cudaStream_t stream) {
+  using Cfg = G2Cfg<NPASS>;
+  auto kern = gemm_img2_kernel<NPASS>;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem));
+  const long long tiles = (long long)((g.M + 255) / 256) * ((g.N + 255) / 256);
+  const int n_kc = (g.K + 63) / 64;
+  if (g.a_rpad % 128 || g.a_rpad < (g.M + 255) / 256 * 256 || g.a_plane < (long long)n_kc * g.a_rpad * 128)
+    return fail(BCNF_E_ARG, "gemm_img2: A image too small (rpad=%d for M=%d: needs a multiple of 256 rows)", g.a_rpad, g.M);
+  if (g.b_rpad % 128 || g.b_rpad < (g.N + 255) / 256 * 256 || g.b_plane < (long long)n_kc * g.b_rpad * 128)
+    return fail(BCNF_E_ARG, "gemm_img2: B image too small (rpad=%d for N=%d: needs a multiple of 256 rows)", g.b_rpad, g.N);
+  const int pairs = (int)std::min<long long>(tiles, num_sms / 2);
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(kG2Threads);
+  cfg.dynamicSmemBytes = Cfg::smem; cfg.stream = stream;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, g));
+  return BCNF_OK;
+}
+
+static void* g_g2_trace = nullptr;
+// debug: device buffer (74 x 16 x 4 uint64) that receives globaltimer stamps of the next bcnf_gemm_img launches
+extern "C" int bcnf_gemm_img_set_trace(void* device_buffer) { g_g2_trace = device_buffer; return BCNF_OK; }
+
+// C = A . B^T (+ bias) on operand images with the CTA-pair kernel (tests, tools)
+extern "C" int bcnf_gemm_img(const void* a_img, int64_t a_plane, int32_t a_rpad, const void* b_img, int64_t b_plane,
+                             int32_t b_rpad, float* C, int64_t ldc, const float* bias, int32_t M, int32_t N, int32_t K,
+                             int32_t passes, int32_t device, void* stream) {
+  if (!a_img || !b_img || !C || M < 0 || N < 0 || K < 1) return fail(BCNF_E_ARG, "bcnf_gemm_img: bad argument");
+  if (passes != 1 && passes != 3) return fail(BCNF_E_ARG, "bcnf_gemm_img: passes must be 1 (bf16) or 3 (bf16x3)");
+  if (M == 0 || N == 0) return BCNF_OK;
+  CUDA_TRY(cudaSetDevice(device));
+  int n_sm = 0;     // (cudaGetDeviceProperties takes milliseconds per call)
+  CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+  G2Args g;
+  g.a_img = (const unsigned char*)a_img; g.a_plane = a_plane; g.a_rpad = a_rpad;
+  g.b_img = (const unsigned char*)b_img; g.b_plane = b_plane; g.b_rpad = b_rpad;
+  g.C = C; g.ldc = ldc; g.bias = bias; g.M = M; g.N = N; g.K = K;
+  g.debug = getenv("BCNF_G2_DEBUG") ? atoi(getenv("BCNF_G2_DEBUG")) : 0;
+  g.trace = (unsigned long long*)g_g2_trace;
+  return passes == 3 ? launch_gemm_img2<3>(g, n_sm, (cudaStream_t)stream) : launch_gemm_img2<1>(g, n_sm, (cudaStream_t)stream);
 }
 
 extern "C" int bcnf_cond_project(bcnf_flow_t* f, const float* h, int64_t n_inst, float* P, void* stream_) {
@@ -720,8 +787,39 @@ extern "C" int bcnf_cond_project(bcnf_flow_t* f, const float* h, int64_t n_inst,
   if (n_inst == 0) return BCNF_OK;
   cudaStream_t stream = (cudaStream_t)stream_;
   CUDA_TRY(cudaSetDevice(f->desc.device));
+  if (f->npass && !getenv("BCNF_PROJ_FMA") && !getenv("BCNF_PROJ_V1")) {
+    // CTA-pair GEMM on operand images, a slice of instances at a time: h -> image (scratch), P = h_img . Wproj_img^T + b
+    const int chunks = (f->sd.C + 63) / 64;
+    const long long slice = 32768;
+    const long long cap_rows = std::min<long long>((n_inst + 255) / 256 * 256, slice);
+    const long long need = 2 * (long long)chunks * cap_rows * 128;
+    if (need > f->h_img_bytes) {
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      if (f->d_h_img) CUDA_TRY(cudaFree(f->d_h_img));
+      f->d_h_img = nullptr; f->h_img_bytes = 0;
+      CUDA_TRY(cudaMalloc(&f->d_h_img, (size_t)need));
+      f->h_img_bytes = need;
+    }
+    for (long long m0 = 0; m0 < n_inst; m0 += slice) {
+      const long long m = std::min<long long>(slice, n_inst - m0);
+      const int rpad = (int)((m + 255) / 256 * 256);
+      const long long plane = (long long)chunks * rpad * 128;
+      ImgPackBatch batch;
+      ImgPackDesc& d = batch.d[0];
+      d.src = h + m0 * f->sd.C; d.s_row = f->sd.C; d.s_k = 1; d.rows = (int)m; d.k = f->sd.C;
+      d.dst = f->d_h_img; d.plane = plane; d.rpad = rpad; d.chunks = chunks;
+      img_pack_kernel<<<dim3(rpad / 32, 1), kTgGroupThreads, 0, stream>>>(batch);
+      CUDA_TRY(cudaGetLastError());
+      G2Args g;
+      g.a_img = f->d_h_img; g.a_plane = plane; g.a_rpad = rpad;
+      g.b_img = f->d_wproj_img; g.b_plane = f->wproj_plane; g.b_rpad = f->wproj_rpad;
+      g.C = P + m0 * f->sd.PW; g.ldc = f->sd.PW; g.bias = f->d_bproj; g.M = (int)m; g.N = f->sd.PW; g.K = f->sd.C; g.debug = 0; g.trace = nullptr;
+      if (int rc = f->npass == 3 ? launch_gemm_img2<3>(g, f->num_sms, stream) : launch_gemm_img2<1>(g, f->num_sms, stream)) return rc;
+    }
+    return BCNF_OK;
+  }
   if (f->npass && !getenv("BCNF_PROJ_FMA")) {
-    // tensor-core projection (same arithmetic mode as the flow kernel of this handle)
+    // previous tensor-core projection kernel (proj_tc.cuh), kept for A/B timing: BCNF_PROJ_V1=1
     auto launch = [&](auto kern) -> int {
       const size_t smem = (size_t)f->pd.smem_bytes;
       if (int rc = opt_in_smem(kern, smem)) return rc;   // both instantiations share this lambda's type: no caching

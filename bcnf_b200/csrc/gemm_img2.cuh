@@ -1,0 +1,221 @@
+// C = A . B^T (+ bias) on operand images, CTA pairs: the throughput GEMM of the package.
+//
+// Used for the condition projection P = h . W1h^T + b1 of every conditioner network at once
+// (torch.cat([y, h]) -> nn.Linear hoisted out of the stack, cnf.py:101-104; 39 % of all MACs of a *_large
+// log-prob evaluation): M = instances, N = sum of padded first-layer widths, K = C.
+//
+// Operands are images (train_tc.cuh: bf16 hi / lo planes, [K/64][rows][128 B], SWIZZLE_128B tile layout), so a
+// producer warp feeds the MMAs with plain bulk copies.  A CTA pair (cluster of 2, tcgen05.mma.cta_group::2)
+// computes 256 x 256 tiles of C: each CTA stages its own 128 rows of A and its half (128 rows) of the B tile
+// (64 KB per stage for the 3-pass split, 3 stages), the leader's issuer thread runs M = 256, N = 256, K = 16 MMAs
+// -- 128 tensor-pipe cycles each, longer than one thread's issue interval, and 64 B/clk of shared-memory operand
+// reads per CTA, the ratio of the large CUTLASS tiles -- into one of two 256-column TMEM accumulators, and eight
+// epilogue warps per CTA drain the other one (lane = row, + bias, fp32 stores) while the next tile's MMAs run.
+// Persistent: pairs walk the tile list round-robin, n fastest, so concurrent pairs share the same rows of A in L2.
+#pragma once
+#include "flow_tc.cuh"
+#include "train_tc.cuh"
+
+namespace bcnf {
+
+constexpr int kG2Stages = 3;
+constexpr int kG2EpiWarps = 8;
+constexpr int kG2Threads = 32 * (4 + kG2EpiWarps);   // warp 0 producer, warp 1 issuer (leader) / relay (peer), 2-3 idle
+constexpr int kG2Tile = 128 * 128;                   // bytes: 128 rows x 64 k, bf16
+
+template <int NPASS>
+struct G2Cfg {
+  static constexpr int planes = NPASS == 3 ? 2 : 1;
+  static constexpr int stage = 2 * planes * kG2Tile;  // A (own 128 rows) + B (own half) per plane
+  static constexpr int bar_off = kG2Stages * stage;
+  static constexpr int smem = bar_off + 256;
+};
+
+struct G2Args {
+  const unsigned char* a_img; long long a_plane; int a_rpad;   // rows = M index, chunks over K
+  const unsigned char* b_img; long long b_plane; int b_rpad;   // rows = N index, chunks over K
+  float* C; long long ldc;
+  const float* bias;        // [N] or null
+  int M, N, K;
+  int debug;                // bit 0: skip the stores of the epilogue (timing experiments)
+  unsigned long long* trace;   // debug: globaltimer stamps [pair][tile (<16)][4] (null in normal runs)
+};
+
+__device__ __forceinline__ unsigned long long g2_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void g2_epi_sync() { asm volatile("bar.sync 2, %0;" ::"n"(32 * kG2EpiWarps) : "memory"); }
+__device__ __forceinline__ uint32_t make_idesc_m256(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+template <int NPASS>
+__global__ void __launch_bounds__(kG2Threads, 1)
+gemm_img2_kernel(const G2Args g) {
+  using Cfg = G2Cfg<NPASS>;
+  extern __shared__ __align__(1024) unsigned char smem_g2[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_g2 + Cfg::bar_off);   // [S] own TMA
+  uint64_t* peer_full = full + 4;                                         // [S] leader: the peer's stage has landed
+  uint64_t* empty = peer_full + 4;                                        // [S] multicast commit
+  uint64_t* acc_full = empty + 4;                                         // [2] multicast commit
+  uint64_t* tmem_empty = acc_full + 2;                                    // [2] leader: both epilogues drained the buffer
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  const uint32_t cta = cluster_ctarank();
+  const bool leader = cta == 0;
+  const int n_kc = (g.K + 63) >> 6;
+  const int tiles_n = (g.N + 255) >> 8, tiles_m = (g.M + 255) >> 8;
+  const long long n_tiles = (long long)tiles_m * tiles_n;
+  const long long n_pairs = gridDim.x >> 1, pair_id = blockIdx.x >> 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < kG2Stages; ++s) { mbar_init(&full[s], 1); mbar_init(&peer_full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&tmem_empty[b], 2); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_s, 0);
+
+  if (warp == 0) {
+    // ===================== producer: own 128 rows of A, own half of the B tile =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long long t = pair_id; t < n_tiles; t += n_pairs) {
+        const int m0 = (int)(t / tiles_n) * 256 + (int)cta * 128, n0 = (int)(t % tiles_n) * 256 + (int)cta * 128;
+        const unsigned char* a_src = g.a_img + (long long)m0 * 128;
+        const unsigned char* b_src = g.b_img + (long long)n0 * 128;
+        for (int kc = 0; kc < n_kc; ++kc, ++it) {
+          const int s = it % kG2Stages;
+          const uint32_t use = it / kG2Stages;
+          if (use > 0) mbar_wait_cluster(&empty[s], (use - 1) & 1);
+          unsigned char* st = smem_g2 + (size_t)s * Cfg::stage;
+          mbar_expect_tx(&full[s], (uint32_t)Cfg::stage);
+          const long long ao = (long long)kc * g.a_rpad * 128, bo = (long long)kc * g.b_rpad * 128;
+          tma_bulk_g2s(st, a_src + ao, kG2Tile, &full[s]);
+          tma_bulk_g2s(st + Cfg::planes * kG2Tile, b_src + bo, kG2Tile, &full[s]);
+          if (NPASS == 3) {
+            tma_bulk_g2s(st + kG2Tile, a_src + g.a_plane + ao, kG2Tile, &full[s]);
+            tma_bulk_g2s(st + 3 * kG2Tile, b_src + g.b_plane + bo, kG2Tile, &full[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (!leader) {
+      // ===================== relay: tell the leader when this CTA's stage has landed =====================
+      // One thread, stages in the order they fill, spinning on test_wait: divergent lanes blocked in try_wait
+      // (a suspending wait) stall each other for the length of the hardware time-out (measured: 10-40x slower runs).
+      if (lane == 0) {
+        long long my_tiles = 0;
+        for (long long t = pair_id; t < n_tiles; t += n_pairs) ++my_tiles;
+        const long long total = my_tiles * n_kc;
+        const uint32_t peer_bar0 = mapa_u32(smem_u32(&peer_full[0]), 0);
+        for (long long it = 0; it < total; ++it) {
+          const int s = (int)(it % kG2Stages);
+          mbar_spin(&full[s], (uint32_t)(it / kG2Stages) & 1u);
+          mbar_arrive_remote(peer_bar0 + 8u * (uint32_t)s);
+        }
+      }
+    } else if (lane == 0) {
+      // ===================== MMA issuer =====================
+      const uint32_t idesc = make_idesc_m256(256);
+      const uint32_t st_addr = smem_u32(smem_g2);
+      uint32_t it = 0, tile_it = 0;
+      for (long long t = pair_id; t < n_tiles; t += n_pairs, ++tile_it) {
+        const uint32_t buf = tile_it & 1u;
+        if (tile_it >= 2) mbar_wait_cluster(&tmem_empty[buf], ((tile_it >> 1) - 1) & 1);
+        tc_fence_after();
+        if (g.trace && tile_it < 16) g.trace[(pair_id * 16 + tile_it) * 4 + 0] = g2_now();
+        const uint32_t acc = tmem_base + buf * 256u;
+        for (int kc = 0; kc < n_kc; ++kc, ++it) {
+          const int s = it % kG2Stages;
+          const uint32_t par = (it / kG2Stages) & 1u;
+          mbar_wait(&full[s], par);
+          mbar_wait_cluster(&peer_full[s], par);
+          tc_fence_after();
+          const int krem = g.K - kc * 64;
+          const int ksteps = krem >= 64 ? 4 : (krem + 15) >> 4;
+          const uint32_t base = st_addr + (uint32_t)s * Cfg::stage;
+          const uint64_t ah = make_smem_desc(base), bh = make_smem_desc(base + Cfg::planes * kG2Tile);
+          const uint64_t al = make_smem_desc(base + kG2Tile), bl = make_smem_desc(base + 3 * kG2Tile);
+          for (int k = 0; k < ksteps; ++k) {
+            umma_2sm(acc, ah + 2 * k, bh + 2 * k, idesc, (kc | k) == 0 ? 0u : 1u);
+            if (NPASS == 3) {
+              umma_2sm(acc, al + 2 * k, bh + 2 * k, idesc, 1u);
+              umma_2sm(acc, ah + 2 * k, bl + 2 * k, idesc, 1u);
+            }
+          }
+          umma_commit_2sm(&empty[s], 3);
+        }
+        umma_commit_2sm(&acc_full[buf], 3);
+        if (g.trace && tile_it < 16) g.trace[(pair_id * 16 + tile_it) * 4 + 1] = g2_now();
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: lane = row of this CTA's 128, two warps per lane quarter x 128 columns ==========
+    const int q = warp & 3, part = (warp - 4) >> 2;
+    const int et = tid - 128;
+    const uint32_t tmem_empty_leader = mapa_u32(smem_u32(tmem_empty), 0);
+    uint32_t tile_it = 0;
+    for (long long t = pair_id; t < n_tiles; t += n_pairs, ++tile_it) {
+      const uint32_t buf = tile_it & 1u;
+      const long long i = (long long)(t / tiles_n) * 256 + (long long)cta * 128 + q * 32 + lane;
+      const int n_base = (int)(t % tiles_n) * 256 + part * 128;
+      mbar_wait_cluster(&acc_full[buf], (tile_it >> 1) & 1);
+      tc_fence_after();
+      if (g.trace && leader && et == 0 && tile_it < 16) g.trace[(pair_id * 16 + tile_it) * 4 + 2] = g2_now();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256u + (uint32_t)(part * 128);
+      float* crow = g.C + i * g.ldc;
+#pragma unroll 1
+      for (int c = 0; c < 128; c += 16) {
+        uint32_t r0[8], r1[8];
+        tmem_ld8_issue(taddr + c, r0);
+        tmem_ld8_issue(taddr + c + 8, r1);
+        tmem_ld_wait();
+        if (i < g.M && !(g.debug & 1)) {
+#pragma unroll
+          for (int h8 = 0; h8 < 2; ++h8) {
+            const uint32_t* r = h8 == 0 ? r0 : r1;
+            const int n = n_base + c + h8 * 8;
+            if (n + 8 <= g.N && (g.ldc & 3) == 0) {
+              float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+              if (g.bias) { b0 = __ldg(reinterpret_cast<const float4*>(g.bias + n)); b1 = __ldg(reinterpret_cast<const float4*>(g.bias + n + 4)); }
+              *reinterpret_cast<float4*>(crow + n) = make_float4(__uint_as_float(r[0]) + b0.x, __uint_as_float(r[1]) + b0.y,
+                                                                 __uint_as_float(r[2]) + b0.z, __uint_as_float(r[3]) + b0.w);
+              *reinterpret_cast<float4*>(crow + n + 4) = make_float4(__uint_as_float(r[4]) + b1.x, __uint_as_float(r[5]) + b1.y,
+                                                                     __uint_as_float(r[6]) + b1.z, __uint_as_float(r[7]) + b1.w);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                if (n + e < g.N) crow[n + e] = __uint_as_float(r[e]) + (g.bias ? __ldg(g.bias + n + e) : 0.f);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      g2_epi_sync();
+      if (et == 0) mbar_arrive_remote(tmem_empty_leader + 8u * buf);
+      if (g.trace && leader && et == 0 && tile_it < 16) g.trace[(pair_id * 16 + tile_it) * 4 + 3] = g2_now();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
+}  // namespace bcnf

@@ -190,6 +190,15 @@ typedef struct {
   int32_t chunks;
 } bcnf_img_pack_desc_t;
 int bcnf_img_pack(const bcnf_img_pack_desc_t* descs, int32_t n, int32_t device, void* stream);
+/* C (M, N; row pitch ldc) = A . B^T (+ bias[N]) on operand images with the CTA-pair kernel (256 x 256 tiles,
+ * tcgen05.mma.cta_group::2): the GEMM behind bcnf_cond_project on tensor-core handles.  a_img: rows = M index,
+ * b_img: rows = N index, both with rpad a multiple of 256 covering M resp. N; passes = 3 (bf16x3) or 1 (bf16). */
+int bcnf_gemm_img(const void* a_img, int64_t a_plane, int32_t a_rpad, const void* b_img, int64_t b_plane, int32_t b_rpad,
+                  float* C, int64_t ldc, const float* bias, int32_t M, int32_t N, int32_t K, int32_t passes,
+                  int32_t device, void* stream);
+/* Debug aid (tools/gemm_img_check.py --trace): device buffer of 74 x 16 x 4 uint64 for the per-tile globaltimer stamps
+ * of the following bcnf_gemm_img launches; NULL switches it off. */
+int bcnf_gemm_img_set_trace(void* device_buffer);
 /* Kernel selection of bcnf_train_gemm, for tests and A/B timing.  bits 0-3: 0 = automatic (tensor cores when the
  * problem fills a 128-row tile, fp32 FMA for slivers), 1 = fp32 FMA kernel only, 2 = tcgen05 kernel wherever it
  * is legal; bits 4-11: force the tensor-core tile width BN (32, 64 or 128; 0 = automatic).  Returns the old mode. */

@@ -1,0 +1,96 @@
+"""CTA-pair GEMM on operand images (csrc/gemm_img2.cuh): error vs fp64 and throughput.
+Usage (GPU box): python tools/gemm_img_check.py"""
+import ctypes as C
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from bcnf_b200 import _cabi, train
+
+DEV = torch.device("cuda:0")
+L = _cabi.lib()
+
+
+class Img256(train._Img):
+    def __init__(self, dev, rows, k):
+        self.rows, self.k = rows, k
+        self.rpad = (rows + 255) // 256 * 256
+        self.chunks = (k + 63) // 64
+        self.plane = self.chunks * self.rpad * 128
+        self.buf = torch.zeros(2 * self.plane, dtype=torch.uint8, device=dev)
+
+
+def run(M, N, K, passes, iters=0):
+    g = torch.Generator().manual_seed(M + N + K)
+    X = torch.randn(M, K, generator=g).to(DEV); W = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    xi, wi = Img256(DEV, M, K), Img256(DEV, N, K)
+    train._pack_images([(X, 0, K, 1, M, K, xi), (W, 0, K, 1, N, K, wi)], DEV)
+    Cm = torch.zeros(M, N, device=DEV)
+    call = lambda: _cabi.check(L.bcnf_gemm_img(xi.ptr, xi.plane, xi.rpad, wi.ptr, wi.plane, wi.rpad, Cm.data_ptr(), N, b.data_ptr(),
+                                               M, N, K, passes, 0, torch.cuda.current_stream().cuda_stream), "bcnf_gemm_img")
+    call(); torch.cuda.synchronize()
+    if M * N * K <= 4e10:
+        ref = X.double() @ W.double().t() + b.double()
+        err = ((Cm.double() - ref).abs().max() / ref.abs().max()).item()
+    else:
+        rows = torch.arange(0, M, max(1, M // 512), device=DEV)
+        ref = X[rows].double() @ W.double().t() + b.double()
+        err = ((Cm[rows].double() - ref).abs().max() / ref.abs().max()).item()
+    ms = None
+    if iters:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(2):
+            call()
+        e0.record()
+        for _ in range(iters):
+            call()
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+    return err, ms
+
+
+def trace(M, N, K, passes):
+    g = torch.Generator().manual_seed(1)
+    X = torch.randn(M, K, generator=g).to(DEV); W = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    xi, wi = Img256(DEV, M, K), Img256(DEV, N, K)
+    train._pack_images([(X, 0, K, 1, M, K, xi), (W, 0, K, 1, N, K, wi)], DEV)
+    Cm = torch.zeros(M, N, device=DEV)
+    buf = torch.zeros(74 * 16 * 4, dtype=torch.int64, device=DEV)
+    call = lambda: _cabi.check(L.bcnf_gemm_img(xi.ptr, xi.plane, xi.rpad, wi.ptr, wi.plane, wi.rpad, Cm.data_ptr(), N, None,
+                                               M, N, K, passes, 0, torch.cuda.current_stream().cuda_stream), "bcnf_gemm_img")
+    for _ in range(3):
+        call()
+    torch.cuda.synchronize()
+    L.bcnf_gemm_img_set_trace(buf.data_ptr())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); call(); e1.record(); torch.cuda.synchronize()
+    L.bcnf_gemm_img_set_trace(None)
+    t = buf.view(74, 16, 4).cpu().numpy().astype("float64")
+    t0 = t[t > 0].min()
+    print(f"--- trace M={M} N={N} K={K} passes={passes}: kernel {e0.elapsed_time(e1) * 1e3:.1f} us; per pair (us since first stamp): "
+          "tile: mma start / mma issued / epilogue start / epilogue end")
+    for p in (0, 1, 37, 73):
+        row = []
+        for k in range(8):
+            if t[p, k, 0] > 0:
+                row.append("/".join(f"{(t[p, k, j] - t0) / 1e3:7.1f}" for j in range(4)))
+        print(f"pair {p:2d}: " + " | ".join(row))
+
+
+if __name__ == "__main__":
+    if "--trace" in sys.argv:
+        trace(32768, 528, 526, 3)
+        trace(16384, 13728, 1360, 3)
+        trace(8192, 8192, 8192, 3)
+        sys.exit(0)
+    quick = "--perf" in sys.argv
+    for M, N, K in ([] if quick else [(300, 700, 90), (256, 256, 64), (1000, 528, 1360), (513, 13728, 1360)]):
+        for passes in (3, 1):
+            err, _ = run(M, N, K, passes)
+            print(f"M={M:6d} N={N:6d} K={K:5d} passes={passes}: rel err {err:.2e}", flush=True)
+    for M, N, K in [(16384, 13728, 1360), (16384, 13728, 5440), (32768, 528, 526), (8192, 8192, 8192)]:
+        for passes in (3, 1):
+            err, ms = run(M, N, K, passes, iters=5)
+            print(f"M={M:6d} N={N:6d} K={K:5d} passes={passes}: rel err {err:.2e}  {ms:8.3f} ms  {2 * M * N * K / ms / 1e9:7.1f} TFLOP/s "
+                  f"(algorithmic; x{passes} executed)", flush=True)
