@@ -84,6 +84,10 @@ def run_img(M, N, K, bn, iters=5):
 
 if __name__ == "__main__":
     DEV = torch.device("cuda:0")
+    if "--ncu" in sys.argv:      # one shape: for ncu --set full -k regex:train_tc2 -s 2 -c 1
+        err, ms = run_img(256, 526, 526, 32, iters=1)
+        print(f"hidden-layer GEMM at batch 256, bn32: rel err {err:.2e}, {ms * 1e3:.1f} us")
+        sys.exit(0)
     print("== TMA-fed image kernel: rel. error vs fp64, us per GEMM (CUDA graph of 20 back-to-back launches) ==")
     for M, N, K in [(256, 526, 526), (256, 526, 1360), (256, 1360, 526), (4096, 526, 526), (32768, 526, 526)]:
         row = []
