@@ -20,6 +20,7 @@
 #include "train_tc.cuh"
 #include "train_glue.cuh"
 #include "gemm_img2.cuh"
+#include "flow_layered.cuh"
 
 using namespace bcnf;
 
@@ -130,7 +131,21 @@ struct bcnf_flow {
   int wproj_rpad = 0;
   unsigned char* d_h_img = nullptr;
   long long h_img_bytes = 0;
+  // layer-by-layer execution (flow_layered.cuh): operand images of the hidden and last Linear of every conditioner
+  // network (forward layer order), and the scratch of one batch of rows
+  struct LwImg { long long off, plane; int rpad; };
+  bool layered_ok = false;
+  unsigned char* d_lw_img = nullptr;
+  long long lw_img_bytes = 0;
+  std::vector<std::vector<LwImg>> lw_img;     // [network][layer 1..L] (index 0 unused)
+  float* d_ly = nullptr;                      // (kLayeredBatch, DP)
+  float* d_lld = nullptr;                     // (kLayeredBatch)
+  float* d_lo = nullptr;                      // (kLayeredBatch, 32)
+  unsigned char* d_lact[2] = {nullptr, nullptr};
+  long long lact_plane = 0;
 };
+
+static const int kLayeredBatch = 74 * 256;    // rows per batch: 74 row tiles x 3 column tiles = 3 full rounds of 74 CTA pairs
 
 static const int kRowThreadChunkCap = 20 * 1024;  // bytes per streamed parameter chunk
 
@@ -240,6 +255,11 @@ extern "C" int bcnf_flow_destroy(bcnf_flow_t* f) {
   if (f->h_tc_pack) cudaFreeHost(f->h_tc_pack);
   if (f->d_proj_blob) cudaFree(f->d_proj_blob);
   if (f->d_wproj_img) cudaFree(f->d_wproj_img);
+  if (f->d_lw_img) cudaFree(f->d_lw_img);
+  if (f->d_ly) cudaFree(f->d_ly);
+  if (f->d_lld) cudaFree(f->d_lld);
+  if (f->d_lo) cudaFree(f->d_lo);
+  for (int b = 0; b < 2; ++b) if (f->d_lact[b]) cudaFree(f->d_lact[b]);
   if (f->d_h_img) cudaFree(f->d_h_img);
   if (f->d_proj_nets) cudaFree(f->d_proj_nets);
   delete f;
@@ -630,6 +650,56 @@ static void emit_tc_half(const bcnf_flow& f, int s, const float* const* w, long 
   }
 }
 
+// Operand images of the hidden and last Linear of every conditioner network for the layer-by-layer path, made from
+// the forward program's fp32 blob (input-major W_l [HP(l-1)][HP(l)]; last Linear [HP(L-1)][2*DOP], t | s halves).
+static int build_layered_images(bcnf_flow* f, cudaStream_t stream) {
+  const StackDims& sd = f->sd;
+  const HalfLayout& hl = sd.half[0];
+  f->layered_ok = f->npass != 0 && !f->desc.two_way && hl.din <= kLgDin && sd.D <= 24 && 2 * hl.dop <= 32;
+  if (!f->layered_ok) return BCNF_OK;
+  const Program& p = f->prog[0];
+  std::vector<const DevOp*> halves;
+  for (const auto& op : p.ops) if (op.type == DOP_HALF) halves.push_back(&op);
+  // layout
+  f->lw_img.assign(halves.size(), std::vector<bcnf_flow::LwImg>(hl.L + 1));
+  long long bytes = 0;
+  for (size_t h = 0; h < halves.size(); ++h)
+    for (int l = 1; l <= hl.L; ++l) {
+      const int rows = l < hl.L ? hl.hp[l] : 2 * hl.dop, k = hl.hp[l - 1];
+      bcnf_flow::LwImg& im = f->lw_img[h][l];
+      im.rpad = (rows + 255) / 256 * 256;
+      im.plane = (long long)((k + 63) / 64) * im.rpad * 128;
+      im.off = bytes;
+      bytes += 2 * im.plane;
+    }
+  if (bytes > f->lw_img_bytes) {
+    if (f->d_lw_img) CUDA_TRY(cudaFree(f->d_lw_img));
+    f->d_lw_img = nullptr; f->lw_img_bytes = 0;
+    CUDA_TRY(cudaMalloc(&f->d_lw_img, (size_t)bytes));
+    f->lw_img_bytes = bytes;
+  }
+  std::vector<ImgPackDesc> descs;
+  for (size_t h = 0; h < halves.size(); ++h)
+    for (int l = 1; l <= hl.L; ++l) {
+      const bcnf_flow::LwImg& im = f->lw_img[h][l];
+      ImgPackDesc d;
+      const int n_out = l < hl.L ? hl.hp[l] : 2 * hl.dop;
+      d.src = p.d_blob + halves[h]->off + (l < hl.L ? hl.off_w[l] : hl.off_wout);
+      d.s_row = 1; d.s_k = n_out; d.rows = n_out; d.k = hl.hp[l - 1];
+      d.dst = f->d_lw_img + im.off; d.plane = im.plane; d.rpad = im.rpad; d.chunks = (hl.hp[l - 1] + 63) / 64;
+      descs.push_back(d);
+    }
+  for (size_t b0 = 0; b0 < descs.size(); b0 += kImgPackMax) {
+    ImgPackBatch batch;
+    const int nb = (int)std::min<size_t>(kImgPackMax, descs.size() - b0);
+    int max_blocks = 0;
+    for (int i = 0; i < nb; ++i) { batch.d[i] = descs[b0 + i]; max_blocks = std::max(max_blocks, descs[b0 + i].rpad / 32); }
+    img_pack_kernel<<<dim3(max_blocks, nb), kTgGroupThreads, 0, stream>>>(batch);
+    CUDA_TRY(cudaGetLastError());
+  }
+  return BCNF_OK;
+}
+
 extern "C" int bcnf_flow_set_params(bcnf_flow_t* f, const bcnf_op_params_t* ops, void* stream_) {
   if (!f || !ops) return fail(BCNF_E_ARG, "bcnf_flow_set_params: null argument");
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -729,6 +799,7 @@ extern "C" int bcnf_flow_set_params(bcnf_flow_t* f, const bcnf_op_params_t* ops,
     d.dst = f->d_wproj_img; d.plane = f->wproj_plane; d.rpad = f->wproj_rpad; d.chunks = chunks;
     img_pack_kernel<<<dim3(f->wproj_rpad / 32, 1), kTgGroupThreads, 0, stream>>>(batch);
     CUDA_TRY(cudaGetLastError());
+    if (int rc = build_layered_images(f, stream)) return rc;
   }
   f->params_set = true;
   return BCNF_OK;
@@ -738,7 +809,13 @@ template <int NPASS>
 static int launch_gemm_img2(const G2Args& g, int num_sms, cudaStream_t stream) {
   using Cfg = G2Cfg<NPASS>;
   auto kern = gemm_img2_kernel<NPASS>;
-  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem));
+  static bool attr_set[64] = {};
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (dev >= 64 || !attr_set[dev]) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem));
+    if (dev < 64) attr_set[dev] = true;
+  }
   const long long tiles = (long long)((g.M + 255) / 256) * ((g.N + 255) / 256);
   const int n_kc = (g.K + 63) / 64;
   if (g.a_rpad % 128 || g.a_rpad < (g.M + 255) / 256 * 256 || g.a_plane < (long long)n_kc * g.a_rpad * 128)
@@ -772,6 +849,7 @@ extern "C" int bcnf_gemm_img(const void* a_img, int64_t a_plane, int32_t a_rpad,
   int n_sm = 0;     // (cudaGetDeviceProperties takes milliseconds per call)
   CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
   G2Args g;
+  memset(&g, 0, sizeof(g));
   g.a_img = (const unsigned char*)a_img; g.a_plane = a_plane; g.a_rpad = a_rpad;
   g.b_img = (const unsigned char*)b_img; g.b_plane = b_plane; g.b_rpad = b_rpad;
   g.C = C; g.ldc = ldc; g.bias = bias; g.M = M; g.N = N; g.K = K;
@@ -811,6 +889,7 @@ extern "C" int bcnf_cond_project(bcnf_flow_t* f, const float* h, int64_t n_inst,
       img_pack_kernel<<<dim3(rpad / 32, 1), kTgGroupThreads, 0, stream>>>(batch);
       CUDA_TRY(cudaGetLastError());
       G2Args g;
+      memset(&g, 0, sizeof(g));
       g.a_img = f->d_h_img; g.a_plane = plane; g.a_rpad = rpad;
       g.b_img = f->d_wproj_img; g.b_plane = f->wproj_plane; g.b_rpad = f->wproj_rpad;
       g.C = P + m0 * f->sd.PW; g.ldc = f->sd.PW; g.bias = f->d_bproj; g.M = (int)m; g.N = f->sd.PW; g.K = f->sd.C; g.debug = 0; g.trace = nullptr;
@@ -924,6 +1003,107 @@ static int launch_tc(bcnf_flow* f, const FlowArgs& a, int dir, cudaStream_t stre
   return BCNF_OK;
 }
 
+// One batch of rows through the stack, layer by layer (flow_layered.cuh).
+template <int NPASS>
+static int run_layered_batch(bcnf_flow* f, int dir, const float* in, const float* P, const int32_t* row2inst,
+                             long long inst_period, long long row_base, int rows, float* out, float* logdet,
+                             cudaStream_t stream) {
+  const StackDims& sd = f->sd;
+  const HalfLayout& hl = sd.half[0];
+  const Program& p = f->prog[dir];
+  const int rpad = (rows + 255) / 256 * 256;
+  int chunks = 1;                                        // every activation image has the widest layer's K chunks
+  for (int l = 0; l < hl.L; ++l) chunks = std::max(chunks, (hl.hp[l] + 63) / 64);
+  int n_half = 0;
+  for (const auto& op : p.ops) n_half += op.type == DOP_HALF;
+  LayeredGlueArgs ga;
+  memset(&ga, 0, sizeof(ga));
+  ga.Y = f->d_ly; ga.LD = f->d_lld; ga.n_rows = rows; ga.row_base = row_base; ga.D = sd.D; ga.DP = sd.DP;
+  ga.P = P; ga.PW = sd.PW; ga.row2inst = row2inst; ga.inst_period = inst_period; ga.passes = NPASS;
+  ga.in = in;
+  const dim3 ggrid((rows + kLgRows - 1) / kLgRows);
+  const size_t glue_smem = (size_t)((hl.hp[0] + 63) / 64) * kLgRows * 128 * (NPASS == 3 ? 2 : 1);
+  static bool glue_attr = false;
+  if (!glue_attr && glue_smem > 48 * 1024) {
+    CUDA_TRY(cudaFuncSetAttribute(flow_layered_glue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    glue_attr = true;
+  }
+  int half_seen = 0;
+  const DevOp* prev = nullptr;
+  auto set_prev = [&]() {
+    if (!prev) { ga.o = nullptr; return; }
+    ga.o = f->d_lo; ga.o_ld = 32;
+    ga.prev_dst0 = prev->src == 0 ? sd.Da : 0; ga.prev_dout = hl.dout; ga.prev_dop = hl.dop; ga.prev_inverse = prev->inverse;
+  };
+  ga.n_ops = 0;
+  for (size_t oi = 0; oi < p.ops.size(); ++oi) {
+    const DevOp& op = p.ops[oi];
+    if (op.type != DOP_HALF) {
+      if (ga.n_ops >= kLgMaxOps) return fail(BCNF_E_UNSUPPORTED, "layered path: more than %d layers between two couplings", kLgMaxOps);
+      ga.op_type[ga.n_ops] = op.type; ga.op_par[ga.n_ops] = p.d_blob + op.off; ++ga.n_ops;
+      continue;
+    }
+    // glue: finish the previous coupling, the ops in between, first Linear of this network -> image 0
+    const int h_fwd = dir == 0 ? half_seen : n_half - 1 - half_seen;     // image table is in forward layer order
+    set_prev();
+    ga.has_next = 1; ga.src0 = op.src == 0 ? 0 : sd.Da; ga.din = hl.din; ga.H1 = hl.h[0]; ga.H1p = hl.hp[0];
+    ga.W1a = p.d_blob + op.off + hl.off_w[0]; ga.proj_off = op.proj_off;
+    const long long act_plane = (long long)chunks * rpad * 128;
+    ga.img = f->d_lact[0]; ga.img_plane = act_plane; ga.img_rpad = rpad;
+    ga.out = nullptr; ga.logdet_out = nullptr;
+    flow_layered_glue_kernel<<<ggrid, kLgThreads, glue_smem, stream>>>(ga);
+    CUDA_TRY(cudaGetLastError());
+    ga.in = nullptr; ga.n_ops = 0;
+    for (int l = 1; l <= hl.L; ++l) {
+      const bcnf_flow::LwImg& wi = f->lw_img[h_fwd][l];
+      G2Args g;
+      memset(&g, 0, sizeof(g));
+      g.a_img = f->d_lact[(l - 1) & 1]; g.a_plane = act_plane; g.a_rpad = rpad;
+      g.b_img = f->d_lw_img + wi.off; g.b_plane = wi.plane; g.b_rpad = wi.rpad;
+      g.M = rows; g.K = hl.hp[l - 1];
+      if (l < hl.L) {
+        g.N = hl.hp[l]; g.bias = p.d_blob + op.off + hl.off_b[l];
+        g.c_img = f->d_lact[l & 1]; g.c_plane = act_plane; g.c_rpad = rpad;
+      } else {
+        g.N = 2 * hl.dop; g.bias = p.d_blob + op.off + hl.off_bout;
+        g.C = f->d_lo; g.ldc = 32;
+      }
+      if (int rc = launch_gemm_img2<NPASS>(g, f->num_sms, stream)) return rc;
+    }
+    prev = &op;
+    ++half_seen;
+  }
+  // last glue: finish the last coupling, trailing ops, write the result
+  set_prev();
+  ga.has_next = 0; ga.out = out; ga.logdet_out = logdet;
+  flow_layered_glue_kernel<<<ggrid, kLgThreads, glue_smem, stream>>>(ga);
+  CUDA_TRY(cudaGetLastError());
+  return BCNF_OK;
+}
+
+static int run_layered(bcnf_flow* f, int dir, const float* in, const float* P, const int32_t* row2inst,
+                       long long inst_period, long long n_rows, float* out, float* logdet, cudaStream_t stream) {
+  const StackDims& sd = f->sd;
+  if (!f->d_ly) {
+    int chunks = 1;
+    for (int l = 0; l < sd.half[0].L; ++l) chunks = std::max(chunks, (sd.half[0].hp[l] + 63) / 64);
+    const long long plane = (long long)chunks * kLayeredBatch * 128;
+    CUDA_TRY(cudaMalloc(&f->d_ly, (size_t)kLayeredBatch * sd.DP * 4));
+    CUDA_TRY(cudaMalloc(&f->d_lld, (size_t)kLayeredBatch * 4));
+    CUDA_TRY(cudaMalloc(&f->d_lo, (size_t)kLayeredBatch * 32 * 4));
+    for (int b = 0; b < 2; ++b) CUDA_TRY(cudaMalloc(&f->d_lact[b], (size_t)(2 * plane)));
+    f->lact_plane = plane;
+  }
+  for (long long r0 = 0; r0 < n_rows; r0 += kLayeredBatch) {
+    const int rows = (int)std::min<long long>(kLayeredBatch, n_rows - r0);
+    const int rc = f->npass == 3
+        ? run_layered_batch<3>(f, dir, in + r0 * sd.D, P, row2inst, inst_period, r0, rows, out + r0 * sd.D, logdet ? logdet + r0 : nullptr, stream)
+        : run_layered_batch<1>(f, dir, in + r0 * sd.D, P, row2inst, inst_period, r0, rows, out + r0 * sd.D, logdet ? logdet + r0 : nullptr, stream);
+    if (rc) return rc;
+  }
+  return BCNF_OK;
+}
+
 static int run_flow(bcnf_flow_t* f, int dir, const float* in, const float* P, const int32_t* row2inst,
                     int64_t inst_period, int64_t n_rows, float* out, float* logdet, void* stream_) {
   if (!f) return fail(BCNF_E_ARG, "bcnf_flow_%s: null handle", dir ? "inverse" : "forward");
@@ -962,8 +1142,12 @@ static int run_flow(bcnf_flow_t* f, int dir, const float* in, const float* P, co
       return rc;
     }
   }
-  if (f->kernel == BCNF_KERNEL_TCGEN05)
+  if (f->kernel == BCNF_KERNEL_TCGEN05) {
+    // layer by layer on the CTA-pair GEMM (BCNF_FLOW_LAYERED=1), or the fused kernel
+    const char* lay = getenv("BCNF_FLOW_LAYERED");
+    if (f->layered_ok && lay && atoi(lay) == 1) return run_layered(f, dir, in, P, row2inst, inst_period, n_rows, out, logdet, stream);
     return f->npass == 3 ? launch_tc<3>(f, a, dir, stream) : launch_tc<1>(f, a, dir, stream);
+  }
   if (f->kernel == BCNF_KERNEL_ROWTHREAD) {
     const int hp = f->sd.half[0].hp[0];
     if (f->sd.D == 19 && hp == 16) return launch_rowthread<19, 16>(f, a, dir, stream);

@@ -27,7 +27,8 @@ template <int NPASS>
 struct G2Cfg {
   static constexpr int planes = NPASS == 3 ? 2 : 1;
   static constexpr int stage = 2 * planes * kG2Tile;  // A (own 128 rows) + B (own half) per plane
-  static constexpr int bar_off = kG2Stages * stage;
+  static constexpr int stg_off = kG2Stages * stage;   // epilogue staging: one 128-row x 64-column chunk, hi and lo plane
+  static constexpr int bar_off = stg_off + 2 * kG2Tile;
   static constexpr int smem = bar_off + 256;
 };
 
@@ -37,6 +38,9 @@ struct G2Args {
   float* C; long long ldc;
   const float* bias;        // [N] or null
   int M, N, K;
+  // epilogue mode 1 (C == null): out = gelu(acc + bias) written as an operand image (rows = M index, k = N index):
+  // the A operand of the next layer's GEMM; columns >= N inside the image are written as zeros
+  unsigned char* c_img; long long c_plane; int c_rpad;
   int debug;                // bit 0: skip the stores of the epilogue (timing experiments)
   unsigned long long* trace;   // debug: globaltimer stamps [pair][tile (<16)][4] (null in normal runs)
 };
@@ -50,6 +54,24 @@ __device__ __forceinline__ void g2_epi_sync() { asm volatile("bar.sync 2, %0;" :
 __device__ __forceinline__ uint32_t make_idesc_m256(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 }
+
+// Tile walk of a CTA pair.  Wide N (the projection): round-robin over the tile list, n fastest, so the pairs running
+// at the same time share rows of A in L2.  Narrow N (a hidden layer: 3 column tiles): a pair owns whole ROW tiles and
+// walks their column tiles back to back, so its 256 rows of A are fetched from L2 by one SM pair three times in a row
+// instead of by three pairs at different times (the activation image of a batch is as large as a third of L2).
+struct G2Walk {
+  long long n_tiles, n_pairs, pair_id;
+  int tiles_m, tiles_n, by_rows;
+  __device__ __forceinline__ long long count() const {
+    if (!by_rows) return pair_id < n_tiles ? (n_tiles - pair_id + n_pairs - 1) / n_pairs : 0;
+    const long long rows = pair_id < tiles_m ? (tiles_m - pair_id + n_pairs - 1) / n_pairs : 0;
+    return rows * tiles_n;
+  }
+  __device__ __forceinline__ void at(long long i, int& m, int& n) const {
+    if (!by_rows) { const long long t = pair_id + i * n_pairs; m = (int)(t / tiles_n); n = (int)(t % tiles_n); }
+    else { m = (int)(pair_id + (i / tiles_n) * n_pairs); n = (int)(i % tiles_n); }
+  }
+};
 
 template <int NPASS>
 __global__ void __launch_bounds__(kG2Threads, 1)
@@ -70,6 +92,10 @@ gemm_img2_kernel(const G2Args g) {
   const int tiles_n = (g.N + 255) >> 8, tiles_m = (g.M + 255) >> 8;
   const long long n_tiles = (long long)tiles_m * tiles_n;
   const long long n_pairs = gridDim.x >> 1, pair_id = blockIdx.x >> 1;
+  G2Walk walk;
+  walk.n_tiles = n_tiles; walk.n_pairs = n_pairs; walk.pair_id = pair_id; walk.tiles_m = tiles_m; walk.tiles_n = tiles_n;
+  walk.by_rows = tiles_n <= 4 && tiles_m >= n_pairs / 2;
+  const long long my_tiles = walk.count();
 
   if (tid == 0) {
     for (int s = 0; s < kG2Stages; ++s) { mbar_init(&full[s], 1); mbar_init(&peer_full[s], 1); mbar_init(&empty[s], 1); }
@@ -90,8 +116,10 @@ gemm_img2_kernel(const G2Args g) {
     // ===================== producer: own 128 rows of A, own half of the B tile =====================
     if (lane == 0) {
       uint32_t it = 0;
-      for (long long t = pair_id; t < n_tiles; t += n_pairs) {
-        const int m0 = (int)(t / tiles_n) * 256 + (int)cta * 128, n0 = (int)(t % tiles_n) * 256 + (int)cta * 128;
+      for (long long ti = 0; ti < my_tiles; ++ti) {
+        int tm, tn;
+        walk.at(ti, tm, tn);
+        const int m0 = tm * 256 + (int)cta * 128, n0 = tn * 256 + (int)cta * 128;
         const unsigned char* a_src = g.a_img + (long long)m0 * 128;
         const unsigned char* b_src = g.b_img + (long long)n0 * 128;
         for (int kc = 0; kc < n_kc; ++kc, ++it) {
@@ -116,8 +144,6 @@ gemm_img2_kernel(const G2Args g) {
       // One thread, stages in the order they fill, spinning on test_wait: divergent lanes blocked in try_wait
       // (a suspending wait) stall each other for the length of the hardware time-out (measured: 10-40x slower runs).
       if (lane == 0) {
-        long long my_tiles = 0;
-        for (long long t = pair_id; t < n_tiles; t += n_pairs) ++my_tiles;
         const long long total = my_tiles * n_kc;
         const uint32_t peer_bar0 = mapa_u32(smem_u32(&peer_full[0]), 0);
         for (long long it = 0; it < total; ++it) {
@@ -131,7 +157,7 @@ gemm_img2_kernel(const G2Args g) {
       const uint32_t idesc = make_idesc_m256(256);
       const uint32_t st_addr = smem_u32(smem_g2);
       uint32_t it = 0, tile_it = 0;
-      for (long long t = pair_id; t < n_tiles; t += n_pairs, ++tile_it) {
+      for (long long ti = 0; ti < my_tiles; ++ti, ++tile_it) {
         const uint32_t buf = tile_it & 1u;
         if (tile_it >= 2) mbar_wait_cluster(&tmem_empty[buf], ((tile_it >> 1) - 1) & 1);
         tc_fence_after();
@@ -167,14 +193,91 @@ gemm_img2_kernel(const G2Args g) {
     const int et = tid - 128;
     const uint32_t tmem_empty_leader = mapa_u32(smem_u32(tmem_empty), 0);
     uint32_t tile_it = 0;
-    for (long long t = pair_id; t < n_tiles; t += n_pairs, ++tile_it) {
+    for (long long ti = 0; ti < my_tiles; ++ti, ++tile_it) {
       const uint32_t buf = tile_it & 1u;
-      const long long i = (long long)(t / tiles_n) * 256 + (long long)cta * 128 + q * 32 + lane;
-      const int n_base = (int)(t % tiles_n) * 256 + part * 128;
+      int tm, tn;
+      walk.at(ti, tm, tn);
+      const long long i = (long long)tm * 256 + (long long)cta * 128 + q * 32 + lane;
+      const int n_base = tn * 256 + part * 128;
       mbar_wait_cluster(&acc_full[buf], (tile_it >> 1) & 1);
       tc_fence_after();
       if (g.trace && leader && et == 0 && tile_it < 16) g.trace[(pair_id * 16 + tile_it) * 4 + 2] = g2_now();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256u + (uint32_t)(part * 128);
+      if (g.c_img) {
+        // ---- gelu(acc + bias) -> bf16 hi/lo image of the next layer's input ----
+        // A lane owns a row, so direct stores would touch 32 different lines per warp instruction (measured: 2 cycles
+        // per 16-byte store, 11-14 us per tile).  The CTA's 128 rows x one 64-column chunk are ONE contiguous 16 KB
+        // block of the image (per plane): stage it in shared memory in image layout and hand it to a bulk store.
+        unsigned char* stg = smem_g2 + Cfg::stg_off;
+        const int c_cols = (int)(g.c_plane / ((long long)g.c_rpad * 128)) * 64;
+        const int row = q * 32 + lane;
+        const long long row0 = (long long)tm * 256 + (long long)cta * 128;
+        const uint32_t tchunk = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256u + (uint32_t)(part * 32);
+        const int n_tile0 = tn * 256;
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          const int nc0 = n_tile0 + cc * 64;                 // first column of this chunk (multiple of 64)
+          if (nc0 >= c_cols) break;
+          uint32_t r[4][8];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) tmem_ld8_issue(tchunk + cc * 64 + u * 8, r[u]);
+          tmem_ld_wait();
+          uint4 hi4[4], lo4[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int n = nc0 + part * 32 + u * 8;
+            f32x2 v[4];
+            if (n + 8 <= g.N) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bias + n + 4));
+              v[0] = gelu_erf_fast2(add2(pack2(__uint_as_float(r[u][0]), __uint_as_float(r[u][1])), pack2(b0.x, b0.y)));
+              v[1] = gelu_erf_fast2(add2(pack2(__uint_as_float(r[u][2]), __uint_as_float(r[u][3])), pack2(b0.z, b0.w)));
+              v[2] = gelu_erf_fast2(add2(pack2(__uint_as_float(r[u][4]), __uint_as_float(r[u][5])), pack2(b1.x, b1.y)));
+              v[3] = gelu_erf_fast2(add2(pack2(__uint_as_float(r[u][6]), __uint_as_float(r[u][7])), pack2(b1.z, b1.w)));
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int na = n + 2 * e, nb = na + 1;
+                const float xa = na < g.N ? gelu_erf_fast(__uint_as_float(r[u][2 * e]) + __ldg(g.bias + na)) : 0.f;
+                const float xb = nb < g.N ? gelu_erf_fast(__uint_as_float(r[u][2 * e + 1]) + __ldg(g.bias + nb)) : 0.f;
+                v[e] = pack2(xa, xb);
+              }
+            }
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float x0, x1;
+              unpack2(v[e], x0, x1);
+              hi[e] = pack_bf16x2(x0, x1);
+              const f32x2 hf = pack2(__uint_as_float(hi[e] << 16), __uint_as_float(hi[e] & 0xffff0000u));
+              float l0, l1;
+              unpack2(add2(v[e], hf ^ 0x8000000080000000ull), l0, l1);
+              lo[e] = pack_bf16x2(l0, l1);
+            }
+            hi4[u] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            lo4[u] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+          // the previous chunk's bulk stores must have read the staging buffers before they are overwritten
+          if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          g2_epi_sync();
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int off = row * 128 + (((part * 4 + u) ^ (row & 7)) << 4);
+            *reinterpret_cast<uint4*>(stg + off) = hi4[u];
+            if (NPASS == 3) *reinterpret_cast<uint4*>(stg + kG2Tile + off) = lo4[u];
+          }
+          fence_proxy_async();
+          g2_epi_sync();
+          if (et == 0) {
+            unsigned char* dst = g.c_img + ((long long)(nc0 >> 6) * g.c_rpad + row0) * 128;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(stg)), "n"(kG2Tile) : "memory");
+            if (NPASS == 3)
+              asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + g.c_plane), "r"(smem_u32(stg + kG2Tile)), "n"(kG2Tile) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+        (void)i;
+      } else {
       float* crow = g.C + i * g.ldc;
 #pragma unroll 1
       for (int c = 0; c < 128; c += 16) {
@@ -202,6 +305,7 @@ gemm_img2_kernel(const G2Args g) {
           }
         }
       }
+      }
       tc_fence_before();
       g2_epi_sync();
       if (et == 0) mbar_arrive_remote(tmem_empty_leader + 8u * buf);
@@ -209,6 +313,7 @@ gemm_img2_kernel(const G2Args g) {
     }
   }
 
+  if (tid == 128) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // epilogue thread 0: its bulk stores are complete
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();

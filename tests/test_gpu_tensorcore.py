@@ -83,6 +83,45 @@ def test_tensorcore_matches_oracle(shape, precision):
             assert errs[k] < tol, (k, errs)
 
 
+LAYERED_SHAPES = [s for s in SHAPES if not s[4]]     # the layer-by-layer schedule covers one-way stacks
+
+
+@pytest.mark.parametrize("shape", LAYERED_SHAPES, ids=lambda s: f"D{s[0]}_H{s[1][0]}x{len(s[1])}_K{s[2]}_C{s[3]}_B{s[5]}")
+def test_layered_schedule_matches_oracle_and_fused_kernel(shape, monkeypatch):
+    """BCNF_FLOW_LAYERED=1: the same stack, one layer at a time on the CTA-pair GEMM (csrc/flow_layered.cuh).  Same
+    arithmetic as the fused kernel (3-pass bf16 split, fp32 elsewhere; the first Linear is exact fp32 FMA here), so
+    the same 1e-5 gate on z and x; the log-det gate is 2e-5 of max|ref| (for a single block the log-det is a sum of
+    nine tanh values of order 0.1, and both schedules sit at ~1e-5 of it)."""
+    size, nested, blocks, n_cond, two_way, rows = shape
+    model = _model(size, nested, blocks, n_cond, "bf16x3", two_way)
+    g = torch.Generator().manual_seed(11)
+    y = torch.randn(rows, size, generator=g)
+    h = torch.randn(rows, n_cond, generator=g)
+    z_in = torch.randn(rows, size, generator=g)
+    z_f = model(y, h, log_det_J=True)
+    ld_f = model.log_det_J
+    x_f = model.inverse(z_in, h)
+    monkeypatch.setenv("BCNF_FLOW_LAYERED", "1")
+    z = model(y, h, log_det_J=True)
+    ld = model.log_det_J
+    x = model.inverse(z_in, h)
+    monkeypatch.delenv("BCNF_FLOW_LAYERED")
+    assert not torch.equal(z, z_f)                   # a different schedule really ran
+    sd = {k: v.cpu().numpy() for k, v in model.state_dict().items()}
+    l32 = fo.layers_from_state_dict(sd)
+    l64 = fo.layers_from_state_dict(sd, convert=lambda v: np.asarray(v, dtype=np.float64))
+    z32, ld32 = fo.stack_forward(l32, y.numpy(), h.numpy())
+    x32 = fo.stack_inverse(l32, z_in.numpy(), h.numpy())
+    z64, _ = fo.stack_forward(l64, y.numpy().astype(np.float64), h.numpy().astype(np.float64))
+    x64 = fo.stack_inverse(l64, z_in.numpy().astype(np.float64), h.numpy().astype(np.float64))
+    assert_parity(z.cpu().numpy(), z32, z64, what="z")
+    assert_parity(x.cpu().numpy(), x32, x64, what="x")
+    assert rel_err(ld.cpu().numpy(), ld32) < 2e-5
+    # and the two schedules agree with each other far inside the gate
+    assert rel_err(z.cpu().numpy(), z_f.cpu().numpy()) < 1e-5 and rel_err(x.cpu().numpy(), x_f.cpu().numpy()) < 1e-5
+    assert rel_err(ld.cpu().numpy(), ld_f.cpu().numpy()) < 2e-5
+
+
 def test_tensorcore_agrees_with_fp32_kernels_on_golden_large_batch():
     # same weights through the FMA kernel and the 3-pass tensor-core kernel, many tiles per CTA pair
     m32 = _model(19, [128] * 3, 4, 32, "fp32")
