@@ -514,8 +514,18 @@ class CondRealNVP_v2(ConditionalInvertibleLayer):
                 "only forward() has a training path -- call .eval() before inverse() / sample()")
 
     def features(self, *conditions: torch.Tensor) -> torch.Tensor:
-        """Condition features h = feature_network_stack(*conditions) on the model's device."""
+        """Condition features h = feature_network_stack(*conditions) on the model's device.
+
+        On tensor-core handles a FullyConnected feature network follows the stack's arithmetic mode in eval mode
+        without autograd (bcnf_b200/feature_tc.py); everything else is the plain PyTorch module.
+        """
         dev = _as_device(self.device)
+        if dev.type == "cuda" and not self.training and not torch.is_grad_enabled():
+            flow = self._flow()
+            passes = {"bf16x3": 3, "bf16": 1}.get(flow.precision, 0) if flow.kernel == "tcgen05" else 0
+            for fn in self.feature_network_stack.feature_networks:
+                if hasattr(fn, "tc_passes"):
+                    fn.tc_passes = passes
         return self.feature_network_stack(*[c.to(dev) for c in conditions])
 
     # -- reference API ------------------------------------------------------------------

@@ -834,6 +834,28 @@ static int launch_gemm_img2(const G2Args& g, int num_sms, cudaStream_t stream) {
   return BCNF_OK;
 }
 
+// gelu(A . B^T + bias) written as an operand image (the A operand of the next Linear): feature MLPs on the tensor cores
+extern "C" int bcnf_gemm_img_gelu(const void* a_img, int64_t a_plane, int32_t a_rpad, const void* b_img, int64_t b_plane,
+                                  int32_t b_rpad, const float* bias, void* c_img, int64_t c_plane, int32_t c_rpad, int32_t M,
+                                  int32_t N, int32_t K, int32_t passes, int32_t device, void* stream) {
+  if (!a_img || !b_img || !c_img || !bias || M < 0 || N < 0 || K < 1) return fail(BCNF_E_ARG, "bcnf_gemm_img_gelu: bad argument");
+  if (passes != 1 && passes != 3) return fail(BCNF_E_ARG, "bcnf_gemm_img_gelu: passes must be 1 (bf16) or 3 (bf16x3)");
+  if (c_rpad % 256 || c_rpad < (M + 255) / 256 * 256 || c_plane % ((long long)c_rpad * 128) || c_plane / ((long long)c_rpad * 128) * 64 < N)
+    return fail(BCNF_E_ARG, "bcnf_gemm_img_gelu: output image too small (rpad=%d plane=%lld for M=%d N=%d)", c_rpad, (long long)c_plane, M, N);
+  if (((uintptr_t)bias & 15) != 0) return fail(BCNF_E_ARG, "bcnf_gemm_img_gelu: bias must be 16-byte aligned");
+  if (M == 0 || N == 0) return BCNF_OK;
+  CUDA_TRY(cudaSetDevice(device));
+  int n_sm = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+  G2Args g;
+  memset(&g, 0, sizeof(g));
+  g.a_img = (const unsigned char*)a_img; g.a_plane = a_plane; g.a_rpad = a_rpad;
+  g.b_img = (const unsigned char*)b_img; g.b_plane = b_plane; g.b_rpad = b_rpad;
+  g.bias = bias; g.M = M; g.N = N; g.K = K;
+  g.c_img = (unsigned char*)c_img; g.c_plane = c_plane; g.c_rpad = c_rpad;
+  return passes == 3 ? launch_gemm_img2<3>(g, n_sm, (cudaStream_t)stream) : launch_gemm_img2<1>(g, n_sm, (cudaStream_t)stream);
+}
+
 static void* g_g2_trace = nullptr;
 // debug: device buffer (74 x 16 x 4 uint64) that receives globaltimer stamps of the next bcnf_gemm_img launches
 extern "C" int bcnf_gemm_img_set_trace(void* device_buffer) { g_g2_trace = device_buffer; return BCNF_OK; }

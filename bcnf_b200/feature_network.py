@@ -109,7 +109,13 @@ class FullyConnectedFeatureNetwork(FeatureNetwork):
                 self.nn.append(nn.Dropout(dropout))
         self.nn.append(nn.Linear(sizes[-2], sizes[-1]))
 
+    tc_passes: int = 0      # set by CondRealNVP_v2 on tensor-core handles: 3 = bf16x3 (fp32-class), 1 = bf16, 0 = PyTorch
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.tc_passes and x.is_cuda and not self.training and not torch.is_grad_enabled():
+            from . import feature_tc
+            if x.size(0) >= feature_tc.MIN_ROWS and feature_tc.supported(self):
+                return feature_tc.forward(self, x, self.tc_passes)
         return self.nn(x.reshape(x.size(0), -1))
 
 

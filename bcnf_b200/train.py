@@ -49,9 +49,9 @@ class _Img:
     planes, [ceil(k/64)][rows padded to 128][128 bytes] each; zero outside the valid extent (allocated zeroed, and
     producers only ever write inside rows x tiles)."""
 
-    def __init__(self, dev: torch.device, rows: int, k: int) -> None:
+    def __init__(self, dev: torch.device, rows: int, k: int, align: int = 128) -> None:
         self.rows, self.k = rows, k
-        self.rpad = (rows + 127) // 128 * 128
+        self.rpad = (rows + align - 1) // align * align          # the CTA-pair GEMM wants multiples of 256 rows
         self.chunks = (k + 63) // 64
         self.plane = self.chunks * self.rpad * 128
         self.buf = torch.zeros(2 * self.plane, dtype=torch.uint8, device=dev)
@@ -64,12 +64,12 @@ class _Img:
 _IMGS: dict[tuple, _Img] = {}
 
 
-def _img(dev: torch.device, tag: Any, rows: int, k: int) -> _Img:
+def _img(dev: torch.device, tag: Any, rows: int, k: int, align: int = 128) -> _Img:
     """Cached scratch image: (device, tag, shape) -> buffer.  Scratch images are reused in stream order."""
-    key = (dev.index or 0, tag, rows, k)
+    key = (dev.index or 0, tag, rows, k, align)
     im = _IMGS.get(key)
     if im is None:
-        im = _IMGS[key] = _Img(dev, rows, k)
+        im = _IMGS[key] = _Img(dev, rows, k, align)
     return im
 
 

@@ -196,6 +196,12 @@ int bcnf_img_pack(const bcnf_img_pack_desc_t* descs, int32_t n, int32_t device, 
 int bcnf_gemm_img(const void* a_img, int64_t a_plane, int32_t a_rpad, const void* b_img, int64_t b_plane, int32_t b_rpad,
                   float* C, int64_t ldc, const float* bias, int32_t M, int32_t N, int32_t K, int32_t passes,
                   int32_t device, void* stream);
+/* Same GEMM with the epilogue gelu(acc + bias) -> operand image c_img (rows = M index, k = N index; columns >= N of the
+ * image are written as zeros): Linear + nn.GELU whose output is the A operand of the next Linear -- the hidden layers of
+ * the layer-by-layer stack schedule and of FullyConnectedFeatureNetwork (reference feature_network.py:114-145). */
+int bcnf_gemm_img_gelu(const void* a_img, int64_t a_plane, int32_t a_rpad, const void* b_img, int64_t b_plane, int32_t b_rpad,
+                       const float* bias, void* c_img, int64_t c_plane, int32_t c_rpad, int32_t M, int32_t N, int32_t K,
+                       int32_t passes, int32_t device, void* stream);
 /* Debug aid (tools/gemm_img_check.py --trace): device buffer of 74 x 16 x 4 uint64 for the per-tile globaltimer stamps
  * of the following bcnf_gemm_img launches; NULL switches it off. */
 int bcnf_gemm_img_set_trace(void* device_buffer);

@@ -122,6 +122,62 @@ def test_layered_schedule_matches_oracle_and_fused_kernel(shape, monkeypatch):
     assert rel_err(ld.cpu().numpy(), ld_f.cpu().numpy()) < 2e-5
 
 
+def test_fc_feature_network_on_tensor_cores_matches_pytorch():
+    """FullyConnectedFeatureNetwork through the CTA-pair GEMM chain (bcnf_b200/feature_tc.py) vs the nn.Sequential it
+    mirrors, fp64 reference: stated tolerance 2e-5 of max|ref| for the 3-pass split (eight chained layers)."""
+    from bcnf_b200 import feature_tc
+    from bcnf_b200.feature_network import FullyConnectedFeatureNetwork
+    torch.manual_seed(3)
+    net = FullyConnectedFeatureNetwork([90, 310, 310, 310, 310, 310, 310, 310, 1360], dropout=0.111).to(DEV).eval()
+    assert feature_tc.supported(net)
+    x = torch.randn(4100, 30, 3, device=DEV)
+    with torch.no_grad():
+        ref = net.double()(x.double().reshape(4100, -1))
+        net.float()
+        h_torch = net(x)
+        net.tc_passes = 3
+        h3 = net(x)
+        net.tc_passes = 1
+        h1 = net(x)
+        # the parameter image cache follows in-place updates
+        net.nn[0].weight.mul_(1.5)
+        net.tc_passes = 0
+        ref2 = net.double()(x.double().reshape(4100, -1))
+        net.float()
+        net.tc_passes = 3
+        h3b = net(x)
+    e = lambda a, b: rel_err(a.double().cpu().numpy(), b.cpu().numpy())
+    print("fc features: torch fp32", e(h_torch, ref), "bf16x3", e(h3, ref), "bf16", e(h1, ref))
+    assert not torch.equal(h3, h_torch)
+    assert e(h3, ref) < 2e-5 and e(h3b, ref2) < 2e-5
+    assert e(h1, ref) < 2e-2
+
+
+def test_model_with_tensor_core_features_stays_inside_the_gate(monkeypatch):
+    """End to end (trajectory_FC_large-shaped: FullyConnected features -> projection -> stack), the feature MLP on the
+    tensor cores vs the PyTorch nn.Sequential: z and log-det move by less than the 1e-5 / 2e-5 gates."""
+    from bcnf_b200 import feature_tc
+    torch.manual_seed(5)
+    fnets = [bcnf_b200.ConcatenateCondition(None, 90),
+             bcnf_b200.FullyConnectedFeatureNetwork([90, 310, 310, 310, 256], dropout=0.1)]
+    model = CondRealNVP_v2(size=19, nested_sizes=[256] * 3, n_blocks=6, n_conditions=256, feature_networks=fnets,
+                           dropout=0.3, act_norm=True, precision="bf16x3").to(DEV).eval()
+    g = torch.Generator().manual_seed(6)
+    rows = 4096
+    y, c = torch.randn(rows, 19, generator=g), torch.randn(rows, 30, 3, generator=g)
+    with torch.no_grad():
+        z_tc = model(y, c, log_det_J=True)
+        ld_tc = model.log_det_J
+        assert model.feature_network_stack.feature_networks[1].tc_passes == 3
+        monkeypatch.setattr(feature_tc, "MIN_ROWS", 1 << 30)           # PyTorch features
+        z_pt = model(y, c, log_det_J=True)
+        ld_pt = model.log_det_J
+    assert not torch.equal(z_tc, z_pt)
+    e_z, e_ld = rel_err(z_tc.cpu().numpy(), z_pt.cpu().numpy()), rel_err(ld_tc.cpu().numpy(), ld_pt.cpu().numpy())
+    print("tensor-core features vs PyTorch features: z", e_z, "logdet", e_ld)
+    assert e_z < 1e-5 and e_ld < 2e-5
+
+
 def test_tensorcore_agrees_with_fp32_kernels_on_golden_large_batch():
     # same weights through the FMA kernel and the 3-pass tensor-core kernel, many tiles per CTA pair
     m32 = _model(19, [128] * 3, 4, 32, "fp32")
