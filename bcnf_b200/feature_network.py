@@ -145,9 +145,13 @@ class LSTMFeatureNetwork(FeatureNetwork):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         seq, _ = self.lstm(x)
-        seq = self.linear(seq)
         axis = 1 if self.pool_axis == "time" else 0
-        return seq.mean(dim=axis) if self.pooling == "mean" else seq.max(dim=axis).values
+        if self.pooling == "mean":
+            # mean pooling commutes with the affine output layer: pool first, then ONE Linear per pooled row instead of
+            # one per time step (reference feature_network.py:168-176 applies the Linear to all seq_len x batch rows:
+            # 30x the FLOPs and a (B, T, output_size) intermediate; same result up to fp32 rounding)
+            return self.linear(seq.mean(dim=axis))
+        return self.linear(seq).max(dim=axis).values
 
 
 class MultiHeadAttention(nn.Module):

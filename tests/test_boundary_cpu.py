@@ -136,3 +136,26 @@ def test_parameter_index_mapping():
     assert m.vectorize({"a": [1, 2], "b": [3, 4]}).shape == (2, 2)
     with pytest.raises(KeyError):
         m.vectorize({"a": 1})
+
+
+def test_lstm_feature_network_pools_before_the_output_layer_without_changing_the_result():
+    """Mean pooling commutes with the affine output layer (reference feature_network.py:168-176 applies the Linear to
+    every time step and pools afterwards): same features up to fp32 rounding, 1/seq_len of the FLOPs."""
+    import torch
+    from bcnf_b200.feature_network import LSTMFeatureNetwork
+    torch.manual_seed(0)
+    for pool_axis, batch in (("time", 7), ("reference", 30)):
+        net = LSTMFeatureNetwork(input_size=3, hidden_size=12, output_size=20, num_layers=2, bidirectional=True,
+                                 pooling="mean", pool_axis=pool_axis).eval()
+        x = torch.randn(batch, 30, 3)
+        with torch.no_grad():
+            seq, _ = net.lstm(x)
+            ref = net.linear(seq).mean(dim=1 if pool_axis == "time" else 0)
+            out = net(x)
+        assert out.shape == ref.shape
+        assert torch.allclose(out, ref, rtol=1e-5, atol=1e-6)
+    net = LSTMFeatureNetwork(input_size=3, hidden_size=12, output_size=20, num_layers=1, pooling="max").eval()
+    x = torch.randn(5, 30, 3)
+    with torch.no_grad():
+        seq, _ = net.lstm(x)
+        assert torch.equal(net(x), net.linear(seq).max(dim=1).values)
