@@ -26,7 +26,7 @@ EXPORTS = ["bcnf_abi_version", "bcnf_last_error", "bcnf_flow_create", "bcnf_flow
            "bcnf_flow_info", "bcnf_flow_set_params", "bcnf_cond_project", "bcnf_flow_forward",
            "bcnf_flow_inverse", "bcnf_train_gemm", "bcnf_train_colsum", "bcnf_train_dropout_mask",
            "bcnf_train_set_gemm_mode", "bcnf_train_gemm_trace", "bcnf_train_pre", "bcnf_train_post",
-           "bcnf_train_post_bwd", "bcnf_train_pre_bwd", "bcnf_img_pack", "bcnf_gemm_img", "bcnf_gemm_img_gelu", "bcnf_gemm_img_set_trace"]
+           "bcnf_train_post_bwd", "bcnf_train_pre_bwd", "bcnf_img_pack", "bcnf_gemm_img", "bcnf_gemm_img_gelu", "bcnf_gemm_img_set_trace", "bcnf_lstm_step"]
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU_DROP, EPI_DGELU_DROP = 0, 1, 2, 3
 
 
@@ -104,6 +104,14 @@ class TrainPreBwdArgs(C.Structure):
                 ("D", C.c_int32), ("H", C.c_int32), ("src0", C.c_int32), ("din", C.c_int32), ("dz", C.c_void_p)]
 
 
+class LstmStep(C.Structure):
+    _fields_ = [("a_hi", C.c_void_p * 16), ("a_lo", C.c_void_p * 16), ("b_img", C.c_void_p), ("b_plane", C.c_int64),
+                ("bias", C.c_void_p), ("cell", C.c_void_p), ("hsum", C.c_void_p), ("state_rows", C.c_int64),
+                ("n_chunks", C.c_int32), ("a_rpad", C.c_int32), ("b_rpad", C.c_int32), ("M", C.c_int32),
+                ("h_hi", C.c_void_p * 4), ("h_lo", C.c_void_p * 4), ("N", C.c_int32), ("passes", C.c_int32),
+                ("pad0", C.c_int32), ("pad1", C.c_int32)]
+
+
 def nvcc_command(out_path: str = LIB_PATH) -> list[str]:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -156,6 +164,7 @@ def lib() -> C.CDLL:
     L.bcnf_gemm_img.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64,
                                 C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     L.bcnf_gemm_img_set_trace.argtypes = [C.c_void_p]
+    L.bcnf_lstm_step.argtypes = [C.POINTER(LstmStep), C.c_int32, C.c_void_p]
     L.bcnf_gemm_img_gelu.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                      C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     L.bcnf_img_pack.argtypes = [C.POINTER(ImgPackDesc), C.c_int32, C.c_int32, C.c_void_p]

@@ -856,6 +856,38 @@ extern "C" int bcnf_gemm_img_gelu(const void* a_img, int64_t a_plane, int32_t a_
   return passes == 3 ? launch_gemm_img2<3>(g, n_sm, (cudaStream_t)stream) : launch_gemm_img2<1>(g, n_sm, (cudaStream_t)stream);
 }
 
+// One time step of one LSTM layer / direction: gates = [x_t | h_(t-1)] . Wcat^T + b on the CTA-pair GEMM with the cell
+// update in the epilogue (gemm_img2.cuh, mode 2)
+static_assert(sizeof(bcnf_lstm_step_t) == 16 * 8 * 2 + 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8 + 4 * 8 * 2 + 16, "bcnf_lstm_step_t layout");
+extern "C" int bcnf_lstm_step(const bcnf_lstm_step_t* a, int32_t device, void* stream) {
+  if (!a || !a->b_img || !a->bias || !a->cell) return fail(BCNF_E_ARG, "bcnf_lstm_step: null argument");
+  if (a->n_chunks < 1 || a->n_chunks > 16) return fail(BCNF_E_ARG, "bcnf_lstm_step: %d operand chunks (1..16)", a->n_chunks);
+  if (a->passes != 1 && a->passes != 3) return fail(BCNF_E_ARG, "bcnf_lstm_step: passes must be 1 or 3");
+  if (a->N < 8 || a->N % 8 || a->N > 1024) return fail(BCNF_E_ARG, "bcnf_lstm_step: N = 4 * hidden must be a multiple of 8, <= 1024");
+  if (a->M < 0 || a->a_rpad % 256 || a->a_rpad < (a->M + 255) / 256 * 256 || a->state_rows < a->M)
+    return fail(BCNF_E_ARG, "bcnf_lstm_step: bad row counts (M=%d a_rpad=%d state_rows=%lld)", a->M, a->a_rpad, (long long)a->state_rows);
+  if (((uintptr_t)a->bias & 15) != 0) return fail(BCNF_E_ARG, "bcnf_lstm_step: bias must be 16-byte aligned");
+  const int tiles_n = (a->N + 255) / 256;
+  for (int k = 0; k < a->n_chunks; ++k)
+    if (!a->a_hi[k] || (a->passes == 3 && !a->a_lo[k])) return fail(BCNF_E_ARG, "bcnf_lstm_step: operand chunk %d missing", k);
+  for (int t = 0; t < tiles_n; ++t)
+    if (!a->h_hi[t] || (a->passes == 3 && !a->h_lo[t])) return fail(BCNF_E_ARG, "bcnf_lstm_step: output chunk %d missing", t);
+  if (a->M == 0) return BCNF_OK;
+  CUDA_TRY(cudaSetDevice(device));
+  int n_sm = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+  G2Args g;
+  memset(&g, 0, sizeof(g));
+  g.a_tab_n = a->n_chunks;
+  for (int k = 0; k < a->n_chunks; ++k) { g.a_tab_hi[k] = (const unsigned char*)a->a_hi[k]; g.a_tab_lo[k] = (const unsigned char*)a->a_lo[k]; }
+  g.a_img = g.a_tab_hi[0]; g.a_rpad = a->a_rpad; g.a_plane = (long long)a->n_chunks * a->a_rpad * 128;   // (size checks only)
+  g.b_img = (const unsigned char*)a->b_img; g.b_plane = a->b_plane; g.b_rpad = a->b_rpad;
+  g.bias = a->bias; g.M = a->M; g.N = a->N; g.K = a->n_chunks * 64;
+  g.lstm = 1; g.cell = a->cell; g.hsum = a->hsum; g.state_rows = a->state_rows;
+  for (int t = 0; t < 4; ++t) { g.h_hi[t] = (unsigned char*)a->h_hi[t]; g.h_lo[t] = (unsigned char*)a->h_lo[t]; }
+  return a->passes == 3 ? launch_gemm_img2<3>(g, n_sm, (cudaStream_t)stream) : launch_gemm_img2<1>(g, n_sm, (cudaStream_t)stream);
+}
+
 static void* g_g2_trace = nullptr;
 // debug: device buffer (74 x 16 x 4 uint64) that receives globaltimer stamps of the next bcnf_gemm_img launches
 extern "C" int bcnf_gemm_img_set_trace(void* device_buffer) { g_g2_trace = device_buffer; return BCNF_OK; }

@@ -41,6 +41,16 @@ struct G2Args {
   // epilogue mode 1 (C == null): out = gelu(acc + bias) written as an operand image (rows = M index, k = N index):
   // the A operand of the next layer's GEMM; columns >= N inside the image are written as zeros
   unsigned char* c_img; long long c_plane; int c_rpad;
+  // A operand gathered chunk by chunk (a_tab_n > 0): K chunk kc is the [a_rpad rows][128 B] block a_tab_hi[kc] / a_tab_lo[kc]
+  // -- lets one GEMM read [x_t | h_(t-1)] from the buffers where earlier launches left them
+  const unsigned char* a_tab_hi[16]; const unsigned char* a_tab_lo[16]; int a_tab_n;
+  // epilogue mode 2, LSTM cell (nn.LSTM gate order i, f, g, o; columns interleaved n = 4*unit + gate, so an 8-column group
+  // holds two whole units): c = sigmoid(f) c + sigmoid(i) tanh(g); h = sigmoid(o) tanh(c).  cell / hsum are fp32
+  // [N/8 groups][state_rows][2] (a lane = a row: coalesced); a 256-column tile = 64 units = ONE 64-column chunk of the h
+  // image, staged in shared memory and written with a bulk store to h_hi[tile] / h_lo[tile].
+  int lstm;
+  float* cell; float* hsum; long long state_rows;
+  unsigned char* h_hi[4]; unsigned char* h_lo[4];
   int debug;                // bit 0: skip the stores of the epilogue (timing experiments)
   unsigned long long* trace;   // debug: globaltimer stamps [pair][tile (<16)][4] (null in normal runs)
 };
@@ -129,10 +139,12 @@ gemm_img2_kernel(const G2Args g) {
           unsigned char* st = smem_g2 + (size_t)s * Cfg::stage;
           mbar_expect_tx(&full[s], (uint32_t)Cfg::stage);
           const long long ao = (long long)kc * g.a_rpad * 128, bo = (long long)kc * g.b_rpad * 128;
-          tma_bulk_g2s(st, a_src + ao, kG2Tile, &full[s]);
+          const unsigned char* ahi = g.a_tab_n > 0 ? g.a_tab_hi[kc] + (long long)m0 * 128 : a_src + ao;
+          tma_bulk_g2s(st, ahi, kG2Tile, &full[s]);
           tma_bulk_g2s(st + Cfg::planes * kG2Tile, b_src + bo, kG2Tile, &full[s]);
           if (NPASS == 3) {
-            tma_bulk_g2s(st + kG2Tile, a_src + g.a_plane + ao, kG2Tile, &full[s]);
+            const unsigned char* alo = g.a_tab_n > 0 ? g.a_tab_lo[kc] + (long long)m0 * 128 : a_src + g.a_plane + ao;
+            tma_bulk_g2s(st + kG2Tile, alo, kG2Tile, &full[s]);
             tma_bulk_g2s(st + 3 * kG2Tile, b_src + g.b_plane + bo, kG2Tile, &full[s]);
           }
         }
@@ -203,7 +215,67 @@ gemm_img2_kernel(const G2Args g) {
       tc_fence_after();
       if (g.trace && leader && et == 0 && tile_it < 16) g.trace[(pair_id * 16 + tile_it) * 4 + 2] = g2_now();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256u + (uint32_t)(part * 128);
-      if (g.c_img) {
+      if (g.lstm) {
+        // ---- LSTM cell: gates -> (c, h); h as the next step's operand image chunk ----
+        unsigned char* stg = smem_g2 + Cfg::stg_off;
+        const int row = q * 32 + lane;
+        const long long row0 = (long long)tm * 256 + (long long)cta * 128;
+        const long long grow = row0 + row;
+        const bool row_ok = grow < g.M;
+        if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous tile's store has read the staging
+        g2_epi_sync();
+#pragma unroll 1
+        for (int c = 0; c < 128; c += 16) {
+          uint32_t r0[8], r1[8];
+          tmem_ld8_issue(taddr + c, r0);
+          tmem_ld8_issue(taddr + c + 8, r1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int h8 = 0; h8 < 2; ++h8) {
+            const uint32_t* r = h8 == 0 ? r0 : r1;
+            const int gcol = tn * 256 + part * 128 + c + h8 * 8;         // first gate column of this pair of units
+            float hv[2] = {0.f, 0.f};
+            if (row_ok && gcol < g.N) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + gcol));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bias + gcol + 4));
+              const long long so = ((long long)(gcol >> 3) * g.state_rows + grow) * 2;
+              float2 cp = *reinterpret_cast<const float2*>(g.cell + so);
+              const float pre[8] = {__uint_as_float(r[0]) + b0.x, __uint_as_float(r[1]) + b0.y, __uint_as_float(r[2]) + b0.z,
+                                    __uint_as_float(r[3]) + b0.w, __uint_as_float(r[4]) + b1.x, __uint_as_float(r[5]) + b1.y,
+                                    __uint_as_float(r[6]) + b1.z, __uint_as_float(r[7]) + b1.w};
+              float cn[2];
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                const float ig = 1.0f / (1.0f + __expf(-pre[4 * u])), fg = 1.0f / (1.0f + __expf(-pre[4 * u + 1]));
+                const float gg = tanhf(pre[4 * u + 2]), og = 1.0f / (1.0f + __expf(-pre[4 * u + 3]));
+                cn[u] = fmaf(fg, u == 0 ? cp.x : cp.y, ig * gg);
+                hv[u] = og * tanhf(cn[u]);
+              }
+              *reinterpret_cast<float2*>(g.cell + so) = make_float2(cn[0], cn[1]);
+              if (g.hsum) {
+                float2 hs = *reinterpret_cast<const float2*>(g.hsum + so);
+                hs.x += hv[0]; hs.y += hv[1];
+                *reinterpret_cast<float2*>(g.hsum + so) = hs;
+              }
+            }
+            const uint32_t hi = pack_bf16x2(hv[0], hv[1]);
+            const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+            const int ucol = part * 32 + ((c + h8 * 8) >> 2);              // unit column inside the 64-unit chunk (even)
+            const int off = row * 128 + (((ucol >> 3) ^ (row & 7)) << 4) + ((ucol & 7) << 1);
+            *reinterpret_cast<uint32_t*>(stg + off) = hi;
+            if (NPASS == 3) *reinterpret_cast<uint32_t*>(stg + kG2Tile + off) = pack_bf16x2(hv[0] - h0, hv[1] - h1);
+          }
+        }
+        fence_proxy_async();
+        g2_epi_sync();
+        if (et == 0) {
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g.h_hi[tn] + row0 * 128), "r"(smem_u32(stg)), "n"(kG2Tile) : "memory");
+          if (NPASS == 3)
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g.h_lo[tn] + row0 * 128), "r"(smem_u32(stg + kG2Tile)), "n"(kG2Tile) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        (void)i;
+      } else if (g.c_img) {
         // ---- gelu(acc + bias) -> bf16 hi/lo image of the next layer's input ----
         // A lane owns a row, so direct stores would touch 32 different lines per warp instruction (measured: 2 cycles
         // per 16-byte store, 11-14 us per tile).  The CTA's 128 rows x one 64-column chunk are ONE contiguous 16 KB

@@ -143,7 +143,13 @@ class LSTMFeatureNetwork(FeatureNetwork):
                             bidirectional=bidirectional, batch_first=True)
         self.linear = nn.Linear(hidden_size * (2 if bidirectional else 1), output_size)
 
+    tc_passes: int = 0      # set by CondRealNVP_v2 on tensor-core handles: 3 = bf16x3 (fp32-class), 1 = bf16, 0 = PyTorch
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.tc_passes and x.is_cuda and x.ndim == 3 and not self.training and not torch.is_grad_enabled():
+            from . import feature_tc
+            if x.size(0) >= feature_tc.MIN_ROWS and feature_tc.lstm_supported(self):
+                return feature_tc.lstm_forward(self, x, self.tc_passes)
         seq, _ = self.lstm(x)
         axis = 1 if self.pool_axis == "time" else 0
         if self.pooling == "mean":

@@ -78,3 +78,109 @@ def forward(net: Any, x: torch.Tensor, passes: int) -> torch.Tensor:
                         "bcnf_gemm_img")
             return h
     raise AssertionError("unreachable")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# LSTMFeatureNetwork (reference feature_network.py:148-178): nn.LSTM -> Linear -> mean over time
+# ------------------------------------------------------------------------------------------------------------------
+def lstm_supported(net: Any) -> bool:
+    lstm = net.lstm
+    hc = (lstm.hidden_size + 63) // 64
+    dirs = 2 if lstm.bidirectional else 1
+    return (net.pooling == "mean" and net.pool_axis == "time" and lstm.batch_first and lstm.bias and lstm.proj_size == 0
+            and lstm.hidden_size % 2 == 0 and 4 * lstm.hidden_size <= 1024 and (dirs + 1) * hc <= 16
+            and (lstm.input_size + 63) // 64 + hc <= 16 and all(p.dtype == torch.float32 for p in net.parameters()))
+
+
+def _lstm_weights(net: Any, layer: int, d: int, dev: torch.device) -> tuple[_Img, torch.Tensor]:
+    """Gate-interleaved [W_ih | W_hh] image (rows n = 4*unit + gate) and bias b_ih + b_hh of one layer / direction."""
+    lstm = net.lstm
+    sfx = f"_l{layer}" + ("_reverse" if d == 1 else "")
+    w_ih, w_hh = getattr(lstm, "weight_ih" + sfx), getattr(lstm, "weight_hh" + sfx)
+    b_ih, b_hh = getattr(lstm, "bias_ih" + sfx), getattr(lstm, "bias_hh" + sfx)
+    key = tuple((t.data_ptr(), t._version) for t in (w_ih, w_hh, b_ih, b_hh))
+    cache = net.__dict__.setdefault("_tc_lstm", {})
+    hit = cache.get((layer, d))
+    if hit is not None and hit[0] == key:
+        return hit[1], hit[2]
+    H = lstm.hidden_size
+    hc = (H + 63) // 64
+    dirs = 2 if lstm.bidirectional else 1
+    idx = (torch.arange(4, device=dev).view(1, 4) * H + torch.arange(H, device=dev).view(H, 1)).reshape(-1)
+    with torch.no_grad():
+        wi, wh = w_ih.detach()[idx], w_hh.detach()[idx]
+        in_cols = (lstm.input_size + 63) // 64 * 64 if layer == 0 else dirs * hc * 64
+        wc = torch.zeros(4 * H, in_cols + hc * 64, device=dev)
+        if layer == 0:
+            wc[:, :lstm.input_size] = wi
+        else:
+            for d2 in range(dirs):      # the previous layer's directions arrive as separate image chunks
+                wc[:, d2 * hc * 64: d2 * hc * 64 + H] = wi[:, d2 * H:(d2 + 1) * H]
+        wc[:, in_cols: in_cols + H] = wh
+        bias = (b_ih.detach() + b_hh.detach())[idx].contiguous()
+    im = _Img(dev, 4 * H, wc.shape[1], align=256)
+    _pack_images([(wc, 0, wc.stride(0), 1, 4 * H, wc.shape[1], im)], dev)
+    cache[(layer, d)] = (key, im, bias)
+    return im, bias
+
+
+def lstm_forward(net: Any, x: torch.Tensor, passes: int) -> torch.Tensor:
+    """x (B, T, input_size) -> features (B, output_size).  One CTA-pair GEMM launch per layer, direction and time step
+    (csrc/gemm_img2.cuh, LSTM-cell epilogue); the mean over time is accumulated by the last layer's epilogues and the
+    output Linear runs once per pooled row."""
+    lstm = net.lstm
+    dev = x.device
+    x = x.contiguous().float()
+    B, T, F = x.shape
+    H, L = lstm.hidden_size, lstm.num_layers
+    dirs = 2 if lstm.bidirectional else 1
+    hc, xc = (H + 63) // 64, (F + 63) // 64
+    R = (B + 255) // 256 * 256
+    lib = _cabi.lib()
+    tag = ("lstm", id(net), B, T)
+    chunk = R * 128
+    # x_t images
+    ximg = [_img(dev, (tag, "x", t), B, F, align=256) for t in range(T)]
+    _pack_images([(x, t * F, T * F, 1, B, F, ximg[t]) for t in range(T)], dev)
+    zero_h = _img(dev, (tag, "h0"), B, hc * 64, align=256)              # h_(-1) = 0 (never written)
+    state = net.__dict__.setdefault("_tc_lstm_state", {})
+    if state.get("tag") != tag:
+        state.clear()
+        state["tag"] = tag
+        state["cell"] = torch.empty(L, dirs, H // 2, R, 2, device=dev)
+        state["hsum"] = torch.empty(dirs, H // 2, R, 2, device=dev)
+    cell, hsum = state["cell"], state["hsum"]
+    cell.zero_()
+    hsum.zero_()
+
+    def chunks(im: _Img, n: int):
+        return [(im.ptr + c * chunk, im.ptr + im.plane + c * chunk) for c in range(n)]
+
+    for layer in range(L):
+        last = layer == L - 1
+        for d in range(dirs):
+            wimg, bias = _lstm_weights(net, layer, d, dev)
+            order = range(T) if d == 0 else range(T - 1, -1, -1)
+            prev = zero_h
+            for step, t in enumerate(order):
+                if last:
+                    out = _img(dev, (tag, "hl", layer, d, step & 1), B, hc * 64, align=256)
+                else:
+                    out = _img(dev, (tag, "h", layer, d, t), B, hc * 64, align=256)
+                a = _cabi.LstmStep()
+                src = chunks(ximg[t], xc) if layer == 0 else [p for d2 in range(dirs) for p in
+                                                              chunks(_img(dev, (tag, "h", layer - 1, d2, t), B, hc * 64, align=256), hc)]
+                src = src + chunks(prev, hc)
+                for k, (ph, pl) in enumerate(src):
+                    a.a_hi[k], a.a_lo[k] = ph, pl
+                a.n_chunks, a.a_rpad = len(src), R
+                a.b_img, a.b_plane, a.b_rpad = wimg.ptr, wimg.plane, wimg.rpad
+                a.bias, a.cell = bias.data_ptr(), cell[layer, d].data_ptr()
+                a.hsum = hsum[d].data_ptr() if last else None
+                a.state_rows, a.M, a.N, a.passes = R, B, 4 * H, passes
+                for k, (ph, pl) in enumerate(chunks(out, hc)):
+                    a.h_hi[k], a.h_lo[k] = ph, pl
+                _cabi.check(lib.bcnf_lstm_step(C.byref(a), dev.index or 0, _stream(dev)), "bcnf_lstm_step")
+                prev = out
+    pooled = hsum[:, :, :B, :].permute(2, 0, 1, 3).reshape(B, dirs * H) * (1.0 / T)
+    return torch.nn.functional.linear(pooled, net.linear.weight, net.linear.bias)

@@ -202,6 +202,21 @@ int bcnf_gemm_img(const void* a_img, int64_t a_plane, int32_t a_rpad, const void
 int bcnf_gemm_img_gelu(const void* a_img, int64_t a_plane, int32_t a_rpad, const void* b_img, int64_t b_plane, int32_t b_rpad,
                        const float* bias, void* c_img, int64_t c_plane, int32_t c_rpad, int32_t M, int32_t N, int32_t K,
                        int32_t passes, int32_t device, void* stream);
+/* One time step of one nn.LSTM layer and direction (LSTMFeatureNetwork, reference feature_network.py:148-178):
+ * gates = [x_t | h_(t-1)] . Wcat^T + bias on the CTA-pair GEMM, cell update in the epilogue.  The A operand is gathered
+ * from n_chunks 64-column image chunks (a_hi / a_lo: [a_rpad rows][128 B] each) -- the chunks of x_t and of the
+ * previous step's h.  Wcat image rows and bias are gate-interleaved: n = 4 * unit + gate (gate order i, f, g, o).
+ * cell (in/out) and hsum (optional, += h) are fp32 [N/8][state_rows][2]; h_t leaves as one image chunk per 64 units. */
+typedef struct {
+  const void* a_hi[16]; const void* a_lo[16];
+  const void* b_img; int64_t b_plane;
+  const float* bias;
+  float* cell; float* hsum; int64_t state_rows;
+  int32_t n_chunks, a_rpad, b_rpad, M;
+  void* h_hi[4]; void* h_lo[4];
+  int32_t N, passes, pad0, pad1;
+} bcnf_lstm_step_t;
+int bcnf_lstm_step(const bcnf_lstm_step_t* args, int32_t device, void* stream);
 /* Debug aid (tools/gemm_img_check.py --trace): device buffer of 74 x 16 x 4 uint64 for the per-tile globaltimer stamps
  * of the following bcnf_gemm_img launches; NULL switches it off. */
 int bcnf_gemm_img_set_trace(void* device_buffer);

@@ -178,6 +178,31 @@ def test_model_with_tensor_core_features_stays_inside_the_gate(monkeypatch):
     assert e_z < 1e-5 and e_ld < 2e-5
 
 
+def test_lstm_feature_network_on_tensor_cores_matches_pytorch():
+    """LSTMFeatureNetwork (2-layer bi-LSTM -> mean over time -> Linear) as one CTA-pair GEMM per layer, direction and time
+    step with the cell update in the epilogue (bcnf_b200/feature_tc.py) vs nn.LSTM in fp64: stated tolerance 5e-5 of
+    max|ref| for the 3-pass split through a 30-step recurrence and two layers."""
+    from bcnf_b200 import feature_tc
+    from bcnf_b200.feature_network import LSTMFeatureNetwork
+    torch.manual_seed(4)
+    net = LSTMFeatureNetwork(input_size=3, hidden_size=140, output_size=1360, num_layers=2, dropout=0.1,
+                             bidirectional=True, pooling="mean").to(DEV).eval()
+    assert feature_tc.lstm_supported(net)
+    x = torch.randn(2100, 30, 3, device=DEV)
+    with torch.no_grad():
+        ref = net.double()(x.double())
+        net.float()
+        h_torch = net(x)
+        net.tc_passes = 3
+        h3 = net(x)
+        h3_again = net(x)
+    e = lambda a, b: rel_err(a.double().cpu().numpy(), b.cpu().numpy())
+    print("lstm features: torch fp32", e(h_torch, ref), "bf16x3", e(h3, ref))
+    assert not torch.equal(h3, h_torch)
+    assert torch.equal(h3, h3_again)                  # state buffers are reset between calls
+    assert e(h3, ref) < 5e-5
+
+
 def test_tensorcore_agrees_with_fp32_kernels_on_golden_large_batch():
     # same weights through the FMA kernel and the 3-pass tensor-core kernel, many tiles per CTA pair
     m32 = _model(19, [128] * 3, 4, 32, "fp32")
