@@ -60,6 +60,9 @@ __device__ __forceinline__ unsigned long long g2_now() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+// logistic and tanh through ex2 / rcp (MUFU): absolute error ~1e-7, a fifth of the instructions of tanhf / full division
+__device__ __forceinline__ float g2_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float g2_tanh(float x) { return fmaf(2.0f, g2_sigmoid(2.0f * x), -1.0f); }
 __device__ __forceinline__ void g2_epi_sync() { asm volatile("bar.sync 2, %0;" ::"n"(32 * kG2EpiWarps) : "memory"); }
 __device__ __forceinline__ uint32_t make_idesc_m256(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
@@ -246,10 +249,10 @@ gemm_img2_kernel(const G2Args g) {
               float cn[2];
 #pragma unroll
               for (int u = 0; u < 2; ++u) {
-                const float ig = 1.0f / (1.0f + __expf(-pre[4 * u])), fg = 1.0f / (1.0f + __expf(-pre[4 * u + 1]));
-                const float gg = tanhf(pre[4 * u + 2]), og = 1.0f / (1.0f + __expf(-pre[4 * u + 3]));
+                const float ig = g2_sigmoid(pre[4 * u]), fg = g2_sigmoid(pre[4 * u + 1]);
+                const float gg = g2_tanh(pre[4 * u + 2]), og = g2_sigmoid(pre[4 * u + 3]);
                 cn[u] = fmaf(fg, u == 0 ? cp.x : cp.y, ig * gg);
-                hv[u] = og * tanhf(cn[u]);
+                hv[u] = og * g2_tanh(cn[u]);
               }
               *reinterpret_cast<float2*>(g.cell + so) = make_float2(cn[0], cn[1]);
               if (g.hsum) {

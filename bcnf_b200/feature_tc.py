@@ -156,31 +156,43 @@ def lstm_forward(net: Any, x: torch.Tensor, passes: int) -> torch.Tensor:
     def chunks(im: _Img, n: int):
         return [(im.ptr + c * chunk, im.ptr + im.plane + c * chunk) for c in range(n)]
 
-    for layer in range(L):
-        last = layer == L - 1
-        for d in range(dirs):
-            wimg, bias = _lstm_weights(net, layer, d, dev)
-            order = range(T) if d == 0 else range(T - 1, -1, -1)
-            prev = zero_h
-            for step, t in enumerate(order):
-                if last:
-                    out = _img(dev, (tag, "hl", layer, d, step & 1), B, hc * 64, align=256)
-                else:
-                    out = _img(dev, (tag, "h", layer, d, t), B, hc * 64, align=256)
-                a = _cabi.LstmStep()
-                src = chunks(ximg[t], xc) if layer == 0 else [p for d2 in range(dirs) for p in
-                                                              chunks(_img(dev, (tag, "h", layer - 1, d2, t), B, hc * 64, align=256), hc)]
-                src = src + chunks(prev, hc)
-                for k, (ph, pl) in enumerate(src):
-                    a.a_hi[k], a.a_lo[k] = ph, pl
-                a.n_chunks, a.a_rpad = len(src), R
-                a.b_img, a.b_plane, a.b_rpad = wimg.ptr, wimg.plane, wimg.rpad
-                a.bias, a.cell = bias.data_ptr(), cell[layer, d].data_ptr()
-                a.hsum = hsum[d].data_ptr() if last else None
-                a.state_rows, a.M, a.N, a.passes = R, B, 4 * H, passes
-                for k, (ph, pl) in enumerate(chunks(out, hc)):
-                    a.h_hi[k], a.h_lo[k] = ph, pl
-                _cabi.check(lib.bcnf_lstm_step(C.byref(a), dev.index or 0, _stream(dev)), "bcnf_lstm_step")
-                prev = out
+    # the launch arguments only depend on cached buffers: build the list once per (shape, parameter version)
+    wts = [[_lstm_weights(net, layer, d, dev) for d in range(dirs)] for layer in range(L)]
+    wkey = tuple((w.ptr, b.data_ptr()) for row in wts for (w, b) in row) + (passes,)
+    if state.get("wkey") != wkey:
+        steps = []
+        for layer in range(L):
+            last = layer == L - 1
+            for d in range(dirs):
+                wimg, bias = wts[layer][d]
+                order = range(T) if d == 0 else range(T - 1, -1, -1)
+                prev = zero_h
+                for step, t in enumerate(order):
+                    if last:
+                        out = _img(dev, (tag, "hl", layer, d, step & 1), B, hc * 64, align=256)
+                    else:
+                        out = _img(dev, (tag, "h", layer, d, t), B, hc * 64, align=256)
+                    a = _cabi.LstmStep()
+                    src = chunks(ximg[t], xc) if layer == 0 else [p for d2 in range(dirs) for p in
+                                                                  chunks(_img(dev, (tag, "h", layer - 1, d2, t), B, hc * 64, align=256), hc)]
+                    src = src + chunks(prev, hc)
+                    for k, (ph, pl) in enumerate(src):
+                        a.a_hi[k], a.a_lo[k] = ph, pl
+                    a.n_chunks, a.a_rpad = len(src), R
+                    a.b_img, a.b_plane, a.b_rpad = wimg.ptr, wimg.plane, wimg.rpad
+                    a.bias, a.cell = bias.data_ptr(), cell[layer, d].data_ptr()
+                    a.hsum = hsum[d].data_ptr() if last else None
+                    a.state_rows, a.M, a.N, a.passes = R, B, 4 * H, passes
+                    for k, (ph, pl) in enumerate(chunks(out, hc)):
+                        a.h_hi[k], a.h_lo[k] = ph, pl
+                    steps.append(a)
+                    prev = out
+        state["steps"], state["wkey"], state["keep"] = steps, wkey, wts
+    di, st = dev.index or 0, _stream(dev)
+    step_fn = lib.bcnf_lstm_step
+    for a in state["steps"]:
+        rc = step_fn(C.byref(a), di, st)
+        if rc:
+            _cabi.check(rc, "bcnf_lstm_step")
     pooled = hsum[:, :, :B, :].permute(2, 0, 1, 3).reshape(B, dirs * H) * (1.0 / T)
     return torch.nn.functional.linear(pooled, net.linear.weight, net.linear.bias)
