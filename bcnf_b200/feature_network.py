@@ -148,7 +148,7 @@ class LSTMFeatureNetwork(FeatureNetwork):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if self.tc_passes and x.is_cuda and x.ndim == 3 and not self.training and not torch.is_grad_enabled():
             from . import feature_tc
-            if x.size(0) >= feature_tc.MIN_ROWS and feature_tc.lstm_supported(self):
+            if x.size(0) >= feature_tc.MIN_ROWS_LSTM and feature_tc.lstm_supported(self):
                 return feature_tc.lstm_forward(self, x, self.tc_passes)
         seq, _ = self.lstm(x)
         axis = 1 if self.pool_axis == "time" else 0

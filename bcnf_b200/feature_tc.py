@@ -10,6 +10,7 @@ or single-pass bf16).  Eval mode, no autograd; parameter images are cached per (
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Any
 
 import torch
@@ -18,7 +19,9 @@ from torch import nn
 from . import _cabi
 from .train import _Img, _img, _pack_images, _stream
 
-MIN_ROWS = 2048     # below this the nine launches cost more than the PyTorch chain
+# below this many rows the launches cost more than the PyTorch modules (BCNF_FEATURE_TC_MIN_ROWS overrides)
+MIN_ROWS = int(os.environ.get("BCNF_FEATURE_TC_MIN_ROWS", "2048"))
+MIN_ROWS_LSTM = int(os.environ.get("BCNF_FEATURE_TC_MIN_ROWS", "512"))   # measured: ahead of cuDNN at 1000 sequences already
 
 
 def supported(net: Any) -> bool:
