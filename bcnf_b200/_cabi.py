@@ -57,7 +57,7 @@ class GemmArgs(C.Structure):
                 ("save", C.c_void_p), ("saved", C.c_void_p), ("seed", C.c_uint64), ("layer_uid", C.c_uint32),
                 ("p_drop", C.c_float), ("seed_ptr", C.c_void_p), ("colsum", C.c_void_p), ("ws", C.c_void_p),
                 ("counters", C.c_void_p), ("ws_floats", C.c_int64), ("n_counters", C.c_int32), ("split_k", C.c_int32),
-                ("a_img", C.c_void_p), ("a_plane", C.c_int64), ("a_rpad", C.c_int32), ("pad0", C.c_int32),
+                ("a_img", C.c_void_p), ("a_plane", C.c_int64), ("a_rpad", C.c_int32), ("img_mn", C.c_int32),
                 ("b_img", C.c_void_p), ("b_plane", C.c_int64), ("b_rpad", C.c_int32), ("pad1", C.c_int32),
                 ("c_img", C.c_void_p), ("c_plane", C.c_int64), ("c_rpad", C.c_int32), ("pad2", C.c_int32)]
 

@@ -1319,7 +1319,36 @@ static int launch_train_tc2_bn(const GemmArgs& g, cudaStream_t stream) {
   return BCNF_OK;
 }
 
+template <int BN>
+static int launch_train_tc3_bn(const GemmArgs& g, cudaStream_t stream) {
+  using Cfg = T3Cfg<BN>;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 64 && !attr_set[dev]) {
+    CUDA_TRY(cudaFuncSetAttribute(train_tc3_dw_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem));
+    attr_set[dev] = true;
+  }
+  const int n_kc = (g.K + 63) / 64;
+  if (g.a_rpad <= 0 || g.b_rpad <= 0 || g.a_rpad < n_kc * 64 || g.b_rpad < n_kc * 64 || g.a_plane % ((long long)g.a_rpad * 128) ||
+      g.b_plane % ((long long)g.b_rpad * 128) || g.a_plane / ((long long)g.a_rpad * 128) * 64 < g.M ||
+      g.b_plane / ((long long)g.b_rpad * 128) * 64 < g.N)
+    return fail(BCNF_E_ARG, "bcnf_train_gemm: images too small for the weight-gradient mode (M=%d N=%d K=%d)", g.M, g.N, g.K);
+  ImgArgs im;
+  memset(&im, 0, sizeof(im));
+  im.a_img = g.a_img; im.a_plane = g.a_plane; im.a_rpad = g.a_rpad;
+  im.b_img = g.b_img; im.b_plane = g.b_plane; im.b_rpad = g.b_rpad;
+  dim3 grid((g.N + BN - 1) / BN, (g.M + kTgBM - 1) / kTgBM);
+  train_tc3_dw_kernel<BN><<<grid, kT2Threads, Cfg::smem, stream>>>(g, im);
+  CUDA_TRY(cudaGetLastError());
+  return BCNF_OK;
+}
+
 static int launch_train_tc2(const GemmArgs& g, int force_bn, cudaStream_t stream) {
+  if (g.img_mn) {
+    if (g.epi != TEPI_NONE || g.colsum || g.c_img) return fail(BCNF_E_ARG, "bcnf_train_gemm: the weight-gradient mode has no epilogue options");
+    return force_bn == 128 ? launch_train_tc3_bn<128>(g, stream) : launch_train_tc3_bn<64>(g, stream);
+  }
   const long long tm = (g.M + kTgBM - 1) / kTgBM;
   int bn = force_bn;
   // at a few hundred rows the CTA's time is the L2 -> SM transfer of its operand panels: narrow tiles, more SMs

@@ -42,7 +42,7 @@ struct GemmArgs {
   int n_counters;
   int split_k;             // 0: library decides (needs ws / counters); 1: never split; n > 1: at most n splits
   // operand images (train_tc.cuh): when a_img and b_img are given the TMA-fed kernel runs and A / B are not read
-  const unsigned char* a_img; long long a_plane; int a_rpad; int pad0;
+  const unsigned char* a_img; long long a_plane; int a_rpad; int img_mn;   // img_mn: weight-gradient mode, see train_tc.cuh
   const unsigned char* b_img; long long b_plane; int b_rpad; int pad1;
   unsigned char* c_img; long long c_plane; int c_rpad; int pad2;     // optional: image of the values written to C
 };

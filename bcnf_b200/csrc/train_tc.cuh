@@ -537,6 +537,151 @@ train_tc2_gemm_kernel(const GemmArgs g, const ImgArgs im) {
   }
 }
 
+// =====================================================================================================
+// Third kernel: weight gradients dW = d^T . x from the SAME images, read as MN-major operands.
+//
+// dW(i, j) = sum_r d(r, i) x(r, j): the contraction runs over the batch rows r.  An image chunk [rows r][64 columns] is
+// exactly the canonical MN-major SWIZZLE_128B operand tile of tcgen05.mma (cute::UMMA make_umma_desc<Major::MN>:
+// ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units -- 64 consecutive M (or N) elements per 128-byte row, 8-row swizzle
+// atoms along K): no second copy of the activations, no transposition.  A tile = 128 columns of d (two image chunks,
+// LBO = one chunk apart) x 64 rows; B tile = BN columns of x (BN/64 chunks) x 64 rows; one K = 16 step advances the
+// descriptors by 16 rows (2 KB).  Otherwise the structure of the kernel above: producer warp with bulk copies, three
+// issuing warps (one per pass, own accumulator), epilogue warps add the accumulators and store fp32 (+ beta C).
+// =====================================================================================================
+template <int BN>
+struct T3Cfg {
+  static constexpr int a_tile = 2 * 64 * 128, b_tile = (BN / 64) * 64 * 128;   // per plane: chunks x 64 rows x 128 B
+  static constexpr int stage = 2 * a_tile + 2 * b_tile;
+  static constexpr int stages = BN <= 64 ? 4 : 3;
+  static constexpr int bar_off = stages * stage;
+  static constexpr int smem = bar_off + 128;
+  static constexpr int tmem_cols = 3 * BN <= 256 ? 256 : 512;
+};
+
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+  // MN-major, SWIZZLE_128B: 64-element (128-byte) MN blocks lbo_bytes apart, 8-row K groups 1024 bytes apart
+  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t make_idesc_mn(int n) {
+  // as make_idesc, with both operands MN-major (bits 15, 16)
+  return make_idesc(n) | (1u << 15) | (1u << 16);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kT2Threads, 1)
+train_tc3_dw_kernel(const GemmArgs g, const ImgArgs im) {
+  using Cfg = T3Cfg<BN>;
+  extern __shared__ __align__(1024) unsigned char smem_t3[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_t3 + Cfg::bar_off);
+  uint64_t* empty = full + 4;
+  uint64_t* acc_full = empty + 4;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  const int i0 = blockIdx.y * kTgBM, j0 = blockIdx.x * BN;       // i: columns of d (image a), j: columns of x (image b)
+  const int n_it = (g.K + 63) >> 6;                              // K = batch rows
+  const int a_chunks_img = (int)(im.a_plane / ((long long)im.a_rpad * 128));
+  const int b_chunks_img = (int)(im.b_plane / ((long long)im.b_rpad * 128));
+  // chunks of this tile that exist in the images (columns past the image only feed discarded rows / columns of dW)
+  const int a_n = min(2, a_chunks_img - (i0 >> 6)), b_n = min(BN / 64, b_chunks_img - (j0 >> 6));
+
+  if (tid == 0) {
+    for (int s = 0; s < Cfg::stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 3); }
+    mbar_init(acc_full, 3);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "n"(Cfg::tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_s, 0);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it % Cfg::stages, use = it / Cfg::stages;
+        if (use > 0) mbar_wait(&empty[s], (uint32_t)(use - 1) & 1u);
+        unsigned char* st = smem_t3 + (size_t)s * Cfg::stage;
+        mbar_expect_tx(&full[s], (uint32_t)(2 * (a_n + b_n) * 64 * 128));
+        const long long r_off = (long long)it * 64 * 128;        // 64 batch rows further down every chunk
+        for (int c = 0; c < a_n; ++c) {
+          const unsigned char* src = im.a_img + ((long long)((i0 >> 6) + c) * im.a_rpad) * 128 + r_off;
+          tma_bulk_g2s(st + c * 8192, src, 8192, &full[s]);
+          tma_bulk_g2s(st + Cfg::a_tile + c * 8192, src + im.a_plane, 8192, &full[s]);
+        }
+        for (int c = 0; c < b_n; ++c) {
+          const unsigned char* src = im.b_img + ((long long)((j0 >> 6) + c) * im.b_rpad) * 128 + r_off;
+          tma_bulk_g2s(st + 2 * Cfg::a_tile + c * 8192, src, 8192, &full[s]);
+          tma_bulk_g2s(st + 2 * Cfg::a_tile + Cfg::b_tile + c * 8192, src + im.b_plane, 8192, &full[s]);
+        }
+      }
+    }
+  } else if (warp < 4) {
+    if (lane == 0) {
+      const int p = warp - 1;                       // 0: a_hi.b_hi   1: a_lo.b_hi   2: a_hi.b_lo
+      const uint32_t idesc = make_idesc_mn(BN);
+      const uint32_t st_addr = smem_u32(smem_t3);
+      const uint32_t a_off = p == 1 ? Cfg::a_tile : 0, b_off = 2 * Cfg::a_tile + (p == 2 ? Cfg::b_tile : 0);
+      const uint32_t acc = tmem_base + (uint32_t)(p * BN);
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it % Cfg::stages;
+        mbar_wait(&full[s], (uint32_t)(it / Cfg::stages) & 1u);
+        tc_fence_after();
+        const int krem = g.K - it * 64;
+        const int ksteps = krem >= 64 ? 4 : (krem + 15) >> 4;
+        const uint32_t base = st_addr + (uint32_t)s * Cfg::stage;
+        const uint64_t ad = make_smem_desc_mn(base + a_off, 8192), bd = make_smem_desc_mn(base + b_off, 8192);
+        for (int k = 0; k < ksteps; ++k) umma_1sm(acc, ad + 128 * k, bd + 128 * k, idesc, (it | k) == 0 ? 0u : 1u);   // +2048 B per step
+        umma_commit_1sm(&empty[s]);
+      }
+      umma_commit_1sm(acc_full);
+    }
+  } else {
+    const int q = warp & 3, part = (warp - 4) >> 2;
+    constexpr int CPP = BN / 4;
+    const int i = i0 + q * 32 + lane;
+    const int jbase = j0 + part * CPP;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(part * CPP);
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < CPP; c += 8) {
+      uint32_t r0[8], r1[8], r2[8];
+      tmem_ld8_issue(taddr + c, r0);
+      tmem_ld8_issue(taddr + BN + c, r1);
+      tmem_ld8_issue(taddr + 2 * BN + c, r2);
+      tmem_ld_wait();
+      if (i < g.M) {
+        float* crow = g.C + (long long)i * g.cs0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int j = jbase + c + e;
+          if (j < g.N) {
+            float val = (__uint_as_float(r0[e]) + __uint_as_float(r1[e])) + __uint_as_float(r2[e]);
+            if (g.beta != 0.f) val += g.beta * crow[j];
+            crow[j] = val;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::tmem_cols));
+  }
+}
+
 // ---- fp32 matrix -> image (parameters in either orientation, network inputs) -----------------------------------
 struct ImgPackDesc {
   const float* src;        // X(row, k) = src[row*s_row + k*s_k]

@@ -52,7 +52,7 @@ class _Img:
     def __init__(self, dev: torch.device, rows: int, k: int, align: int = 128) -> None:
         self.rows, self.k = rows, k
         self.rpad = (rows + align - 1) // align * align          # the CTA-pair GEMM wants multiples of 256 rows
-        self.chunks = (k + 63) // 64
+        self.chunks = (k + 127) // 128 * 2                       # whole 128-column pairs: a weight-gradient tile reads two chunks
         self.plane = self.chunks * self.rpad * 128
         self.buf = torch.zeros(2 * self.plane, dtype=torch.uint8, device=dev)
 
@@ -84,7 +84,7 @@ def _pack_images(descs: list[tuple[torch.Tensor, int, int, int, int, int, _Img]]
 
 def _gemm(A, a_strides, B, b_strides, Cm, M, N, K, *, beta=0.0, epi=_cabi.EPI_NONE, bias=None, save=None,
           saved=None, seed=0, uid=0, p=0.0, seed_ptr=None, colsum=None, split_k=0, c_stride=None,
-          a_img: _Img | None = None, b_img: _Img | None = None, c_img: _Img | None = None) -> None:
+          a_img: _Img | None = None, b_img: _Img | None = None, c_img: _Img | None = None, mn: bool = False) -> None:
     g = _cabi.GemmArgs()
     if split_k != 1:
         ws, counters = _workspace(Cm.device)
@@ -94,6 +94,7 @@ def _gemm(A, a_strides, B, b_strides, Cm, M, N, K, *, beta=0.0, epi=_cabi.EPI_NO
     if a_img is not None and b_img is not None:
         g.a_img, g.a_plane, g.a_rpad = a_img.ptr, a_img.plane, a_img.rpad
         g.b_img, g.b_plane, g.b_rpad = b_img.ptr, b_img.plane, b_img.rpad
+        g.img_mn = 1 if mn else 0
     else:
         g.A, g.B = A.data_ptr(), B.data_ptr()
         g.as0, g.as1 = a_strides
@@ -296,7 +297,9 @@ class _StackFn(torch.autograd.Function):
             a.W1, a.w1_pitch, a.P, a.p_pitch, a.H = ws[0].data_ptr(), ws[0].stride(0), P[ui].data_ptr(), P[ui].stride(0), widths[0]
             a.pre, a.act, a.pitch = pre[0].data_ptr(), act[0].data_ptr(), pre[0].stride(0)
             a.seed, a.layer_uid, a.p_drop, a.seed_ptr = spec.seed, layer_uid(u.li, u.net, 0), spec.p_drop, spec.seed_ptr
-            aimg = [_img(dev, ("act", l & 1), B, widths[l]) for l in range(L)]     # ping-pong scratch along the chain
+            # images of the activations: the A operand of the next forward GEMM now, the B operand of the weight-gradient
+            # GEMM in the backward pass (one per network and layer: they live until then)
+            aimg = [_img(dev, ("act", ui, l), B, widths[l]) for l in range(L)]
             if L > 1:
                 a.act_img, a.img_plane, a.img_rpad = aimg[0].ptr, aimg[0].plane, aimg[0].rpad
             _call("bcnf_train_pre", a, dev)
@@ -378,8 +381,10 @@ class _StackFn(torch.autograd.Function):
             a.pre, a.pitch, a.d_o, a.d_pre = pre[L - 1].data_ptr(), pre[L - 1].stride(0), d_o.data_ptr(), d_pre[L - 1].data_ptr()
             a.seed, a.layer_uid, a.p_drop, a.seed_ptr = spec.seed, layer_uid(u.li, u.net, L - 1), spec.p_drop, spec.seed_ptr
             a.n_ops = _fill_ops(a.ops, u.ops, params, op_saves, grads)
-            # images of d pre[l] along the chain: ping-pong scratch, except d pre[0], which the other stream reads later
-            gimg = [_img(dev, ("dpre0", ui), B, widths[0])] + [_img(dev, ("dpre", l & 1), B, widths[l]) for l in range(1, L)]
+            # images of d pre[l]: A operand of the next data-gradient GEMM on this stream and of the weight-gradient
+            # GEMMs on the side streams (one per network and layer)
+            gimg = [_img(dev, ("dpre", ui, l), B, widths[l]) for l in range(L)]
+            aimg = [_img(dev, ("act", ui, l), B, widths[l]) for l in range(L)]
             a.dpre_img, a.img_plane, a.img_rpad = gimg[L - 1].ptr, gimg[L - 1].plane, gimg[L - 1].rpad
             _call("bcnf_train_post_bwd", a, dev)
             for l in range(L - 1, 0, -1):
@@ -399,14 +404,15 @@ class _StackFn(torch.autograd.Function):
                 sd.wait_event(done)
             for l in range(L - 1, 0, -1):
                 with torch.cuda.stream(sides[rr % len(sides)]):
-                    _gemm(d_pre[l], (1, d_pre[l].stride(0)), act[l - 1], (act[l - 1].stride(0), 1), dws[l], widths[l],
-                          widths[l - 1], B, split_k=1)
+                    # dW_l = d pre[l]^T act[l-1]: both images read MN-major (contraction over the batch rows)
+                    _gemm(None, None, None, None, dws[l], widths[l], widths[l - 1], B, split_k=1, a_img=gimg[l],
+                          b_img=aimg[l - 1], mn=True)
                 rr += 1
             w1g = dws[0]
             with torch.cuda.stream(sides[rr % len(sides)]):
                 # first Linear: columns [din, din + C) against h
-                _gemm(d_pre[0], (1, d_pre[0].stride(0)), h, (h.stride(0), 1), w1g[:, u.din:], widths[0], Cn, B, split_k=1,
-                      c_stride=w1g.stride(0))
+                _gemm(None, None, None, None, w1g[:, u.din:], widths[0], Cn, B, split_k=1, c_stride=w1g.stride(0),
+                      a_img=gimg[0], b_img=_img(dev, "h", B, Cn), mn=True)
             rr += 1
             with torch.cuda.stream(sides[0]):
                 _colsum(d_pre[L - 1], dbs[L - 1], cols=widths[L - 1])

@@ -172,7 +172,9 @@ typedef struct {
    * up to 128) the TMA-fed kernel runs and A / B may be NULL.  c_img: the values written to C are also written as an
    * image (rows = i, k = j) -- the A operand of the next GEMM of the chain.  Images come from bcnf_img_pack, the
    * c_img of a previous GEMM, or the act_img / dpre_img outputs of bcnf_train_pre / bcnf_train_post_bwd. */
-  const void* a_img; int64_t a_plane; int32_t a_rpad; int32_t pad0;
+  const void* a_img; int64_t a_plane; int32_t a_rpad;
+  int32_t img_mn;        /* 1: weight-gradient mode C(i, j) = sum_r a(r, i) b(r, j): both images are read MN-major (rows = r, the
+                          * contraction index; M / N = their column counts, K = their row count) */
   const void* b_img; int64_t b_plane; int32_t b_rpad; int32_t pad1;
   void* c_img; int64_t c_plane; int32_t c_rpad; int32_t pad2;
 } bcnf_gemm_args_t;

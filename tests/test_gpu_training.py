@@ -119,6 +119,14 @@ def test_image_gemm_chain_matches_fp64(dims, bn):
         # beta = 1
         train._gemm(None, None, None, None, d, B, N, N, split_k=1, a_img=h_img, b_img=w2t_img, beta=1.0)
         assert close(d, 2 * ref_d)
+        # weight-gradient mode: dW = act^T x, both images read MN-major (contraction over their rows)
+        if bn != 32:
+            dw = torch.empty(N, K, device=DEV)
+            train._gemm(None, None, None, None, dw, N, K, B, split_k=1, a_img=h_img, b_img=x_img, mn=True)
+            ref_dw = ref_act.t() @ x.double()
+            assert close(dw, ref_dw)
+            train._gemm(None, None, None, None, dw, N, K, B, split_k=1, a_img=h_img, b_img=x_img, mn=True, beta=1.0)
+            assert close(dw, 2 * ref_dw)
     finally:
         _cabi.lib().bcnf_train_set_gemm_mode(old)
 
