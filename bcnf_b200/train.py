@@ -61,6 +61,25 @@ class _Img:
         return self.buf.data_ptr()
 
 
+class _PoolLease:
+    """A pool of images on loan to one forward / backward pair.  Pools of a given (device, shapes) are recycled through a
+    free list -- their padding stays zero, producers only ever write valid data or zeros -- but never shared by two
+    calls whose saved state is alive at the same time: the lease returns the pool when the autograd context that
+    holds it is released."""
+    _free: dict[tuple, list[list[_Img]]] = {}
+
+    def __init__(self, dev: torch.device, shapes: list[tuple[int, int]]) -> None:
+        self.key = (dev.index or 0, tuple(shapes))
+        free = _PoolLease._free.setdefault(self.key, [])
+        self.images = free.pop() if free else [_Img(dev, rows, k) for rows, k in shapes]
+
+    def __del__(self) -> None:
+        try:
+            _PoolLease._free.setdefault(self.key, []).append(self.images)
+        except Exception:      # interpreter shutdown
+            pass
+
+
 _IMGS: dict[tuple, _Img] = {}
 
 
@@ -251,7 +270,9 @@ class _StackFn(torch.autograd.Function):
         side.wait_stream(main)
         P, p_ready, wimg = [], [], []
         with torch.cuda.stream(side):
-            h_img = _img(dev, "h", B, Cn)
+            # images this call saves for its backward: h (d W1h) and every hidden activation but the last of each network
+            lease = _PoolLease(dev, [(B, Cn)] + [(B, params[u.w0 + l].shape[0]) for u in units for l in range(L - 1)])
+            h_img, act_pool = lease.images[0], lease.images[1:]
             _pack_images([(h, 0, h.stride(0), 1, B, Cn, h_img)], dev)
             for u in units:
                 ws = params[u.w0: u.w0 + spec.n_lin]
@@ -298,8 +319,9 @@ class _StackFn(torch.autograd.Function):
             a.pre, a.act, a.pitch = pre[0].data_ptr(), act[0].data_ptr(), pre[0].stride(0)
             a.seed, a.layer_uid, a.p_drop, a.seed_ptr = spec.seed, layer_uid(u.li, u.net, 0), spec.p_drop, spec.seed_ptr
             # images of the activations: the A operand of the next forward GEMM now, the B operand of the weight-gradient
-            # GEMM in the backward pass (one per network and layer: they live until then)
-            aimg = [_img(dev, ("act", ui, l), B, widths[l]) for l in range(L)]
+            # GEMM in the backward pass.  They are part of what this call saves for its backward, so they belong to the
+            # call (allocated zeroed: the padding must be zero), not to a shape-keyed cache
+            aimg = act_pool[ui * (L - 1): (ui + 1) * (L - 1)] + [None]
             if L > 1:
                 a.act_img, a.img_plane, a.img_rpad = aimg[0].ptr, aimg[0].plane, aimg[0].rpad
             _call("bcnf_train_pre", a, dev)
@@ -319,12 +341,14 @@ class _StackFn(torch.autograd.Function):
             a.ls_save, a.ydst_save = ls.data_ptr(), ydst.data_ptr()
             a.n_ops = _fill_ops(a.ops, u.ops, params, op_saves, None)
             _call("bcnf_train_post", a, dev)
-            saved_units.append((y, pre, act, ls, ydst, op_saves))
+            saved_units.append((y, pre, act, ls, ydst, op_saves, aimg))
             y = y_out
         main.wait_stream(side)
         ctx.spec, ctx.params, ctx.h = spec, params, h
         ctx.plan = (lead, units, lead_saves, saved_units)
         ctx.wimg = wimg
+        ctx.h_img = h_img
+        ctx.lease = lease
         ctx.keep = P
         return y, ld
 
@@ -359,14 +383,16 @@ class _StackFn(torch.autograd.Function):
                 if typ == _cabi.GLUE_ACTNORM:
                     grads[po], grads[po + 1] = zeros_like(params[po]), zeros_like(params[po + 1])
         dh = new(B, Cn)
-        keep: list[Any] = []                                 # everything the side streams read stays alive until the join
+        grad_lease = _PoolLease(dev, [(B, params[u.w0 + l].shape[0]) for u in units for l in range(L)])
+        grad_pool = grad_lease.images
+        keep: list[Any] = [grad_lease]                                 # everything the side streams read stays alive until the join
         for sd in sides:
             sd.wait_stream(main)
         first_dh = True
         rr = 0
         for ui in range(len(units) - 1, -1, -1):
             u = units[ui]
-            y_in, pre, act, ls, ydst, op_saves = saved_units[ui]
+            y_in, pre, act, ls, ydst, op_saves, aimg = saved_units[ui]
             ws = params[u.w0: u.w0 + spec.n_lin]
             widths = [w.shape[0] for w in ws[:-1]]
             no = 2 * u.dout
@@ -383,8 +409,7 @@ class _StackFn(torch.autograd.Function):
             a.n_ops = _fill_ops(a.ops, u.ops, params, op_saves, grads)
             # images of d pre[l]: A operand of the next data-gradient GEMM on this stream and of the weight-gradient
             # GEMMs on the side streams (one per network and layer)
-            gimg = [_img(dev, ("dpre", ui, l), B, widths[l]) for l in range(L)]
-            aimg = [_img(dev, ("act", ui, l), B, widths[l]) for l in range(L)]
+            gimg = grad_pool[ui * L: (ui + 1) * L]
             a.dpre_img, a.img_plane, a.img_rpad = gimg[L - 1].ptr, gimg[L - 1].plane, gimg[L - 1].rpad
             _call("bcnf_train_post_bwd", a, dev)
             for l in range(L - 1, 0, -1):
@@ -412,7 +437,7 @@ class _StackFn(torch.autograd.Function):
             with torch.cuda.stream(sides[rr % len(sides)]):
                 # first Linear: columns [din, din + C) against h
                 _gemm(None, None, None, None, w1g[:, u.din:], widths[0], Cn, B, split_k=1, c_stride=w1g.stride(0),
-                      a_img=gimg[0], b_img=_img(dev, "h", B, Cn), mn=True)
+                      a_img=gimg[0], b_img=ctx.h_img, mn=True)
             rr += 1
             with torch.cuda.stream(sides[0]):
                 _colsum(d_pre[L - 1], dbs[L - 1], cols=widths[L - 1])
