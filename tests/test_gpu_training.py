@@ -258,3 +258,26 @@ def test_cuda_graph_trainer_matches_eager_statistics():
     assert len({round(l, 6) for l in losses[:6]}) > 1          # replays are not identical: masks and weights change
     with pytest.raises(ValueError):
         bcnf_b200.Trainer(model, torch.optim.Adam(model.parameters(), lr=1e-3), cuda_graph=True)
+
+
+def test_two_forwards_before_one_backward_keep_their_own_saved_state():
+    """The operand images a forward pass saves for its backward belong to that call (leased pools, bcnf_b200/train.py):
+    interleaving two forward passes before the backward gives the same gradients as running them one after the other."""
+    model = _model(19, [128, 128, 128], 3, 24, dropout=0.0).train()
+    g = torch.Generator().manual_seed(9)
+    y1, h1 = torch.randn(200, 19, generator=g).to(DEV), torch.randn(200, 24, generator=g).to(DEV)
+    y2, h2 = torch.randn(200, 19, generator=g).to(DEV), torch.randn(200, 24, generator=g).to(DEV)
+    nll = lambda z, ld: (0.5 * (z ** 2).sum(1) - ld).mean()
+    params = [p for p in model.parameters() if p.requires_grad]
+    z1, ld1 = train.stack_forward_train(model, y1, h1, seed=3)
+    z2, ld2 = train.stack_forward_train(model, y2, h2, seed=3)          # second forward while the first one's state is alive
+    (nll(z1, ld1) + nll(z2, ld2)).backward()
+    both = [p.grad.clone() for p in params]
+    for p in params:
+        p.grad = None
+    z1, ld1 = train.stack_forward_train(model, y1, h1, seed=3)
+    nll(z1, ld1).backward()
+    z2, ld2 = train.stack_forward_train(model, y2, h2, seed=3)
+    nll(z2, ld2).backward()
+    for a, p in zip(both, params):
+        assert rel_err(a.cpu().numpy(), p.grad.cpu().numpy()) < 1e-6
