@@ -95,34 +95,47 @@ def lstm_supported(net: Any) -> bool:
             and (lstm.input_size + 63) // 64 + hc <= 16 and all(p.dtype == torch.float32 for p in net.parameters()))
 
 
+def lstm_cat_weights(lstm: nn.LSTM, layer: int, d: int) -> tuple[torch.Tensor, torch.Tensor, int]:
+    """Gate-interleaved [W_ih | W_hh] of one layer / direction in the K layout of the step GEMM, and b_ih + b_hh.
+
+    Row n = 4 * unit + gate (nn.LSTM gate order i, f, g, o).  Columns: the input part -- layer 0: the features of x_t,
+    padded to whole 64-column chunks; deeper layers: one block of ceil(H/64) chunks per direction of the layer below
+    (its h images) -- followed by ceil(H/64) chunks for h_(t-1); everything outside the real columns is zero.
+    Returns (W (4H, K), bias (4H), number of input columns).  Pure torch: also the CPU check of the layout."""
+    sfx = f"_l{layer}" + ("_reverse" if d == 1 else "")
+    w_ih, w_hh = getattr(lstm, "weight_ih" + sfx).detach(), getattr(lstm, "weight_hh" + sfx).detach()
+    b = (getattr(lstm, "bias_ih" + sfx).detach() + getattr(lstm, "bias_hh" + sfx).detach())
+    H = lstm.hidden_size
+    hc = (H + 63) // 64
+    dirs = 2 if lstm.bidirectional else 1
+    dev = w_ih.device
+    idx = (torch.arange(4, device=dev).view(1, 4) * H + torch.arange(H, device=dev).view(H, 1)).reshape(-1)
+    wi, wh = w_ih[idx], w_hh[idx]
+    in_cols = (lstm.input_size + 63) // 64 * 64 if layer == 0 else dirs * hc * 64
+    wc = torch.zeros(4 * H, in_cols + hc * 64, device=dev)
+    if layer == 0:
+        wc[:, :lstm.input_size] = wi
+    else:
+        for d2 in range(dirs):          # the directions of the layer below arrive as separate image chunks
+            wc[:, d2 * hc * 64: d2 * hc * 64 + H] = wi[:, d2 * H:(d2 + 1) * H]
+    wc[:, in_cols: in_cols + H] = wh
+    return wc, b[idx].contiguous(), in_cols
+
+
 def _lstm_weights(net: Any, layer: int, d: int, dev: torch.device) -> tuple[_Img, torch.Tensor]:
-    """Gate-interleaved [W_ih | W_hh] image (rows n = 4*unit + gate) and bias b_ih + b_hh of one layer / direction."""
+    """Operand image of lstm_cat_weights and the interleaved bias, cached per parameter version."""
     lstm = net.lstm
     sfx = f"_l{layer}" + ("_reverse" if d == 1 else "")
-    w_ih, w_hh = getattr(lstm, "weight_ih" + sfx), getattr(lstm, "weight_hh" + sfx)
-    b_ih, b_hh = getattr(lstm, "bias_ih" + sfx), getattr(lstm, "bias_hh" + sfx)
-    key = tuple((t.data_ptr(), t._version) for t in (w_ih, w_hh, b_ih, b_hh))
+    ts = [getattr(lstm, n + sfx) for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+    key = tuple((t.data_ptr(), t._version) for t in ts)
     cache = net.__dict__.setdefault("_tc_lstm", {})
     hit = cache.get((layer, d))
     if hit is not None and hit[0] == key:
         return hit[1], hit[2]
-    H = lstm.hidden_size
-    hc = (H + 63) // 64
-    dirs = 2 if lstm.bidirectional else 1
-    idx = (torch.arange(4, device=dev).view(1, 4) * H + torch.arange(H, device=dev).view(H, 1)).reshape(-1)
     with torch.no_grad():
-        wi, wh = w_ih.detach()[idx], w_hh.detach()[idx]
-        in_cols = (lstm.input_size + 63) // 64 * 64 if layer == 0 else dirs * hc * 64
-        wc = torch.zeros(4 * H, in_cols + hc * 64, device=dev)
-        if layer == 0:
-            wc[:, :lstm.input_size] = wi
-        else:
-            for d2 in range(dirs):      # the previous layer's directions arrive as separate image chunks
-                wc[:, d2 * hc * 64: d2 * hc * 64 + H] = wi[:, d2 * H:(d2 + 1) * H]
-        wc[:, in_cols: in_cols + H] = wh
-        bias = (b_ih.detach() + b_hh.detach())[idx].contiguous()
-    im = _Img(dev, 4 * H, wc.shape[1], align=256)
-    _pack_images([(wc, 0, wc.stride(0), 1, 4 * H, wc.shape[1], im)], dev)
+        wc, bias, _ = lstm_cat_weights(lstm, layer, d)
+    im = _Img(dev, wc.shape[0], wc.shape[1], align=256)
+    _pack_images([(wc, 0, wc.stride(0), 1, wc.shape[0], wc.shape[1], im)], dev)
     cache[(layer, d)] = (key, im, bias)
     return im, bias
 

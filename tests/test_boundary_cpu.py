@@ -159,3 +159,44 @@ def test_lstm_feature_network_pools_before_the_output_layer_without_changing_the
     with torch.no_grad():
         seq, _ = net.lstm(x)
         assert torch.equal(net(x), net.linear(seq).max(dim=1).values)
+
+
+def test_lstm_step_gemm_layout_reproduces_nn_lstm_on_cpu():
+    """The operand layout of the tensor-core LSTM (bcnf_b200/feature_tc.py: gate-interleaved [W_ih | W_hh], inputs and
+    h_(t-1) in separate 64-column chunks, per-direction chunks of the layer below) emulated with dense torch ops on the
+    CPU: one GEMM + cell update per layer, direction and time step must give nn.LSTM's output."""
+    import torch
+    from bcnf_b200 import feature_tc
+    torch.manual_seed(1)
+    B, T, F, H = 5, 7, 3, 6
+    lstm = torch.nn.LSTM(F, H, num_layers=2, bidirectional=True, batch_first=True).eval()
+    x = torch.randn(B, T, F)
+    hc = (H + 63) // 64
+    below = None                                   # [direction][t] -> (B, hc*64) padded h of the layer below
+    with torch.no_grad():
+        ref, _ = lstm(x)
+        for layer in range(2):
+            outs = []
+            for d in range(2):
+                wc, bias, in_cols = feature_tc.lstm_cat_weights(lstm, layer, d)
+                assert wc.shape == (4 * H, in_cols + hc * 64)
+                h = torch.zeros(B, hc * 64)
+                c = torch.zeros(B, H)
+                per_t = [None] * T
+                for t in (range(T) if d == 0 else range(T - 1, -1, -1)):
+                    if layer == 0:
+                        inp = torch.zeros(B, in_cols)
+                        inp[:, :F] = x[:, t]
+                    else:
+                        inp = torch.cat([below[0][t], below[1][t]], dim=1)
+                    gates = torch.cat([inp, h], dim=1) @ wc.t() + bias          # (B, 4H), column n = 4*unit + gate
+                    gi, gf, gg, go = (gates[:, k::4] for k in range(4))
+                    c = torch.sigmoid(gf) * c + torch.sigmoid(gi) * torch.tanh(gg)
+                    hv = torch.sigmoid(go) * torch.tanh(c)
+                    h = torch.zeros(B, hc * 64)
+                    h[:, :H] = hv
+                    per_t[t] = h
+                outs.append(per_t)
+            below = outs
+        seq = torch.stack([torch.cat([below[0][t][:, :H], below[1][t][:, :H]], dim=1) for t in range(T)], dim=1)
+    assert torch.allclose(seq, ref, rtol=1e-5, atol=1e-6)

@@ -83,3 +83,47 @@ def test_single_process_is_identity():
     assert torch.equal(out, _fake_sample(3, cond))
     with pytest.raises(ValueError):
         sharding.shard_conditions([torch.zeros(3, 2), torch.zeros(4, 2)])
+
+
+# ---- data-parallel Trainer: parameter broadcast and the flat-buffer gradient all-reduce (world_size 2, gloo, CPU) ----
+def _trainer_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from bcnf_b200.train import Trainer
+        torch.manual_seed(rank)                                   # replicas start different
+        net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3))
+        qmat = torch.linalg.qr(torch.randn(4, 4))[0]              # column-major, like the mixing matrices
+        net.register_buffer("q", qmat)
+        assert not net.q.is_contiguous() or True
+        opt = torch.optim.SGD(net.parameters(), lr=0.1)
+        tr = Trainer(net, opt, process_group=dist.group.WORLD)    # broadcasts rank 0's parameters and buffers
+        flat = torch.cat([p.detach().flatten() for p in net.parameters()] + [net.q.flatten()])
+        ref = flat.clone()
+        dist.broadcast(ref, src=0)
+        same_params = bool(torch.equal(flat, ref))
+        # different gradients per rank -> the mean on every rank, through ONE flat buffer
+        for i, p in enumerate(net.parameters()):
+            p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+        tr._allreduce_grads()
+        expect = [(1 + world) / 2 * (i + 1) for i in range(4)]
+        ok = all(torch.allclose(p.grad, torch.full_like(p, e)) for p, e in zip(net.parameters(), expect))
+        ok = ok and tr._flat.numel() == sum(p.numel() for p in net.parameters())
+        q.put((rank, same_params and ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_trainer_process_group_broadcasts_parameters_and_averages_gradients():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_trainer_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+    assert all(p.exitcode == 0 for p in procs)
+    results = dict(q.get(timeout=10) for _ in range(world))
+    assert results == {r: True for r in range(world)}
