@@ -200,3 +200,23 @@ def test_lstm_step_gemm_layout_reproduces_nn_lstm_on_cpu():
             below = outs
         seq = torch.stack([torch.cat([below[0][t][:, :H], below[1][t][:, :H]], dim=1) for t in range(T)], dim=1)
     assert torch.allclose(seq, ref, rtol=1e-5, atol=1e-6)
+
+
+def test_training_plan_splits_the_layer_list_into_networks_and_glue_ops():
+    """bcnf_b200/train.py: model.layers -> glue ops before the first coupling + one unit per conditioner network with the
+    ActNorm / mixing layers that follow it (reference layer order, cnf.py:392-423)."""
+    from bcnf_b200 import _cabi, train
+    kinds = ["actnorm", "coupling", "ortho", "actnorm", "coupling", "ortho", "actnorm", "coupling"]
+    spec = train._Spec(kinds, n_lin=4, two_way=False, size=19, n_conditions=8, p_drop=0.0, seed=0)
+    lead, units = train._plan(spec)
+    assert lead == [(_cabi.GLUE_ACTNORM, 0)]
+    assert [(u.li, u.net, u.src0, u.din, u.dst0, u.dout) for u in units] == [(1, 0, 0, 10, 10, 9), (4, 0, 0, 10, 10, 9),
+                                                                             (7, 0, 0, 10, 10, 9)]
+    # parameter offsets: actnorm (2), coupling (2 * n_lin), ortho (1), ...
+    assert [u.w0 for u in units] == [2, 13, 24]
+    assert units[0].ops == [(_cabi.GLUE_ORTHO, 10), (_cabi.GLUE_ACTNORM, 11)] and units[2].ops == []
+    spec2 = train._Spec(["coupling", "ortho", "coupling"], n_lin=3, two_way=True, size=21, n_conditions=4, p_drop=0.0, seed=0)
+    lead2, units2 = train._plan(spec2)
+    assert lead2 == [] and [(u.li, u.net, u.src0, u.din, u.dst0, u.dout) for u in units2] == [
+        (0, 0, 0, 11, 11, 10), (0, 1, 11, 10, 0, 11), (2, 0, 0, 11, 11, 10), (2, 1, 11, 10, 0, 11)]
+    assert units2[0].ops == [] and units2[1].ops == [(_cabi.GLUE_ORTHO, 12)]

@@ -281,3 +281,48 @@ def test_two_forwards_before_one_backward_keep_their_own_saved_state():
     nll(z2, ld2).backward()
     for a, p in zip(both, params):
         assert rel_err(a.cpu().numpy(), p.grad.cpu().numpy()) < 1e-6
+
+
+def _bf16_round(x32: np.ndarray) -> np.ndarray:
+    """fp32 -> nearest bf16 (ties to even), returned as the 16-bit pattern."""
+    u = x32.astype(np.float32).view(np.uint32).astype(np.uint64)
+    u = u + 0x7FFF + ((u >> 16) & 1)
+    return (u >> 16).astype(np.uint16)
+
+
+def _image_reference(x: np.ndarray, rpad: int, chunks: int) -> np.ndarray:
+    """The operand image of include/bcnf_b200.h restated in numpy: bf16 hi plane then lo plane, each
+    [chunks][rpad rows][128 bytes], 16-byte units of a row XOR-swizzled by (row & 7), zero outside x."""
+    rows, k = x.shape
+    hi = _bf16_round(x)
+    hi_f = (hi.astype(np.uint32) << 16).view(np.float32)
+    lo = _bf16_round(x - hi_f)
+    planes = np.zeros((2, chunks, rpad, 64), dtype=np.uint16)
+    for plane, src in enumerate((hi, lo)):
+        for c in range(chunks):
+            blk = np.zeros((rows, 64), dtype=np.uint16)
+            w = max(0, min(64, k - 64 * c))
+            blk[:, :w] = src[:, 64 * c: 64 * c + w]
+            units = blk.reshape(rows, 8, 8)                              # 8 units of 8 bf16 (16 bytes)
+            r = np.arange(rows)
+            for u in range(8):
+                planes[plane, c, :rows, :].reshape(rows, 8, 8)[r, u ^ (r & 7)] = units[:, u]
+    return planes.reshape(-1).view(np.uint8)
+
+
+@pytest.mark.parametrize("rows,k", [(5, 3), (77, 90), (256, 526), (300, 1360)])
+def test_operand_image_layout_is_bit_exact(rows, k):
+    """bcnf_img_pack against the numpy restatement of the format, both source orientations."""
+    g = torch.Generator().manual_seed(rows * 1000 + k)
+    x = torch.randn(rows, k, generator=g)
+    dev = torch.device(DEV)
+    im = train._Img(dev, rows, k)
+    xd = x.to(DEV)
+    train._pack_images([(xd, 0, k, 1, rows, k, im)], dev)
+    ref = _image_reference(x.numpy(), im.rpad, im.chunks)
+    assert np.array_equal(im.buf.cpu().numpy(), ref)
+    # the same matrix read through its transpose (row index contiguous in memory)
+    xt = x.t().contiguous().to(DEV)                                      # (k, rows): X(row, col) = xt[col, row]
+    im2 = train._Img(dev, rows, k)
+    train._pack_images([(xt, 0, 1, rows, rows, k, im2)], dev)
+    assert np.array_equal(im2.buf.cpu().numpy(), ref)
