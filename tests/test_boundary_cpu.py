@@ -220,3 +220,46 @@ def test_training_plan_splits_the_layer_list_into_networks_and_glue_ops():
     assert lead2 == [] and [(u.li, u.net, u.src0, u.din, u.dst0, u.dout) for u in units2] == [
         (0, 0, 0, 11, 11, 10), (0, 1, 11, 10, 0, 11), (2, 0, 0, 11, 11, 10), (2, 1, 11, 10, 0, 11)]
     assert units2[0].ops == [] and units2[1].ops == [(_cabi.GLUE_ORTHO, 12)]
+
+
+def test_tensor_core_feature_paths_only_take_what_they_reproduce():
+    """bcnf_b200/feature_tc.py host logic: which feature-network modules the tensor-core paths accept."""
+    import torch
+    from torch import nn
+    from bcnf_b200 import feature_tc
+    from bcnf_b200.feature_network import FullyConnectedFeatureNetwork, LSTMFeatureNetwork
+    assert feature_tc.supported(FullyConnectedFeatureNetwork([90, 310, 310, 1360], dropout=0.1))
+    assert feature_tc.supported(FullyConnectedFeatureNetwork([90, 80]))
+    assert not feature_tc.supported(FullyConnectedFeatureNetwork([90, 64, 8], activation=nn.ReLU))
+    assert not feature_tc.supported(FullyConnectedFeatureNetwork([90, 64, 8], batch_norm=True))
+    assert not feature_tc.supported(FullyConnectedFeatureNetwork([90, 64, 8]).double())
+    ok = LSTMFeatureNetwork(3, 140, 1360, num_layers=2, bidirectional=True, pooling="mean")
+    assert feature_tc.lstm_supported(ok)
+    assert not feature_tc.lstm_supported(LSTMFeatureNetwork(3, 140, 1360, num_layers=2, pooling="max"))
+    assert not feature_tc.lstm_supported(LSTMFeatureNetwork(3, 140, 1360, num_layers=1, pool_axis="reference"))
+    assert not feature_tc.lstm_supported(LSTMFeatureNetwork(3, 141, 64, num_layers=1))        # odd hidden size
+    assert not feature_tc.lstm_supported(LSTMFeatureNetwork(3, 512, 64, num_layers=1))        # 4H > 1024
+    # CPU tensors, training mode or autograd never reach the tensor-core path
+    ok.tc_passes = 3
+    x = torch.randn(4, 30, 3)
+    with torch.no_grad():
+        assert ok.eval()(x).shape == (4, 1360)
+
+
+def test_image_pool_leases_are_recycled_but_never_shared():
+    import gc
+    import torch
+    from bcnf_b200 import train
+    dev = torch.device("cpu")
+    shapes = [(8, 70), (8, 130)]
+    a = train._PoolLease(dev, shapes)
+    b = train._PoolLease(dev, shapes)                       # alive at the same time: different buffers
+    assert a.images[0].buf.data_ptr() != b.images[0].buf.data_ptr()
+    assert a.images[1].chunks == 4 and a.images[0].rpad == 128 and not a.images[0].buf.any()
+    ptr = a.images[0].buf.data_ptr()
+    del a
+    gc.collect()
+    c = train._PoolLease(dev, shapes)                       # the released pool comes back
+    assert c.images[0].buf.data_ptr() == ptr
+    d = train._PoolLease(dev, [(8, 70)])                    # other shapes: other pool
+    assert d.images[0].buf.data_ptr() not in (ptr, b.images[0].buf.data_ptr())
