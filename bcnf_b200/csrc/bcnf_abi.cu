@@ -926,6 +926,12 @@ extern "C" int bcnf_cond_project(bcnf_flow_t* f, const float* h, int64_t n_inst,
     const long long cap_rows = std::min<long long>((n_inst + 255) / 256 * 256, slice);
     const long long need = 2 * (long long)chunks * cap_rows * 128;
     if (need > f->h_img_bytes) {
+      // (growing the scratch allocates: not possible while the caller's stream is being captured into a CUDA graph)
+      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+      CUDA_TRY(cudaStreamIsCapturing(stream, &cap));
+      if (cap != cudaStreamCaptureStatusNone)
+        return fail(BCNF_E_STATE, "bcnf_cond_project: the scratch image for %lld instances is not allocated yet; call once "
+                                  "with this many instances outside CUDA-graph capture", (long long)n_inst);
       CUDA_TRY(cudaStreamSynchronize(stream));
       if (f->d_h_img) CUDA_TRY(cudaFree(f->d_h_img));
       f->d_h_img = nullptr; f->h_img_bytes = 0;
