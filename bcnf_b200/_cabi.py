@@ -23,7 +23,7 @@ PREC_FP32, PREC_BF16X3, PREC_BF16 = 0, 1, 2
 KERNEL_NAMES = {0: "rowthread", 1: "tiled", 2: "tcgen05"}
 
 EXPORTS = ["bcnf_abi_version", "bcnf_last_error", "bcnf_flow_create", "bcnf_flow_destroy",
-           "bcnf_flow_info", "bcnf_flow_set_params", "bcnf_cond_project", "bcnf_flow_forward",
+           "bcnf_flow_info", "bcnf_flow_debug_words", "bcnf_flow_set_params", "bcnf_cond_project", "bcnf_flow_forward",
            "bcnf_flow_inverse", "bcnf_train_gemm", "bcnf_train_colsum", "bcnf_train_dropout_mask",
            "bcnf_train_set_gemm_mode", "bcnf_train_gemm_trace", "bcnf_train_pre", "bcnf_train_post",
            "bcnf_train_post_bwd", "bcnf_train_pre_bwd", "bcnf_img_pack", "bcnf_gemm_img", "bcnf_gemm_img_gelu", "bcnf_gemm_img_set_trace", "bcnf_lstm_step"]
@@ -153,6 +153,7 @@ def lib() -> C.CDLL:
     L.bcnf_flow_create.argtypes = [C.POINTER(FlowDesc), C.POINTER(C.c_int32), C.POINTER(C.c_void_p)]
     L.bcnf_flow_destroy.argtypes = [C.c_void_p]
     L.bcnf_flow_info.argtypes = [C.c_void_p, C.POINTER(FlowInfo)]
+    L.bcnf_flow_debug_words.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
     L.bcnf_flow_set_params.argtypes = [C.c_void_p, C.POINTER(OpParams), C.c_void_p]
     L.bcnf_cond_project.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     flow_args = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,

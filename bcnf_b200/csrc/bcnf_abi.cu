@@ -21,6 +21,7 @@
 #include "train_glue.cuh"
 #include "gemm_img2.cuh"
 #include "flow_layered.cuh"
+#include "flow_tc2.cuh"
 
 using namespace bcnf;
 
@@ -143,6 +144,20 @@ struct bcnf_flow {
   float* d_lo = nullptr;                      // (kLayeredBatch, 32)
   unsigned char* d_lact[2] = {nullptr, nullptr};
   long long lact_plane = 0;
+  // second-generation fused kernel (flow_tc2.cuh): weight images of every Linear of every conditioner network, the
+  // per-direction table of their offsets, and one activation scratch per stream that has run the kernel
+  bool tc1_ok = false;                        // the first-generation kernel's plan (f.td) is valid
+  bool s2_ok = false;
+  bool s2_use = false;                        // dispatch forward / inverse to it (decided once, at create)
+  S2Dims s2;
+  unsigned char* d_s2_img = nullptr;
+  long long s2_img_bytes = 0;
+  long long* d_s2_off[2] = {nullptr, nullptr};
+  struct S2Scratch { cudaStream_t stream; unsigned char* act; };
+  std::vector<S2Scratch> s2_scratch;
+  unsigned int* d_s2_dbg = nullptr;            // device alias of h_s2_dbg (mapped pinned memory: readable after a trap)
+  unsigned int* h_s2_dbg = nullptr;
+  int s2_ctas = 0;
 };
 
 static const int kLayeredBatch = 74 * 256;    // rows per batch: 74 row tiles x 3 column tiles = 3 full rounds of 74 CTA pairs
@@ -262,6 +277,10 @@ extern "C" int bcnf_flow_destroy(bcnf_flow_t* f) {
   for (int b = 0; b < 2; ++b) if (f->d_lact[b]) cudaFree(f->d_lact[b]);
   if (f->d_h_img) cudaFree(f->d_h_img);
   if (f->d_proj_nets) cudaFree(f->d_proj_nets);
+  if (f->d_s2_img) cudaFree(f->d_s2_img);
+  for (int d = 0; d < 2; ++d) if (f->d_s2_off[d]) cudaFree(f->d_s2_off[d]);
+  for (auto& sc : f->s2_scratch) if (sc.act) cudaFree(sc.act);
+  if (f->h_s2_dbg) cudaFreeHost(f->h_s2_dbg);
   delete f;
   return BCNF_OK;
 }
@@ -351,6 +370,67 @@ static const char* tc_plan(bcnf_flow& f, int npass) {
   return nullptr;
 }
 
+
+// ---- second-generation fused kernel (flow_tc2.cuh): layer / chunk structure, shared-memory carve-up ---------------
+static void s2_set_chunks(S2Layer& ly, int np) {
+  const int n = (np + 255) / 256;
+  for (int i = 0; i < kS2MaxChunks; ++i) ly.chunk_n[i] = 0;
+  ly.n_chunks = n;
+  if (n == 1) { ly.chunk_n[0] = np; return; }
+  const int base = round_up((np + n - 1) / n, 64);      // all but the last chunk cover whole 64-column image chunks
+  for (int i = 0, left = np; i < n; ++i) { ly.chunk_n[i] = std::min(base, left); left -= ly.chunk_n[i]; }
+}
+
+// Returns 0 and fills f.s2 if the stack fits the kernel, else a reason string.
+static const char* s2_plan(bcnf_flow& f, int npass) {
+  const StackDims& sd = f.sd;
+  S2Dims& d = f.s2;
+  memset(&d, 0, sizeof(d));
+  if (sd.D > kS2YPitch - 1) return "size > 28";
+  const int PL = npass == 3 ? 2 : 1;
+  int a_kchunks = 1;
+  for (int s = 0; s < 2; ++s) {
+    const HalfLayout& hl = sd.half[s];
+    S2Half& tl = d.half[s];
+    if (hl.din > 16) return "own-half width > 16";
+    if (2 * hl.dop > 32) return "last Linear wider than 32 columns";
+    if (hl.L + 1 > kTcMaxLayers) return "too many hidden layers";
+    tl.L = hl.L;
+    tl.n_last = round_up(2 * hl.dop, 16);
+    long long off = 0;
+    for (int l = 0; l <= hl.L; ++l) {
+      S2Layer& ly = tl.layer[l];
+      if (l < hl.L && (hl.h[l] < 48 || hl.hp[l] > 1024)) return "hidden width outside [48, 1024]";
+      const int k_real = l == 0 ? hl.din : hl.h[l - 1];
+      const int np = l == hl.L ? tl.n_last : hl.hp[l];
+      s2_set_chunks(ly, np);
+      if (ly.n_chunks > kS2MaxChunks) return "too many N chunks";
+      ly.n_kst = (k_real + 63) / 64;
+      ly.last_ksteps = (k_real - 64 * (ly.n_kst - 1) + 15) / 16;
+      ly.n_img = l < hl.L ? (np + 63) / 64 : 0;
+      ly.w_rpad = round_up(np, 32);
+      ly.w_plane = (long long)ly.n_kst * ly.w_rpad * 128;
+      ly.w_off = off;
+      off += 2 * ly.w_plane;
+      a_kchunks = std::max(a_kchunks, ly.n_img);
+    }
+    tl.net_bytes = off;
+  }
+  d.n_halfops = f.n_half;
+  d.two_way = f.desc.two_way ? 1 : 0;
+  d.a_kchunks = a_kchunks;
+  d.a_plane = (long long)a_kchunks * kS2Tile;
+  d.b_off = PL * kS2Tile;
+  d.b_lo_off = d.b_off + kS2Tile;
+  d.stage_bytes = 2 * PL * kS2Tile;
+  d.stg_off = kS2Stages * d.stage_bytes;
+  d.misc_off = d.stg_off + 2 * kS2Tile;
+  d.smem_bytes = d.misc_off + kS2MiscBytes;
+  d.cta_bytes = 2LL * PL * d.a_plane;
+  if (d.smem_bytes > f.max_smem_optin) return "stages + staging exceed shared memory";
+  return nullptr;
+}
+
 template <typename K>
 static int opt_in_smem(K kernel, size_t bytes) {
   CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -428,10 +508,21 @@ extern "C" int bcnf_flow_create(const bcnf_flow_desc_t* desc, const int32_t* op_
   if (desc->precision != BCNF_PREC_FP32 && allow_rowthread) {   // BCNF_FORCE_KERNEL=tiled pins the fp32 tiled kernel
     const int npass = desc->precision == BCNF_PREC_BF16X3 ? 3 : 1;
     if (prop.major != 10) { delete f; return fail(BCNF_E_UNSUPPORTED, "tcgen05 path needs an sm_100 device (got sm_%d%d)", prop.major, prop.minor); }
-    if (const char* why = tc_plan(*f, npass)) { delete f; return fail(BCNF_E_UNSUPPORTED, "tensor-core path: %s", why); }
+    // two generations of the fused kernel: the second (128 rows per CTA, activations through L2, flow_tc2.cuh) where the
+    // stack fits it, else the first (64 rows per CTA, activations in shared memory, flow_tc.cuh);
+    // BCNF_FLOW_TC=1 pins the first generation (A/B timing, tests of both).  Read once, here.
+    const char* why1 = tc_plan(*f, npass);
+    const char* why2 = s2_plan(*f, npass);
+    if (why1 && why2) { delete f; return fail(BCNF_E_UNSUPPORTED, "tensor-core path: %s", why2); }
+    f->tc1_ok = why1 == nullptr;
+    f->s2_ok = why2 == nullptr;
     f->npass = npass;
     f->kernel = BCNF_KERNEL_TCGEN05;
     f->rows_per_cta = kTcRows;
+    const char* gen = getenv("BCNF_FLOW_TC");
+    f->s2_use = f->s2_ok && !(gen && atoi(gen) == 1 && f->tc1_ok);
+    f->s2_ctas = 2 * (f->num_sms / 2);
+    if (f->s2_use) f->rows_per_cta = kS2Rows;
   } else if (rowthread_ok) {
     f->kernel = BCNF_KERNEL_ROWTHREAD;
     f->rows_per_cta = kRowThreadBlock;
@@ -483,7 +574,7 @@ extern "C" int bcnf_flow_create(const bcnf_flow_desc_t* desc, const int32_t* op_
     bcnf_flow_destroy(f);
     return fail(BCNF_E_NOMEM, "pack table allocation failed");
   }
-  if (f->npass) {
+  if (f->npass && f->tc1_ok) {
     // one tile stream per conditioner network, in forward layer order; both directions index into it
     const int n = (int)f->op_types.size();
     f->tc_off_by_layer.assign(2 * n, -1);
@@ -581,6 +672,14 @@ extern "C" int bcnf_flow_create(const bcnf_flow_desc_t* desc, const int32_t* op_
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { bcnf_flow_destroy(f); return fail((int)e, "create: %s", cudaGetErrorString(e)); }
   *out = f;
+  return BCNF_OK;
+}
+
+// Watchdog record of the second-generation fused kernel: {wait code, aux, block, thread} of the first wait that timed
+// out (all zero in a healthy run).  Host memory: still readable after the trap has killed the context.
+extern "C" int bcnf_flow_debug_words(const bcnf_flow_t* f, uint32_t* out4) {
+  if (!f || !out4) return fail(BCNF_E_ARG, "bcnf_flow_debug_words: null argument");
+  for (int i = 0; i < 4; ++i) out4[i] = f->h_s2_dbg ? f->h_s2_dbg[i] : 0u;
   return BCNF_OK;
 }
 
@@ -700,6 +799,105 @@ static int build_layered_images(bcnf_flow* f, cudaStream_t stream) {
   return BCNF_OK;
 }
 
+
+// Weight images of every Linear of every conditioner network for flow_tc2.cuh, made from the forward program's fp32
+// blob (input-major matrices: W1a [DINP][HP0], W_l [HP(l-1)][HP(l)], last Linear [HP(L-1)][2*DOP] with t | s halves),
+// and the per-direction table: device op index -> byte offset of its network's images.
+static int build_s2_images(bcnf_flow* f, cudaStream_t stream) {
+  if (!f->s2_ok) return BCNF_OK;
+  const StackDims& sd = f->sd;
+  const Program& p = f->prog[0];
+  std::vector<long long> net_off;          // per conditioner network, forward program order
+  long long bytes = 0;
+  for (const auto& op : p.ops)
+    if (op.type == DOP_HALF) { net_off.push_back(bytes); bytes += f->s2.half[op.src].net_bytes; }
+  if (bytes > f->s2_img_bytes) {
+    if (f->d_s2_img) CUDA_TRY(cudaFree(f->d_s2_img));
+    f->d_s2_img = nullptr; f->s2_img_bytes = 0;
+    CUDA_TRY(cudaMalloc(&f->d_s2_img, (size_t)bytes));
+    f->s2_img_bytes = bytes;
+  }
+  std::vector<ImgPackDesc> descs;
+  {
+    size_t h = 0;
+    for (const auto& op : p.ops) {
+      if (op.type != DOP_HALF) continue;
+      const HalfLayout& hl = sd.half[op.src];
+      const S2Half& tl = f->s2.half[op.src];
+      for (int l = 0; l <= hl.L; ++l) {
+        const S2Layer& ly = tl.layer[l];
+        ImgPackDesc d;
+        const int n_out = l < hl.L ? hl.hp[l] : 2 * hl.dop;
+        d.src = p.d_blob + op.off + (l == 0 ? hl.off_w[0] : (l < hl.L ? hl.off_w[l] : hl.off_wout));
+        d.s_row = 1; d.s_k = n_out; d.rows = n_out; d.k = l == 0 ? hl.dinp : hl.hp[l - 1];
+        d.dst = f->d_s2_img + net_off[h] + ly.w_off; d.plane = ly.w_plane; d.rpad = ly.w_rpad; d.chunks = ly.n_kst;
+        descs.push_back(d);
+      }
+      ++h;
+    }
+  }
+  for (size_t b0 = 0; b0 < descs.size(); b0 += kImgPackMax) {
+    ImgPackBatch batch;
+    const int nb = (int)std::min<size_t>(kImgPackMax, descs.size() - b0);
+    int max_blocks = 0;
+    for (int i = 0; i < nb; ++i) { batch.d[i] = descs[b0 + i]; max_blocks = std::max(max_blocks, descs[b0 + i].rpad / 32); }
+    img_pack_kernel<<<dim3(max_blocks, nb), kTgGroupThreads, 0, stream>>>(batch);
+    CUDA_TRY(cudaGetLastError());
+  }
+  // offset tables (static per handle: built once)
+  if (!f->d_s2_off[0]) {
+    const int n = (int)f->op_types.size();
+    // forward network index of each (layer, sub-network)
+    std::vector<long long> by_layer(2 * n, -1);
+    {
+      size_t h = 0;
+      for (int i = 0; i < n; ++i)
+        if (f->op_types[i] == BCNF_OP_COUPLING)
+          for (int s2 = 0; s2 < (f->desc.two_way ? 2 : 1); ++s2) by_layer[2 * i + s2] = net_off[h++];
+    }
+    for (int dir = 0; dir < 2; ++dir) {
+      std::vector<long long> offs(f->prog[dir].ops.size(), 0);
+      int oi = 0;
+      for (int sidx = 0; sidx < n; ++sidx) {
+        const int i = dir == 0 ? sidx : n - 1 - sidx;
+        if (f->op_types[i] == BCNF_OP_COUPLING) {
+          offs[oi++] = by_layer[2 * i];
+          if (f->desc.two_way) offs[oi++] = by_layer[2 * i + 1];
+        } else {
+          oi++;
+        }
+      }
+      CUDA_TRY(cudaMalloc(&f->d_s2_off[dir], offs.size() * sizeof(long long)));
+      CUDA_TRY(cudaMemcpyAsync(f->d_s2_off[dir], offs.data(), offs.size() * sizeof(long long), cudaMemcpyHostToDevice, stream));
+      CUDA_TRY(cudaStreamSynchronize(stream));      // (offs is a host temporary; create-time only)
+    }
+  }
+  if (!f->h_s2_dbg) {
+    CUDA_TRY(cudaHostAlloc(&f->h_s2_dbg, 64, cudaHostAllocMapped));
+    memset(f->h_s2_dbg, 0, 64);
+    CUDA_TRY(cudaHostGetDevicePointer(&f->d_s2_dbg, f->h_s2_dbg, 0));
+  }
+  return BCNF_OK;
+}
+
+// Activation scratch of the stream `stream` (one per stream that runs the kernel: two launches of one handle on
+// different streams may overlap).  The first stream's scratch is allocated by set_params; another stream's on its
+// first call, which is therefore not capturable.
+static int s2_scratch_for(bcnf_flow* f, cudaStream_t stream, unsigned char** out) {
+  for (auto& sc : f->s2_scratch)
+    if (sc.stream == stream) { *out = sc.act; return BCNF_OK; }
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  CUDA_TRY(cudaStreamIsCapturing(stream, &cap));
+  if (cap != cudaStreamCaptureStatusNone)
+    return fail(BCNF_E_STATE, "the activation scratch of this stream is not allocated yet; run the flow once on it "
+                              "outside CUDA-graph capture");
+  unsigned char* act = nullptr;
+  CUDA_TRY(cudaMalloc(&act, (size_t)f->s2_ctas * (size_t)f->s2.cta_bytes));
+  f->s2_scratch.push_back({stream, act});
+  *out = act;
+  return BCNF_OK;
+}
+
 extern "C" int bcnf_flow_set_params(bcnf_flow_t* f, const bcnf_op_params_t* ops, void* stream_) {
   if (!f || !ops) return fail(BCNF_E_ARG, "bcnf_flow_set_params: null argument");
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -753,12 +951,12 @@ extern "C" int bcnf_flow_set_params(bcnf_flow_t* f, const bcnf_op_params_t* ops,
   if (f->npass) {
     std::vector<TcPackDesc> tv;
     tv.reserve(f->tc_pack_cap);
-    for (int i = 0; i < n; ++i)
+    for (int i = 0; i < n && f->tc1_ok; ++i)
       if (f->op_types[i] == BCNF_OP_COUPLING) {
         emit_tc_half(*f, 0, ops[i].w_a, f->tc_off_by_layer[2 * i], tv);
         if (f->desc.two_way) emit_tc_half(*f, 1, ops[i].w_b, f->tc_off_by_layer[2 * i + 1], tv);
       }
-    for (size_t k = 0; k < f->proj_nets.size(); ++k) {
+    for (size_t k = 0; k < f->proj_nets.size() && f->tc1_ok; ++k) {
       const ProjNet& pn = f->proj_nets[k];
       const int li = f->proj_net_layer[k];
       const HalfLayout& hl = sd.half[pn.src];
@@ -783,11 +981,13 @@ extern "C" int bcnf_flow_set_params(bcnf_flow_t* f, const bcnf_op_params_t* ops,
       }
     }
     if ((int)tv.size() > f->tc_pack_cap) return fail(BCNF_E_STATE, "internal: tile pack table overflow");
-    CUDA_TRY(cudaStreamSynchronize(stream));
-    memcpy(f->h_tc_pack, tv.data(), tv.size() * sizeof(TcPackDesc));
-    CUDA_TRY(cudaMemcpyAsync(f->d_tc_pack, f->h_tc_pack, tv.size() * sizeof(TcPackDesc), cudaMemcpyHostToDevice, stream));
-    tc_pack_kernel<<<(unsigned)tv.size(), 256, 0, stream>>>(f->d_tc_pack);
-    CUDA_TRY(cudaGetLastError());
+    if (!tv.empty()) {
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      memcpy(f->h_tc_pack, tv.data(), tv.size() * sizeof(TcPackDesc));
+      CUDA_TRY(cudaMemcpyAsync(f->d_tc_pack, f->h_tc_pack, tv.size() * sizeof(TcPackDesc), cudaMemcpyHostToDevice, stream));
+      tc_pack_kernel<<<(unsigned)tv.size(), 256, 0, stream>>>(f->d_tc_pack);
+      CUDA_TRY(cudaGetLastError());
+    }
     // image of Wproj for the CTA-pair projection GEMM: rows = projection column j, k = condition feature
     const int chunks = (sd.C + 63) / 64;
     f->wproj_rpad = (sd.PW + 255) / 256 * 256;
@@ -800,6 +1000,11 @@ extern "C" int bcnf_flow_set_params(bcnf_flow_t* f, const bcnf_op_params_t* ops,
     img_pack_kernel<<<dim3(f->wproj_rpad / 32, 1), kTgGroupThreads, 0, stream>>>(batch);
     CUDA_TRY(cudaGetLastError());
     if (int rc = build_layered_images(f, stream)) return rc;
+    if (int rc = build_s2_images(f, stream)) return rc;
+    if (f->s2_ok && f->s2_scratch.empty()) {
+      unsigned char* act = nullptr;
+      if (int rc = s2_scratch_for(f, stream, &act)) return rc;
+    }
   }
   f->params_set = true;
   return BCNF_OK;
@@ -957,7 +1162,7 @@ extern "C" int bcnf_cond_project(bcnf_flow_t* f, const float* h, int64_t n_inst,
     }
     return BCNF_OK;
   }
-  if (f->npass && !getenv("BCNF_PROJ_FMA")) {
+  if (f->npass && f->tc1_ok && !getenv("BCNF_PROJ_FMA")) {
     // previous tensor-core projection kernel (proj_tc.cuh), kept for A/B timing: BCNF_PROJ_V1=1
     auto launch = [&](auto kern) -> int {
       const size_t smem = (size_t)f->pd.smem_bytes;
@@ -1060,6 +1265,38 @@ static int launch_tc(bcnf_flow* f, const FlowArgs& a, int dir, cudaStream_t stre
   const unsigned char* blob = f->d_tc_blob;
   const long long* offs = f->d_tc_off[dir];
   CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, a, sd, td, blob, offs));
+  return BCNF_OK;
+}
+
+
+template <int NPASS>
+static int launch_tc2(bcnf_flow* f, const FlowArgs& a, int dir, cudaStream_t stream) {
+  const size_t smem = (size_t)f->s2.smem_bytes;
+  auto kern = flow_tc2_kernel<NPASS>;
+  static size_t configured[64] = {};
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (dev >= 64 || configured[dev] < smem) {
+    if (int rc = opt_in_smem(kern, smem)) return rc;
+    if (dev < 64) configured[dev] = smem;
+  }
+  unsigned char* act = nullptr;
+  if (int rc = s2_scratch_for(f, stream, &act)) return rc;
+  const long long tiles = (a.n_rows + 2 * kS2Rows - 1) / (2 * kS2Rows);
+  const int pairs = (int)std::min<long long>(tiles, f->s2_ctas / 2);
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(kS2Threads);
+  cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  const StackDims sd = f->sd;
+  const S2Dims d2 = f->s2;
+  const unsigned char* img = f->d_s2_img;
+  const long long* offs = f->d_s2_off[dir];
+  unsigned int* dbg = f->d_s2_dbg;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, a, sd, d2, img, offs, act, dbg));
   return BCNF_OK;
 }
 
@@ -1206,6 +1443,8 @@ static int run_flow(bcnf_flow_t* f, int dir, const float* in, const float* P, co
     // layer by layer on the CTA-pair GEMM (BCNF_FLOW_LAYERED=1), or the fused kernel
     const char* lay = getenv("BCNF_FLOW_LAYERED");
     if (f->layered_ok && lay && atoi(lay) == 1) return run_layered(f, dir, in, P, row2inst, inst_period, n_rows, out, logdet, stream);
+    if (f->s2_use) return f->npass == 3 ? launch_tc2<3>(f, a, dir, stream) : launch_tc2<1>(f, a, dir, stream);
+    if (!f->tc1_ok) return fail(BCNF_E_STATE, "internal: no fused tensor-core kernel planned for this stack");
     return f->npass == 3 ? launch_tc<3>(f, a, dir, stream) : launch_tc<1>(f, a, dir, stream);
   }
   if (f->kernel == BCNF_KERNEL_ROWTHREAD) {

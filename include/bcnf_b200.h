@@ -106,6 +106,10 @@ const char* bcnf_last_error(void);
 int bcnf_flow_create(const bcnf_flow_desc_t* desc, const int32_t* op_types, bcnf_flow_t** out);
 int bcnf_flow_destroy(bcnf_flow_t* flow);
 int bcnf_flow_info(const bcnf_flow_t* flow, bcnf_flow_info_t* info);
+/* Diagnostics of the fused tensor-core kernel: every wait inside it carries a watchdog that records
+ * {wait code, aux, block, thread} and traps (the launch fails with a CUDA error) instead of hanging the
+ * device if a hand-off never arrives.  All zero in a healthy run.  No reference counterpart. */
+int bcnf_flow_debug_words(const bcnf_flow_t* flow, uint32_t* out4);
 
 /* (Re)pack the parameters from the caller's tensors (device pointers).  Call after
  * load_state_dict / every optimiser step.  Replaces nothing in the reference: it is the
