@@ -157,6 +157,7 @@ struct bcnf_flow {
   std::vector<S2Scratch> s2_scratch;
   unsigned int* d_s2_dbg = nullptr;            // device alias of h_s2_dbg (mapped pinned memory: readable after a trap)
   unsigned int* h_s2_dbg = nullptr;
+  S2BiasCol* d_s2_bias = nullptr;
   int s2_ctas = 0;
 };
 
@@ -281,6 +282,7 @@ extern "C" int bcnf_flow_destroy(bcnf_flow_t* f) {
   for (int d = 0; d < 2; ++d) if (f->d_s2_off[d]) cudaFree(f->d_s2_off[d]);
   for (auto& sc : f->s2_scratch) if (sc.act) cudaFree(sc.act);
   if (f->h_s2_dbg) cudaFreeHost(f->h_s2_dbg);
+  if (f->d_s2_bias) cudaFree(f->d_s2_bias);
   delete f;
   return BCNF_OK;
 }
@@ -373,12 +375,13 @@ static const char* tc_plan(bcnf_flow& f, int npass) {
 
 // ---- second-generation fused kernel (flow_tc2.cuh): layer / chunk structure, shared-memory carve-up ---------------
 static void s2_set_chunks(S2Layer& ly, int np) {
+  // Full 256-column chunks, then the remainder (528 -> 256, 256, 16).  The LAST chunk of a layer is the one whose
+  // epilogue the next layer's MMAs have to wait for: keeping it small keeps that wait short, and an M = 256, N = 16
+  // MMA costs the same shared-memory cycles per column as the balanced split (192, 192, 144) would.
   const int n = (np + 255) / 256;
   for (int i = 0; i < kS2MaxChunks; ++i) ly.chunk_n[i] = 0;
   ly.n_chunks = n;
-  if (n == 1) { ly.chunk_n[0] = np; return; }
-  const int base = round_up((np + n - 1) / n, 64);      // all but the last chunk cover whole 64-column image chunks
-  for (int i = 0, left = np; i < n; ++i) { ly.chunk_n[i] = std::min(base, left); left -= ly.chunk_n[i]; }
+  for (int i = 0, left = np; i < n; ++i) { ly.chunk_n[i] = std::min(256, left); left -= ly.chunk_n[i]; }
 }
 
 // Returns 0 and fills f.s2 if the stack fits the kernel, else a reason string.
@@ -386,14 +389,24 @@ static const char* s2_plan(bcnf_flow& f, int npass) {
   const StackDims& sd = f.sd;
   S2Dims& d = f.s2;
   memset(&d, 0, sizeof(d));
-  if (sd.D > kS2YPitch - 1) return "size > 28";
+  if (sd.D > kS2YPitch - 1) return "size > 24";
+  {
+    // ActNorm / mixing parameters between two conditioner networks are staged in shared memory: longest run
+    long long run = 0, best = 0;
+    for (const auto& op : f.prog[0].ops) {
+      if (op.type == DOP_HALF) { run = 0; continue; }
+      run += op.type == DOP_MIX ? (long long)sd.D * sd.DP : 2 * sd.DP + 4;
+      best = std::max(best, run);
+    }
+    if (best * 4 > kS2GparBytes) return "ActNorm / mixing parameters between two couplings exceed the staging area";
+  }
   const int PL = npass == 3 ? 2 : 1;
   int a_kchunks = 1;
   for (int s = 0; s < 2; ++s) {
     const HalfLayout& hl = sd.half[s];
     S2Half& tl = d.half[s];
     if (hl.din > 16) return "own-half width > 16";
-    if (2 * hl.dop > 32) return "last Linear wider than 32 columns";
+    if (2 * hl.dop > kS2TsPitch - 1) return "last Linear wider than 24 columns";
     if (hl.L + 1 > kTcMaxLayers) return "too many hidden layers";
     tl.L = hl.L;
     tl.n_last = round_up(2 * hl.dop, 16);
@@ -401,7 +414,13 @@ static const char* s2_plan(bcnf_flow& f, int npass) {
     for (int l = 0; l <= hl.L; ++l) {
       S2Layer& ly = tl.layer[l];
       if (l < hl.L && (hl.h[l] < 48 || hl.hp[l] > 1024)) return "hidden width outside [48, 1024]";
-      const int k_real = l == 0 ? hl.din : hl.h[l - 1];
+      // bias folded into the GEMM where the previous layer's width leaves a free padding column (526 -> 528): the
+      // input image carries a constant 1 in column h and the weight image the bias there (no bias reads in the epilogue)
+      const bool fold = l >= 1 && hl.h[l - 1] % 16 != 0 && !getenv("BCNF_TC2_NOFOLD");
+      ly.bias_k = fold ? hl.h[l - 1] : -1;
+      ly.one_col = -1;
+      if (fold) tl.layer[l - 1].one_col = hl.h[l - 1];
+      const int k_real = l == 0 ? hl.din : hl.h[l - 1] + (fold ? 1 : 0);
       const int np = l == hl.L ? tl.n_last : hl.hp[l];
       s2_set_chunks(ly, np);
       if (ly.n_chunks > kS2MaxChunks) return "too many N chunks";
@@ -843,6 +862,33 @@ static int build_s2_images(bcnf_flow* f, cudaStream_t stream) {
     for (int i = 0; i < nb; ++i) { batch.d[i] = descs[b0 + i]; max_blocks = std::max(max_blocks, descs[b0 + i].rpad / 32); }
     img_pack_kernel<<<dim3(max_blocks, nb), kTgGroupThreads, 0, stream>>>(batch);
     CUDA_TRY(cudaGetLastError());
+  }
+  // folded biases: one weight-image column per (network, layer)
+  {
+    std::vector<S2BiasCol> cols;
+    size_t h = 0;
+    for (const auto& op : p.ops) {
+      if (op.type != DOP_HALF) continue;
+      const HalfLayout& hl = sd.half[op.src];
+      const S2Half& tl = f->s2.half[op.src];
+      for (int l = 1; l <= hl.L; ++l) {
+        const S2Layer& ly = tl.layer[l];
+        if (ly.bias_k < 0) continue;
+        S2BiasCol c;
+        c.bias = p.d_blob + op.off + (l < hl.L ? hl.off_b[l] : hl.off_bout);
+        c.img = f->d_s2_img + net_off[h] + ly.w_off; c.plane = ly.w_plane; c.rpad = ly.w_rpad;
+        c.n = l < hl.L ? hl.hp[l] : 2 * hl.dop; c.k = ly.bias_k; c.pad = 0;
+        cols.push_back(c);
+      }
+      ++h;
+    }
+    if (!cols.empty()) {
+      if (!f->d_s2_bias) CUDA_TRY(cudaMalloc(&f->d_s2_bias, cols.size() * sizeof(S2BiasCol)));
+      CUDA_TRY(cudaMemcpyAsync(f->d_s2_bias, cols.data(), cols.size() * sizeof(S2BiasCol), cudaMemcpyHostToDevice, stream));
+      CUDA_TRY(cudaStreamSynchronize(stream));       // (cols is a host temporary)
+      s2_bias_col_kernel<<<(unsigned)cols.size(), 256, 0, stream>>>(f->d_s2_bias);
+      CUDA_TRY(cudaGetLastError());
+    }
   }
   // offset tables (static per handle: built once)
   if (!f->d_s2_off[0]) {
@@ -1292,7 +1338,8 @@ static int launch_tc2(bcnf_flow* f, const FlowArgs& a, int dir, cudaStream_t str
   cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(kS2Threads);
   cfg.dynamicSmemBytes = smem; cfg.stream = stream;
   const StackDims sd = f->sd;
-  const S2Dims d2 = f->s2;
+  S2Dims d2 = f->s2;
+  if (const char* dbgenv = getenv("BCNF_TC2_DEBUG")) d2.debug = atoi(dbgenv);     // timing experiments (wrong results)
   const unsigned char* img = f->d_s2_img;
   const long long* offs = f->d_s2_off[dir];
   unsigned int* dbg = f->d_s2_dbg;
@@ -1417,9 +1464,32 @@ static int run_flow(bcnf_flow_t* f, int dir, const float* in, const float* P, co
   a.blob = p.d_blob; a.ops = p.d_ops; a.n_ops = (int)p.ops.size();
   a.chunks = p.d_chunks; a.n_chunks = (int)p.chunks.size();
   a.trace = nullptr;
+  a.blob_floats = p.blob_floats;
+  if (const char* tp = f->kernel == BCNF_KERNEL_TCGEN05 && f->s2_use ? getenv("BCNF_TC2_TRACE") : nullptr) {
+    // debug aid: dump the clock64 stamps of block 0's issuer / epilogue / producer to the named file (synchronises!)
+    const size_t n = 4 * 8192;
+    long long* d_tr = nullptr;
+    CUDA_TRY(cudaMalloc(&d_tr, n * sizeof(long long)));
+    CUDA_TRY(cudaMemsetAsync(d_tr, 0, n * sizeof(long long), stream));
+    a.trace = d_tr;
+    int rc = f->npass == 3 ? launch_tc2<3>(f, a, dir, stream) : launch_tc2<1>(f, a, dir, stream);
+    std::vector<long long> h(n);
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    CUDA_TRY(cudaMemcpy(h.data(), d_tr, n * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(d_tr);
+    if (FILE* fp = fopen(tp, "w")) {
+      for (int role = 0; role < 4; ++role)
+        for (int i = 0; i < 2048; ++i) {
+          const long long* e = &h[role * 8192 + i * 4];
+          if (e[0] | e[1] | e[2] | e[3]) fprintf(fp, "%d %d %lld %lld %lld %lld\n", role, i, e[0], e[1], e[2], e[3]);
+        }
+      fclose(fp);
+    }
+    return rc;
+  }
   if (const char* tp = getenv("BCNF_TC_TRACE")) {
     // debug aid: dump clock64 stamps of the first tile's pipeline to the named file (synchronises!)
-    if (f->kernel == BCNF_KERNEL_TCGEN05) {
+    if (f->kernel == BCNF_KERNEL_TCGEN05 && !f->s2_use) {
       long long* d_tr = nullptr;
       CUDA_TRY(cudaMalloc(&d_tr, 64 * 8 * sizeof(long long)));
       CUDA_TRY(cudaMemsetAsync(d_tr, 0, 64 * 8 * sizeof(long long), stream));

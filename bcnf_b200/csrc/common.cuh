@@ -161,6 +161,7 @@ struct FlowArgs {
   const Chunk* chunks;
   int n_chunks;
   long long* trace;       // debug: clock64 stamps of the tensor-core pipeline (null in normal runs)
+  long long blob_floats;  // size of `blob` (floats)
 };
 
 __device__ __forceinline__ long long row_instance(const FlowArgs& a, long long r) {
