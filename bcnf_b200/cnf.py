@@ -516,11 +516,12 @@ class CondRealNVP_v2(ConditionalInvertibleLayer):
     def features(self, *conditions: torch.Tensor) -> torch.Tensor:
         """Condition features h = feature_network_stack(*conditions) on the model's device.
 
-        On tensor-core handles a FullyConnected feature network follows the stack's arithmetic mode in eval mode
-        without autograd (bcnf_b200/feature_tc.py); everything else is the plain PyTorch module.
+        On tensor-core handles the FullyConnected / LSTM feature networks follow the stack's arithmetic mode whenever the
+        model is in eval mode (bcnf_b200/feature_tc.py; no autograd history -- the eval-mode stack has none either);
+        in training mode, and for the Transformer, the plain PyTorch module runs.
         """
         dev = _as_device(self.device)
-        if dev.type == "cuda" and not self.training and not torch.is_grad_enabled():
+        if dev.type == "cuda" and not self.training:
             flow = self._flow()
             passes = {"bf16x3": 3, "bf16": 1}.get(flow.precision, 0) if flow.kernel == "tcgen05" else 0
             for fn in self.feature_network_stack.feature_networks:

@@ -15,12 +15,10 @@
 #include "flow_rowthread.cuh"
 #include "flow_tc.cuh"
 #include "flow_tiled.cuh"
-#include "proj_tc.cuh"
 #include "train_ops.cuh"
 #include "train_tc.cuh"
 #include "train_glue.cuh"
 #include "gemm_img2.cuh"
-#include "flow_layered.cuh"
 #include "flow_tc2.cuh"
 
 using namespace bcnf;
@@ -37,6 +35,24 @@ static int fail(int code, const char* fmt, ...) {
   va_end(ap);
   return code;
 }
+// Entry points run on the handle's (or the caller-named) device and restore the caller's current device on the way out:
+// torch keeps its own notion of the current device, and bcnf_flow_destroy is reached from Python's garbage collector.
+struct DeviceGuard {
+  int prev = -1;
+  bool changed = false;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int dev) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) { err = cudaSetDevice(dev); changed = err == cudaSuccess; }
+  }
+  ~DeviceGuard() { if (changed) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define DEVICE_GUARD(dev)                                                                              \
+  DeviceGuard guard__(dev);                                                                            \
+  if (guard__.err != cudaSuccess) return fail((int)guard__.err, "cudaSetDevice(%d): %s", (int)(dev), cudaGetErrorString(guard__.err))
+
 #define CUDA_TRY(expr)                                                                      \
   do {                                                                                      \
     cudaError_t e__ = (expr);                                                               \
@@ -119,12 +135,6 @@ struct bcnf_flow {
   TcPackDesc* d_tc_pack = nullptr;
   TcPackDesc* h_tc_pack = nullptr;
   int tc_pack_cap = 0;
-  // tensor-core condition projection
-  ProjTcDims pd;
-  unsigned char* d_proj_blob = nullptr;
-  ProjNet* d_proj_nets = nullptr;
-  std::vector<ProjNet> proj_nets;
-  std::vector<int> proj_net_layer;   // index in op_types of each conditioner network's coupling layer
   // CTA-pair GEMM on operand images (gemm_img2.cuh): image of Wproj (rows = projection column, k = condition
   // feature), rebuilt by set_params, and a scratch image of the h rows of one slice of instances
   unsigned char* d_wproj_img = nullptr;
@@ -132,20 +142,12 @@ struct bcnf_flow {
   int wproj_rpad = 0;
   unsigned char* d_h_img = nullptr;
   long long h_img_bytes = 0;
-  // layer-by-layer execution (flow_layered.cuh): operand images of the hidden and last Linear of every conditioner
-  // network (forward layer order), and the scratch of one batch of rows
-  struct LwImg { long long off, plane; int rpad; };
-  bool layered_ok = false;
-  unsigned char* d_lw_img = nullptr;
-  long long lw_img_bytes = 0;
-  std::vector<std::vector<LwImg>> lw_img;     // [network][layer 1..L] (index 0 unused)
-  float* d_ly = nullptr;                      // (kLayeredBatch, DP)
-  float* d_lld = nullptr;                     // (kLayeredBatch)
-  float* d_lo = nullptr;                      // (kLayeredBatch, 32)
-  unsigned char* d_lact[2] = {nullptr, nullptr};
-  long long lact_plane = 0;
   // second-generation fused kernel (flow_tc2.cuh): weight images of every Linear of every conditioner network, the
   // per-direction table of their offsets, and one activation scratch per stream that has run the kernel
+  // switches read from the environment ONCE, at create (tests / A-B timing / debugging; never on the launch path)
+  bool env_proj_fma = false;                  // BCNF_PROJ_FMA=1: fp32 FMA projection kernel on a tensor-core handle
+  int env_tc2_debug = 0;                      // BCNF_TC2_DEBUG: timing experiments of flow_tc2 (wrong results)
+  std::string env_tc2_trace, env_tc_trace;    // BCNF_TC2_TRACE / BCNF_TC_TRACE: file that receives a pipeline trace
   bool tc1_ok = false;                        // the first-generation kernel's plan (f.td) is valid
   bool s2_ok = false;
   bool s2_use = false;                        // dispatch forward / inverse to it (decided once, at create)
@@ -160,8 +162,6 @@ struct bcnf_flow {
   S2BiasCol* d_s2_bias = nullptr;
   int s2_ctas = 0;
 };
-
-static const int kLayeredBatch = 74 * 256;    // rows per batch: 74 row tiles x 3 column tiles = 3 full rounds of 74 CTA pairs
 
 static const int kRowThreadChunkCap = 20 * 1024;  // bytes per streamed parameter chunk
 
@@ -258,7 +258,7 @@ extern "C" const char* bcnf_last_error(void) { return g_err; }
 
 extern "C" int bcnf_flow_destroy(bcnf_flow_t* f) {
   if (!f) return BCNF_OK;
-  cudaSetDevice(f->desc.device);
+  DeviceGuard guard(f->desc.device);
   free_program(f->prog[0]);
   free_program(f->prog[1]);
   if (f->d_wproj) cudaFree(f->d_wproj);
@@ -269,15 +269,8 @@ extern "C" int bcnf_flow_destroy(bcnf_flow_t* f) {
   for (int d = 0; d < 2; ++d) if (f->d_tc_off[d]) cudaFree(f->d_tc_off[d]);
   if (f->d_tc_pack) cudaFree(f->d_tc_pack);
   if (f->h_tc_pack) cudaFreeHost(f->h_tc_pack);
-  if (f->d_proj_blob) cudaFree(f->d_proj_blob);
   if (f->d_wproj_img) cudaFree(f->d_wproj_img);
-  if (f->d_lw_img) cudaFree(f->d_lw_img);
-  if (f->d_ly) cudaFree(f->d_ly);
-  if (f->d_lld) cudaFree(f->d_lld);
-  if (f->d_lo) cudaFree(f->d_lo);
-  for (int b = 0; b < 2; ++b) if (f->d_lact[b]) cudaFree(f->d_lact[b]);
   if (f->d_h_img) cudaFree(f->d_h_img);
-  if (f->d_proj_nets) cudaFree(f->d_proj_nets);
   if (f->d_s2_img) cudaFree(f->d_s2_img);
   for (int d = 0; d < 2; ++d) if (f->d_s2_off[d]) cudaFree(f->d_s2_off[d]);
   for (auto& sc : f->s2_scratch) if (sc.act) cudaFree(sc.act);
@@ -321,13 +314,7 @@ static const char* tc_plan(bcnf_flow& f, int npass) {
   TcDims& td = f.td;
   memset(&td, 0, sizeof(td));
   int a_chunks = 1, max_half_rows = 8, max_doh = 8;
-  // Weight tile width: 64 columns (SWIZZLE_128B) by default.  32-column tiles (SWIZZLE_64B, BCNF_TC_KW=32) halve the
-  // stage size so that every issuing warp is double-buffered in the 3-pass mode; measured on B200 (r01) they are
-  // not faster (2.65 vs 2.76 M samples/s on FC_large): the MMA phase is bound by shared-memory bandwidth (operand
-  // reads of the MMAs + TMA stage writes ~ 2.0 MB per layer per SM at ~64 B/clk), not by staging depth.
-  const char* kw_env = getenv("BCNF_TC_KW");
-  td.kw = kw_env ? atoi(kw_env) : 64;
-  if (td.kw != 32 && td.kw != 64) td.kw = 64;
+  td.kw = 64;                 // weight tiles are 64 K columns wide (SWIZZLE_128B)
   for (int s = 0; s < 2; ++s) {
     const HalfLayout& hl = sd.half[s];
     if (hl.din > 64) return "own-half width > 64";
@@ -455,6 +442,17 @@ static int opt_in_smem(K kernel, size_t bytes) {
   CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   return 0;
 }
+// cudaFuncSetAttribute is per device: remember what each device has been opted in to (one table per kernel instance)
+template <typename K>
+static int opt_in_smem_once(K kernel, size_t bytes, size_t (&configured)[64]) {
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || configured[dev] < bytes) {
+    if (int rc = opt_in_smem(kernel, bytes)) return rc;
+    if (dev >= 0 && dev < 64) configured[dev] = bytes;
+  }
+  return 0;
+}
 
 extern "C" int bcnf_flow_create(const bcnf_flow_desc_t* desc, const int32_t* op_types, bcnf_flow_t** out) {
   if (!desc || !op_types || !out) return fail(BCNF_E_ARG, "bcnf_flow_create: null argument");
@@ -476,7 +474,7 @@ extern "C" int bcnf_flow_create(const bcnf_flow_desc_t* desc, const int32_t* op_
     if (op_types[i] < 0 || op_types[i] > 2)
       return fail(BCNF_E_ARG, "layer %d has unknown type %d", i, op_types[i]);   // cnf.py:485
 
-  CUDA_TRY(cudaSetDevice(desc->device));
+  DEVICE_GUARD(desc->device);
   bcnf_flow* f = new (std::nothrow) bcnf_flow();
   if (!f) return fail(BCNF_E_NOMEM, "out of host memory");
   f->desc = *desc;
@@ -540,6 +538,10 @@ extern "C" int bcnf_flow_create(const bcnf_flow_desc_t* desc, const int32_t* op_
     f->rows_per_cta = kTcRows;
     const char* gen = getenv("BCNF_FLOW_TC");
     f->s2_use = f->s2_ok && !(gen && atoi(gen) == 1 && f->tc1_ok);
+    f->env_proj_fma = getenv("BCNF_PROJ_FMA") != nullptr;
+    if (const char* e = getenv("BCNF_TC2_DEBUG")) f->env_tc2_debug = atoi(e);
+    if (const char* e = getenv("BCNF_TC2_TRACE")) f->env_tc2_trace = e;
+    if (const char* e = getenv("BCNF_TC_TRACE")) f->env_tc_trace = e;
     f->s2_ctas = 2 * (f->num_sms / 2);
     if (f->s2_use) f->rows_per_cta = kS2Rows;
   } else if (rowthread_ok) {
@@ -607,8 +609,6 @@ extern "C" int bcnf_flow_create(const bcnf_flow_desc_t* desc, const int32_t* op_
           for (int l = 0; l <= f->td.half[s].L; ++l) n_tiles += f->td.half[s].layer[l].n_chunks * f->td.half[s].layer[l].kc;
         }
     f->tc_blob_bytes = off;
-    // flow tiles + projection tiles (K = C in 64-wide chunks, <= 4 N chunks per conditioner network)
-    n_tiles += f->n_half * 4 * ((sd.C + 63) / 64);
     f->tc_pack_cap = n_tiles;
     bool ok = cudaMalloc(&f->d_tc_blob, off) == cudaSuccess &&
               cudaMalloc(&f->d_tc_pack, (size_t)n_tiles * sizeof(TcPackDesc)) == cudaSuccess &&
@@ -635,57 +635,6 @@ extern "C" int bcnf_flow_create(const bcnf_flow_desc_t* desc, const int32_t* op_
       return fail(BCNF_E_NOMEM, "device allocation of %lld bytes (bf16 weight tiles) failed", off);
     }
     bytes += off;
-    // ---- tensor-core projection: tile streams of the h-columns of every first Linear ----
-    ProjTcDims& pd = f->pd;
-    memset(&pd, 0, sizeof(pd));
-    pd.C = sd.C; pd.PW = sd.PW; pd.two_way = desc->two_way ? 1 : 0;
-    const int kc_total = (sd.C + 63) / 64;
-    for (int s = 0; s < 2; ++s) {
-      pd.layer[s] = f->td.half[s].layer[0];      // N chunking of the first Linear; K = C in 64-wide tiles
-      pd.layer[s].kc = kc_total;
-      long long b = 0;
-      for (int nc = 0; nc < pd.layer[s].n_chunks; ++nc) b += (long long)4 * (pd.layer[s].chunk_n[nc] / 2) * 128;
-      pd.stream_bytes[s] = b * kc_total;
-    }
-    {
-      int mhr = 8;
-      for (int s = 0; s < 2; ++s)
-        for (int nc = 0; nc < pd.layer[s].n_chunks; ++nc) mhr = std::max(mhr, pd.layer[s].chunk_n[nc] / 2);
-      pd.stage_bytes = mhr * 128 * (f->npass == 3 ? 2 : 1);
-    }
-    pd.a_stages = 3;
-    const int a_bytes = pd.a_stages * (f->npass == 3 ? 2 : 1) * kTcATile;
-    pd.off_b = a_bytes;
-    pd.b_stages = std::min(8, (f->max_smem_optin - a_bytes - 2048) / pd.stage_bytes);
-    pd.off_misc = pd.off_b + pd.b_stages * pd.stage_bytes;
-    pd.smem_bytes = pd.off_misc + 2048;
-    long long poff = 0;
-    f->proj_nets.clear(); f->proj_net_layer.clear();
-    {
-      const Program& p0 = f->prog[0];
-      int oi = 0;
-      for (int i = 0; i < n; ++i) {
-        if (f->op_types[i] == BCNF_OP_COUPLING) {
-          for (int s = 0; s < (desc->two_way ? 2 : 1); ++s) {
-            ProjNet pn; pn.stream_off = poff; pn.proj_off = p0.ops[oi + s].proj_off; pn.src = s;
-            f->proj_nets.push_back(pn); f->proj_net_layer.push_back(i);
-            poff += pd.stream_bytes[s];
-          }
-          oi += desc->two_way ? 2 : 1;
-        } else {
-          oi += 1;
-        }
-      }
-    }
-    if (pd.b_stages < 2 || f->proj_nets.empty() ||
-        cudaMalloc(&f->d_proj_blob, poff) != cudaSuccess ||
-        cudaMalloc(&f->d_proj_nets, f->proj_nets.size() * sizeof(ProjNet)) != cudaSuccess) {
-      cudaGetLastError();
-      bcnf_flow_destroy(f);
-      return fail(BCNF_E_NOMEM, "device allocation of %lld bytes (projection weight tiles) failed", poff);
-    }
-    cudaMemcpy(f->d_proj_nets, f->proj_nets.data(), f->proj_nets.size() * sizeof(ProjNet), cudaMemcpyHostToDevice);
-    bytes += poff;
   }
   f->packed_bytes = bytes;
   cudaError_t e = cudaGetLastError();
@@ -767,57 +716,6 @@ static void emit_tc_half(const bcnf_flow& f, int s, const float* const* w, long 
     }
   }
 }
-
-// Operand images of the hidden and last Linear of every conditioner network for the layer-by-layer path, made from
-// the forward program's fp32 blob (input-major W_l [HP(l-1)][HP(l)]; last Linear [HP(L-1)][2*DOP], t | s halves).
-static int build_layered_images(bcnf_flow* f, cudaStream_t stream) {
-  const StackDims& sd = f->sd;
-  const HalfLayout& hl = sd.half[0];
-  f->layered_ok = f->npass != 0 && !f->desc.two_way && hl.din <= kLgDin && sd.D <= 24 && 2 * hl.dop <= 32;
-  if (!f->layered_ok) return BCNF_OK;
-  const Program& p = f->prog[0];
-  std::vector<const DevOp*> halves;
-  for (const auto& op : p.ops) if (op.type == DOP_HALF) halves.push_back(&op);
-  // layout
-  f->lw_img.assign(halves.size(), std::vector<bcnf_flow::LwImg>(hl.L + 1));
-  long long bytes = 0;
-  for (size_t h = 0; h < halves.size(); ++h)
-    for (int l = 1; l <= hl.L; ++l) {
-      const int rows = l < hl.L ? hl.hp[l] : 2 * hl.dop, k = hl.hp[l - 1];
-      bcnf_flow::LwImg& im = f->lw_img[h][l];
-      im.rpad = (rows + 255) / 256 * 256;
-      im.plane = (long long)((k + 63) / 64) * im.rpad * 128;
-      im.off = bytes;
-      bytes += 2 * im.plane;
-    }
-  if (bytes > f->lw_img_bytes) {
-    if (f->d_lw_img) CUDA_TRY(cudaFree(f->d_lw_img));
-    f->d_lw_img = nullptr; f->lw_img_bytes = 0;
-    CUDA_TRY(cudaMalloc(&f->d_lw_img, (size_t)bytes));
-    f->lw_img_bytes = bytes;
-  }
-  std::vector<ImgPackDesc> descs;
-  for (size_t h = 0; h < halves.size(); ++h)
-    for (int l = 1; l <= hl.L; ++l) {
-      const bcnf_flow::LwImg& im = f->lw_img[h][l];
-      ImgPackDesc d;
-      const int n_out = l < hl.L ? hl.hp[l] : 2 * hl.dop;
-      d.src = p.d_blob + halves[h]->off + (l < hl.L ? hl.off_w[l] : hl.off_wout);
-      d.s_row = 1; d.s_k = n_out; d.rows = n_out; d.k = hl.hp[l - 1];
-      d.dst = f->d_lw_img + im.off; d.plane = im.plane; d.rpad = im.rpad; d.chunks = (hl.hp[l - 1] + 63) / 64;
-      descs.push_back(d);
-    }
-  for (size_t b0 = 0; b0 < descs.size(); b0 += kImgPackMax) {
-    ImgPackBatch batch;
-    const int nb = (int)std::min<size_t>(kImgPackMax, descs.size() - b0);
-    int max_blocks = 0;
-    for (int i = 0; i < nb; ++i) { batch.d[i] = descs[b0 + i]; max_blocks = std::max(max_blocks, descs[b0 + i].rpad / 32); }
-    img_pack_kernel<<<dim3(max_blocks, nb), kTgGroupThreads, 0, stream>>>(batch);
-    CUDA_TRY(cudaGetLastError());
-  }
-  return BCNF_OK;
-}
-
 
 // Weight images of every Linear of every conditioner network for flow_tc2.cuh, made from the forward program's fp32
 // blob (input-major matrices: W1a [DINP][HP0], W_l [HP(l-1)][HP(l)], last Linear [HP(L-1)][2*DOP] with t | s halves),
@@ -947,7 +845,7 @@ static int s2_scratch_for(bcnf_flow* f, cudaStream_t stream, unsigned char** out
 extern "C" int bcnf_flow_set_params(bcnf_flow_t* f, const bcnf_op_params_t* ops, void* stream_) {
   if (!f || !ops) return fail(BCNF_E_ARG, "bcnf_flow_set_params: null argument");
   cudaStream_t stream = (cudaStream_t)stream_;
-  CUDA_TRY(cudaSetDevice(f->desc.device));
+  DEVICE_GUARD(f->desc.device);
   const int n = (int)f->op_types.size();
   std::vector<PackDesc> v;
   v.reserve(f->pack_cap);
@@ -1002,30 +900,6 @@ extern "C" int bcnf_flow_set_params(bcnf_flow_t* f, const bcnf_op_params_t* ops,
         emit_tc_half(*f, 0, ops[i].w_a, f->tc_off_by_layer[2 * i], tv);
         if (f->desc.two_way) emit_tc_half(*f, 1, ops[i].w_b, f->tc_off_by_layer[2 * i + 1], tv);
       }
-    for (size_t k = 0; k < f->proj_nets.size() && f->tc1_ok; ++k) {
-      const ProjNet& pn = f->proj_nets[k];
-      const int li = f->proj_net_layer[k];
-      const HalfLayout& hl = sd.half[pn.src];
-      const TcLayer& ly = f->pd.layer[pn.src];
-      const float* const* wsrc = pn.src == 0 ? ops[li].w_a : ops[li].w_b;
-      TcPackDesc d{};
-      d.w = wsrc[0];
-      d.pitch = hl.din + sd.C;
-      d.col0 = hl.din;                 // the feature columns of cat([y_half, h]) (cnf.py:101)
-      d.k_valid = sd.C;
-      d.n_valid = hl.h[0];
-      d.out_mode = 0; d.doh = 0;
-      unsigned char* dst = f->d_proj_blob + pn.stream_off;
-      for (int kc = 0; kc < ly.kc; ++kc) {
-        int coff = 0;
-        for (int nc = 0; nc < ly.n_chunks; ++nc) {
-          d.dst = dst; d.chunk_off = coff; d.chunk_n = ly.chunk_n[nc]; d.kc = kc; d.kw = 64;
-          tv.push_back(d);
-          dst += (size_t)4 * (ly.chunk_n[nc] / 2) * 128;
-          coff += ly.chunk_n[nc];
-        }
-      }
-    }
     if ((int)tv.size() > f->tc_pack_cap) return fail(BCNF_E_STATE, "internal: tile pack table overflow");
     if (!tv.empty()) {
       CUDA_TRY(cudaStreamSynchronize(stream));
@@ -1039,13 +913,16 @@ extern "C" int bcnf_flow_set_params(bcnf_flow_t* f, const bcnf_op_params_t* ops,
     f->wproj_rpad = (sd.PW + 255) / 256 * 256;
     f->wproj_plane = (long long)chunks * f->wproj_rpad * 128;
     if (!f->d_wproj_img) CUDA_TRY(cudaMalloc(&f->d_wproj_img, (size_t)(2 * f->wproj_plane)));
+    if (!f->d_h_img) {     // scratch image of one slice of instances' features (bcnf_cond_project never allocates)
+      f->h_img_bytes = 2LL * chunks * 32768 * 128;
+      CUDA_TRY(cudaMalloc(&f->d_h_img, (size_t)f->h_img_bytes));
+    }
     ImgPackBatch batch;
     ImgPackDesc& d = batch.d[0];
     d.src = f->d_wproj; d.s_row = 1; d.s_k = sd.PW; d.rows = sd.PW; d.k = sd.C;
     d.dst = f->d_wproj_img; d.plane = f->wproj_plane; d.rpad = f->wproj_rpad; d.chunks = chunks;
     img_pack_kernel<<<dim3(f->wproj_rpad / 32, 1), kTgGroupThreads, 0, stream>>>(batch);
     CUDA_TRY(cudaGetLastError());
-    if (int rc = build_layered_images(f, stream)) return rc;
     if (int rc = build_s2_images(f, stream)) return rc;
     if (f->s2_ok && f->s2_scratch.empty()) {
       unsigned char* act = nullptr;
@@ -1095,7 +972,7 @@ extern "C" int bcnf_gemm_img_gelu(const void* a_img, int64_t a_plane, int32_t a_
     return fail(BCNF_E_ARG, "bcnf_gemm_img_gelu: output image too small (rpad=%d plane=%lld for M=%d N=%d)", c_rpad, (long long)c_plane, M, N);
   if (((uintptr_t)bias & 15) != 0) return fail(BCNF_E_ARG, "bcnf_gemm_img_gelu: bias must be 16-byte aligned");
   if (M == 0 || N == 0) return BCNF_OK;
-  CUDA_TRY(cudaSetDevice(device));
+  DEVICE_GUARD(device);
   int n_sm = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
   G2Args g;
@@ -1124,7 +1001,7 @@ extern "C" int bcnf_lstm_step(const bcnf_lstm_step_t* a, int32_t device, void* s
   for (int t = 0; t < tiles_n; ++t)
     if (!a->h_hi[t] || (a->passes == 3 && !a->h_lo[t])) return fail(BCNF_E_ARG, "bcnf_lstm_step: output chunk %d missing", t);
   if (a->M == 0) return BCNF_OK;
-  CUDA_TRY(cudaSetDevice(device));
+  DEVICE_GUARD(device);
   int n_sm = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
   G2Args g;
@@ -1150,7 +1027,7 @@ extern "C" int bcnf_gemm_img(const void* a_img, int64_t a_plane, int32_t a_rpad,
   if (!a_img || !b_img || !C || M < 0 || N < 0 || K < 1) return fail(BCNF_E_ARG, "bcnf_gemm_img: bad argument");
   if (passes != 1 && passes != 3) return fail(BCNF_E_ARG, "bcnf_gemm_img: passes must be 1 (bf16) or 3 (bf16x3)");
   if (M == 0 || N == 0) return BCNF_OK;
-  CUDA_TRY(cudaSetDevice(device));
+  DEVICE_GUARD(device);
   int n_sm = 0;     // (cudaGetDeviceProperties takes milliseconds per call)
   CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
   G2Args g;
@@ -1158,10 +1035,13 @@ extern "C" int bcnf_gemm_img(const void* a_img, int64_t a_plane, int32_t a_rpad,
   g.a_img = (const unsigned char*)a_img; g.a_plane = a_plane; g.a_rpad = a_rpad;
   g.b_img = (const unsigned char*)b_img; g.b_plane = b_plane; g.b_rpad = b_rpad;
   g.C = C; g.ldc = ldc; g.bias = bias; g.M = M; g.N = N; g.K = K;
-  g.debug = getenv("BCNF_G2_DEBUG") ? atoi(getenv("BCNF_G2_DEBUG")) : 0;
+  static const int g2_debug = getenv("BCNF_G2_DEBUG") ? atoi(getenv("BCNF_G2_DEBUG")) : 0;   // read once per process
+  g.debug = g2_debug;
   g.trace = (unsigned long long*)g_g2_trace;
   return passes == 3 ? launch_gemm_img2<3>(g, n_sm, (cudaStream_t)stream) : launch_gemm_img2<1>(g, n_sm, (cudaStream_t)stream);
 }
+
+static const long long kProjSlice = 32768;   // instances per launch of the projection GEMM (scratch image: one slice)
 
 extern "C" int bcnf_cond_project(bcnf_flow_t* f, const float* h, int64_t n_inst, float* P, void* stream_) {
   if (!f || !h || !P) return fail(BCNF_E_ARG, "bcnf_cond_project: null argument");
@@ -1169,26 +1049,16 @@ extern "C" int bcnf_cond_project(bcnf_flow_t* f, const float* h, int64_t n_inst,
   if (!f->params_set) return fail(BCNF_E_STATE, "bcnf_flow_set_params has not been called");
   if (n_inst == 0) return BCNF_OK;
   cudaStream_t stream = (cudaStream_t)stream_;
-  CUDA_TRY(cudaSetDevice(f->desc.device));
-  if (f->npass && !getenv("BCNF_PROJ_FMA") && !getenv("BCNF_PROJ_V1")) {
+  DEVICE_GUARD(f->desc.device);
+  if (f->npass && !f->env_proj_fma) {
     // CTA-pair GEMM on operand images, a slice of instances at a time: h -> image (scratch), P = h_img . Wproj_img^T + b
     const int chunks = (f->sd.C + 63) / 64;
-    const long long slice = 32768;
+    const long long slice = kProjSlice;
     const long long cap_rows = std::min<long long>((n_inst + 255) / 256 * 256, slice);
     const long long need = 2 * (long long)chunks * cap_rows * 128;
-    if (need > f->h_img_bytes) {
-      // (growing the scratch allocates: not possible while the caller's stream is being captured into a CUDA graph)
-      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-      CUDA_TRY(cudaStreamIsCapturing(stream, &cap));
-      if (cap != cudaStreamCaptureStatusNone)
-        return fail(BCNF_E_STATE, "bcnf_cond_project: the scratch image for %lld instances is not allocated yet; call once "
-                                  "with this many instances outside CUDA-graph capture", (long long)n_inst);
-      CUDA_TRY(cudaStreamSynchronize(stream));
-      if (f->d_h_img) CUDA_TRY(cudaFree(f->d_h_img));
-      f->d_h_img = nullptr; f->h_img_bytes = 0;
-      CUDA_TRY(cudaMalloc(&f->d_h_img, (size_t)need));
-      f->h_img_bytes = need;
-    }
+    // the scratch image holds one slice of instances and was sized for a full slice by bcnf_flow_set_params: no
+    // allocation and no synchronisation here, whatever n_inst is (graph capture at any instance count)
+    if (need > f->h_img_bytes) return fail(BCNF_E_STATE, "internal: projection scratch image smaller than one slice");
     for (long long m0 = 0; m0 < n_inst; m0 += slice) {
       const long long m = std::min<long long>(slice, n_inst - m0);
       const int rpad = (int)((m + 255) / 256 * 256);
@@ -1208,32 +1078,6 @@ extern "C" int bcnf_cond_project(bcnf_flow_t* f, const float* h, int64_t n_inst,
     }
     return BCNF_OK;
   }
-  if (f->npass && f->tc1_ok && !getenv("BCNF_PROJ_FMA")) {
-    // previous tensor-core projection kernel (proj_tc.cuh), kept for A/B timing: BCNF_PROJ_V1=1
-    auto launch = [&](auto kern) -> int {
-      const size_t smem = (size_t)f->pd.smem_bytes;
-      if (int rc = opt_in_smem(kern, smem)) return rc;   // both instantiations share this lambda's type: no caching
-      const long long n_mt = (n_inst + 2 * kTcRows - 1) / (2 * kTcRows);
-      const long long items = n_mt * (long long)f->proj_nets.size();
-      const int clusters = (int)std::min<long long>(items, f->num_sms / 2);
-      cudaLaunchConfig_t cfg{};
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr; cfg.numAttrs = 1;
-      cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(kTcThreads);
-      cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-      const float* bp = f->d_bproj;
-      const unsigned char* blob = f->d_proj_blob;
-      const ProjNet* nets = f->d_proj_nets;
-      const int n_nets = (int)f->proj_nets.size();
-      const long long ni = n_inst;
-      const ProjTcDims pd = f->pd;
-      CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, h, P, bp, blob, nets, n_nets, ni, pd));
-      return BCNF_OK;
-    };
-    return f->npass == 3 ? launch(proj_tc_kernel<3>) : launch(proj_tc_kernel<1>);
-  }
   const int N = f->sd.PW, K = f->sd.C;
   const long long max_rows = 65535LL * kProjBM;
   for (long long m0 = 0; m0 < n_inst; m0 += max_rows) {
@@ -1251,8 +1095,8 @@ static int launch_rowthread(bcnf_flow* f, const FlowArgs& a, int dir, cudaStream
   const int cap = round_up(std::max(f->prog[0].max_chunk_bytes, f->prog[1].max_chunk_bytes), 128);
   const size_t smem = 2 * (size_t)cap + 16;
   auto kern = flow_rowthread_kernel<D, HP>;
-  static thread_local size_t configured = 0;
-  if (configured < smem) { if (int rc = opt_in_smem(kern, smem)) return rc; configured = smem; }
+  static size_t configured[64] = {};
+  if (int rc = opt_in_smem_once(kern, smem, configured)) return rc;
   int occ = 0;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kRowThreadBlock, smem));
   if (occ < 1) return fail(BCNF_E_UNSUPPORTED, "row-per-thread kernel does not fit on an SM");
@@ -1268,8 +1112,8 @@ template <int R>
 static int launch_tiled(bcnf_flow* f, const FlowArgs& a, cudaStream_t stream) {
   const size_t smem = f->tiled_lay.bytes(R);
   auto kern = flow_tiled_kernel<R>;
-  static thread_local size_t configured = 0;
-  if (configured < smem) { if (int rc = opt_in_smem(kern, smem)) return rc; configured = smem; }
+  static size_t configured[64] = {};
+  if (int rc = opt_in_smem_once(kern, smem, configured)) return rc;
   int occ = 0;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kTiledThreads, smem));
   if (occ < 1) return fail(BCNF_E_UNSUPPORTED, "tiled kernel does not fit on an SM (%zu bytes)", smem);
@@ -1284,15 +1128,10 @@ template <int NPASS>
 static int launch_tc(bcnf_flow* f, const FlowArgs& a, int dir, cudaStream_t stream) {
   const size_t smem = (size_t)f->td.smem_bytes;
   auto kern = flow_tc_kernel<NPASS>;
-  static thread_local size_t configured = 0;
-  if (configured < smem) { if (int rc = opt_in_smem(kern, smem)) return rc; configured = smem; }
-  // cluster = 2, 4 or 8 CTAs (1, 2 or 4 CTA pairs sharing one multicast weight stream)
+  static size_t configured[64] = {};
+  if (int rc = opt_in_smem_once(kern, smem, configured)) return rc;
   const long long tiles = (a.n_rows + 2 * kTcRows - 1) / (2 * kTcRows);
-  // Measured on B200 (r01, FC_large): 2.62 / 2.34 / 2.16 M samples/s for clusters of 2 / 4 / 8 -- the stream is
-  // bound by the depth of the stage ring, not by L2 bandwidth, and clusters of 4 / 8 strand 16 / 20 SMs.
-  int csize = 2;
-  const char* e = getenv("BCNF_TC_CLUSTER");            // tuning / test override: exactly this cluster size
-  if (e && (atoi(e) == 2 || atoi(e) == 4 || atoi(e) == 8)) csize = atoi(e);
+  const int csize = 2;                  // one CTA pair per 128-row tile
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1320,12 +1159,7 @@ static int launch_tc2(bcnf_flow* f, const FlowArgs& a, int dir, cudaStream_t str
   const size_t smem = (size_t)f->s2.smem_bytes;
   auto kern = flow_tc2_kernel<NPASS>;
   static size_t configured[64] = {};
-  int dev = 0;
-  CUDA_TRY(cudaGetDevice(&dev));
-  if (dev >= 64 || configured[dev] < smem) {
-    if (int rc = opt_in_smem(kern, smem)) return rc;
-    if (dev < 64) configured[dev] = smem;
-  }
+  if (int rc = opt_in_smem_once(kern, smem, configured)) return rc;
   unsigned char* act = nullptr;
   if (int rc = s2_scratch_for(f, stream, &act)) return rc;
   const long long tiles = (a.n_rows + 2 * kS2Rows - 1) / (2 * kS2Rows);
@@ -1339,112 +1173,11 @@ static int launch_tc2(bcnf_flow* f, const FlowArgs& a, int dir, cudaStream_t str
   cfg.dynamicSmemBytes = smem; cfg.stream = stream;
   const StackDims sd = f->sd;
   S2Dims d2 = f->s2;
-  if (const char* dbgenv = getenv("BCNF_TC2_DEBUG")) d2.debug = atoi(dbgenv);     // timing experiments (wrong results)
+  d2.debug = f->env_tc2_debug;          // timing experiments (wrong results); 0 outside them
   const unsigned char* img = f->d_s2_img;
   const long long* offs = f->d_s2_off[dir];
   unsigned int* dbg = f->d_s2_dbg;
   CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, a, sd, d2, img, offs, act, dbg));
-  return BCNF_OK;
-}
-
-// One batch of rows through the stack, layer by layer (flow_layered.cuh).
-template <int NPASS>
-static int run_layered_batch(bcnf_flow* f, int dir, const float* in, const float* P, const int32_t* row2inst,
-                             long long inst_period, long long row_base, int rows, float* out, float* logdet,
-                             cudaStream_t stream) {
-  const StackDims& sd = f->sd;
-  const HalfLayout& hl = sd.half[0];
-  const Program& p = f->prog[dir];
-  const int rpad = (rows + 255) / 256 * 256;
-  int chunks = 1;                                        // every activation image has the widest layer's K chunks
-  for (int l = 0; l < hl.L; ++l) chunks = std::max(chunks, (hl.hp[l] + 63) / 64);
-  int n_half = 0;
-  for (const auto& op : p.ops) n_half += op.type == DOP_HALF;
-  LayeredGlueArgs ga;
-  memset(&ga, 0, sizeof(ga));
-  ga.Y = f->d_ly; ga.LD = f->d_lld; ga.n_rows = rows; ga.row_base = row_base; ga.D = sd.D; ga.DP = sd.DP;
-  ga.P = P; ga.PW = sd.PW; ga.row2inst = row2inst; ga.inst_period = inst_period; ga.passes = NPASS;
-  ga.in = in;
-  const dim3 ggrid((rows + kLgRows - 1) / kLgRows);
-  const size_t glue_smem = (size_t)((hl.hp[0] + 63) / 64) * kLgRows * 128 * (NPASS == 3 ? 2 : 1);
-  static bool glue_attr = false;
-  if (!glue_attr && glue_smem > 48 * 1024) {
-    CUDA_TRY(cudaFuncSetAttribute(flow_layered_glue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    glue_attr = true;
-  }
-  int half_seen = 0;
-  const DevOp* prev = nullptr;
-  auto set_prev = [&]() {
-    if (!prev) { ga.o = nullptr; return; }
-    ga.o = f->d_lo; ga.o_ld = 32;
-    ga.prev_dst0 = prev->src == 0 ? sd.Da : 0; ga.prev_dout = hl.dout; ga.prev_dop = hl.dop; ga.prev_inverse = prev->inverse;
-  };
-  ga.n_ops = 0;
-  for (size_t oi = 0; oi < p.ops.size(); ++oi) {
-    const DevOp& op = p.ops[oi];
-    if (op.type != DOP_HALF) {
-      if (ga.n_ops >= kLgMaxOps) return fail(BCNF_E_UNSUPPORTED, "layered path: more than %d layers between two couplings", kLgMaxOps);
-      ga.op_type[ga.n_ops] = op.type; ga.op_par[ga.n_ops] = p.d_blob + op.off; ++ga.n_ops;
-      continue;
-    }
-    // glue: finish the previous coupling, the ops in between, first Linear of this network -> image 0
-    const int h_fwd = dir == 0 ? half_seen : n_half - 1 - half_seen;     // image table is in forward layer order
-    set_prev();
-    ga.has_next = 1; ga.src0 = op.src == 0 ? 0 : sd.Da; ga.din = hl.din; ga.H1 = hl.h[0]; ga.H1p = hl.hp[0];
-    ga.W1a = p.d_blob + op.off + hl.off_w[0]; ga.proj_off = op.proj_off;
-    const long long act_plane = (long long)chunks * rpad * 128;
-    ga.img = f->d_lact[0]; ga.img_plane = act_plane; ga.img_rpad = rpad;
-    ga.out = nullptr; ga.logdet_out = nullptr;
-    flow_layered_glue_kernel<<<ggrid, kLgThreads, glue_smem, stream>>>(ga);
-    CUDA_TRY(cudaGetLastError());
-    ga.in = nullptr; ga.n_ops = 0;
-    for (int l = 1; l <= hl.L; ++l) {
-      const bcnf_flow::LwImg& wi = f->lw_img[h_fwd][l];
-      G2Args g;
-      memset(&g, 0, sizeof(g));
-      g.a_img = f->d_lact[(l - 1) & 1]; g.a_plane = act_plane; g.a_rpad = rpad;
-      g.b_img = f->d_lw_img + wi.off; g.b_plane = wi.plane; g.b_rpad = wi.rpad;
-      g.M = rows; g.K = hl.hp[l - 1];
-      if (l < hl.L) {
-        g.N = hl.hp[l]; g.bias = p.d_blob + op.off + hl.off_b[l];
-        g.c_img = f->d_lact[l & 1]; g.c_plane = act_plane; g.c_rpad = rpad;
-      } else {
-        g.N = 2 * hl.dop; g.bias = p.d_blob + op.off + hl.off_bout;
-        g.C = f->d_lo; g.ldc = 32;
-      }
-      if (int rc = launch_gemm_img2<NPASS>(g, f->num_sms, stream)) return rc;
-    }
-    prev = &op;
-    ++half_seen;
-  }
-  // last glue: finish the last coupling, trailing ops, write the result
-  set_prev();
-  ga.has_next = 0; ga.out = out; ga.logdet_out = logdet;
-  flow_layered_glue_kernel<<<ggrid, kLgThreads, glue_smem, stream>>>(ga);
-  CUDA_TRY(cudaGetLastError());
-  return BCNF_OK;
-}
-
-static int run_layered(bcnf_flow* f, int dir, const float* in, const float* P, const int32_t* row2inst,
-                       long long inst_period, long long n_rows, float* out, float* logdet, cudaStream_t stream) {
-  const StackDims& sd = f->sd;
-  if (!f->d_ly) {
-    int chunks = 1;
-    for (int l = 0; l < sd.half[0].L; ++l) chunks = std::max(chunks, (sd.half[0].hp[l] + 63) / 64);
-    const long long plane = (long long)chunks * kLayeredBatch * 128;
-    CUDA_TRY(cudaMalloc(&f->d_ly, (size_t)kLayeredBatch * sd.DP * 4));
-    CUDA_TRY(cudaMalloc(&f->d_lld, (size_t)kLayeredBatch * 4));
-    CUDA_TRY(cudaMalloc(&f->d_lo, (size_t)kLayeredBatch * 32 * 4));
-    for (int b = 0; b < 2; ++b) CUDA_TRY(cudaMalloc(&f->d_lact[b], (size_t)(2 * plane)));
-    f->lact_plane = plane;
-  }
-  for (long long r0 = 0; r0 < n_rows; r0 += kLayeredBatch) {
-    const int rows = (int)std::min<long long>(kLayeredBatch, n_rows - r0);
-    const int rc = f->npass == 3
-        ? run_layered_batch<3>(f, dir, in + r0 * sd.D, P, row2inst, inst_period, r0, rows, out + r0 * sd.D, logdet ? logdet + r0 : nullptr, stream)
-        : run_layered_batch<1>(f, dir, in + r0 * sd.D, P, row2inst, inst_period, r0, rows, out + r0 * sd.D, logdet ? logdet + r0 : nullptr, stream);
-    if (rc) return rc;
-  }
   return BCNF_OK;
 }
 
@@ -1456,7 +1189,7 @@ static int run_flow(bcnf_flow_t* f, int dir, const float* in, const float* P, co
   if (n_rows == 0) return BCNF_OK;   // empty batch: nothing to read or write
   if (!in || !P || !out) return fail(BCNF_E_ARG, "bcnf_flow_%s: null argument", dir ? "inverse" : "forward");
   cudaStream_t stream = (cudaStream_t)stream_;
-  CUDA_TRY(cudaSetDevice(f->desc.device));
+  DEVICE_GUARD(f->desc.device);
   const Program& p = f->prog[dir];
   FlowArgs a;
   a.in = in; a.out = out; a.logdet = logdet; a.P = P; a.row2inst = row2inst;
@@ -1465,7 +1198,7 @@ static int run_flow(bcnf_flow_t* f, int dir, const float* in, const float* P, co
   a.chunks = p.d_chunks; a.n_chunks = (int)p.chunks.size();
   a.trace = nullptr;
   a.blob_floats = p.blob_floats;
-  if (const char* tp = f->kernel == BCNF_KERNEL_TCGEN05 && f->s2_use ? getenv("BCNF_TC2_TRACE") : nullptr) {
+  if (const char* tp = f->kernel == BCNF_KERNEL_TCGEN05 && f->s2_use && !f->env_tc2_trace.empty() ? f->env_tc2_trace.c_str() : nullptr) {
     // debug aid: dump the clock64 stamps of block 0's issuer / epilogue / producer to the named file (synchronises!)
     const size_t n = 4 * 8192;
     long long* d_tr = nullptr;
@@ -1487,7 +1220,7 @@ static int run_flow(bcnf_flow_t* f, int dir, const float* in, const float* P, co
     }
     return rc;
   }
-  if (const char* tp = getenv("BCNF_TC_TRACE")) {
+  if (const char* tp = f->env_tc_trace.empty() ? nullptr : f->env_tc_trace.c_str()) {
     // debug aid: dump clock64 stamps of the first tile's pipeline to the named file (synchronises!)
     if (f->kernel == BCNF_KERNEL_TCGEN05 && !f->s2_use) {
       long long* d_tr = nullptr;
@@ -1510,9 +1243,6 @@ static int run_flow(bcnf_flow_t* f, int dir, const float* in, const float* P, co
     }
   }
   if (f->kernel == BCNF_KERNEL_TCGEN05) {
-    // layer by layer on the CTA-pair GEMM (BCNF_FLOW_LAYERED=1), or the fused kernel
-    const char* lay = getenv("BCNF_FLOW_LAYERED");
-    if (f->layered_ok && lay && atoi(lay) == 1) return run_layered(f, dir, in, P, row2inst, inst_period, n_rows, out, logdet, stream);
     if (f->s2_use) return f->npass == 3 ? launch_tc2<3>(f, a, dir, stream) : launch_tc2<1>(f, a, dir, stream);
     if (!f->tc1_ok) return fail(BCNF_E_STATE, "internal: no fused tensor-core kernel planned for this stack");
     return f->npass == 3 ? launch_tc<3>(f, a, dir, stream) : launch_tc<1>(f, a, dir, stream);
@@ -1549,7 +1279,7 @@ static long long* g_train_trace = nullptr;   // debug: device buffer of 64 clock
 
 // Debug aid (tools/tc_gemm_check.py): run one tensor-core GEMM with the pipeline stamps of CTA (0,0,0) recorded.
 extern "C" int bcnf_train_gemm_trace(const bcnf_gemm_args_t* args, int32_t device, void* stream, int64_t* out64) {
-  CUDA_TRY(cudaSetDevice(device));
+  DEVICE_GUARD(device);
   long long* d = nullptr;
   CUDA_TRY(cudaMalloc(&d, 64 * sizeof(long long)));
   CUDA_TRY(cudaMemset(d, 0, 64 * sizeof(long long)));
@@ -1678,7 +1408,7 @@ static_assert(sizeof(bcnf_img_pack_desc_t) == sizeof(ImgPackDesc), "bcnf_img_pac
 
 extern "C" int bcnf_img_pack(const bcnf_img_pack_desc_t* descs, int32_t n, int32_t device, void* stream) {
   if (n < 0 || (n > 0 && !descs)) return fail(BCNF_E_ARG, "bcnf_img_pack: bad argument");
-  CUDA_TRY(cudaSetDevice(device));
+  DEVICE_GUARD(device);
   for (int b0 = 0; b0 < n; b0 += kImgPackMax) {
     ImgPackBatch batch;
     const int nb = n - b0 < kImgPackMax ? n - b0 : kImgPackMax;
@@ -1721,7 +1451,7 @@ extern "C" int bcnf_train_gemm(const bcnf_gemm_args_t* args, int32_t device, voi
   if (args->epilogue == BCNF_EPI_DGELU_DROP && !args->saved) return fail(BCNF_E_ARG, "bcnf_train_gemm: saved missing");
   if (args->p_drop < 0.f || args->p_drop >= 1.f) return fail(BCNF_E_ARG, "bcnf_train_gemm: p_drop=%f", args->p_drop);
   if (args->M == 0 || args->N == 0) return BCNF_OK;
-  CUDA_TRY(cudaSetDevice(device));
+  DEVICE_GUARD(device);
   GemmArgs g;
   memcpy(&g, args, sizeof(g));
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -1757,7 +1487,7 @@ extern "C" int bcnf_train_colsum(const float* X, int32_t M, int32_t N, int64_t l
   if (!X || !out) return fail(BCNF_E_ARG, "bcnf_train_colsum: null argument");
   if (M < 0 || N < 0) return fail(BCNF_E_ARG, "bcnf_train_colsum: negative size");
   if (N == 0) return BCNF_OK;
-  CUDA_TRY(cudaSetDevice(device));
+  DEVICE_GUARD(device);
   colsum_kernel<<<(N + 31) / 32, 256, 0, (cudaStream_t)stream_>>>(X, M, N, ldx, out, beta);
   CUDA_TRY(cudaGetLastError());
   return BCNF_OK;
@@ -1769,7 +1499,7 @@ extern "C" int bcnf_train_dropout_mask(float* out, int32_t M, int32_t N, uint64_
   if (M < 0 || N < 0 || p_drop < 0.f || p_drop >= 1.f) return fail(BCNF_E_ARG, "bcnf_train_dropout_mask: bad argument");
   const long long n = (long long)M * N;
   if (n == 0) return BCNF_OK;
-  CUDA_TRY(cudaSetDevice(device));
+  DEVICE_GUARD(device);
   dropout_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(out, M, N, seed, layer_uid, p_drop,
                                                                                             (const unsigned long long*)seed_ptr);
   CUDA_TRY(cudaGetLastError());
@@ -1814,7 +1544,7 @@ extern "C" int bcnf_train_pre(const bcnf_train_pre_args_t* args, int32_t device,
   if (int rc = check_glue_dims("bcnf_train_pre", args->B, args->D, args->H, args->src0, args->din, 0)) return rc;
   if (args->p_drop < 0.f || args->p_drop >= 1.f) return fail(BCNF_E_ARG, "bcnf_train_pre: p_drop=%f", args->p_drop);
   if (args->B == 0 || args->H == 0) return BCNF_OK;
-  CUDA_TRY(cudaSetDevice(device));
+  DEVICE_GUARD(device);
   TrainPreArgs a;
   memcpy(&a, args, sizeof(a));
   dim3 grid((a.H + 127) / 128, (a.B + kPreRows - 1) / kPreRows);
@@ -1828,7 +1558,7 @@ extern "C" int bcnf_train_post(const bcnf_train_post_args_t* args, int32_t devic
   if (args->a && (!args->Wout || !args->bout || !args->ls_save || !args->ydst_save)) return fail(BCNF_E_ARG, "bcnf_train_post: null argument");
   if (int rc = check_glue_dims("bcnf_train_post", args->B, args->D, args->H, args->dst0, args->dout, args->n_ops)) return rc;
   if (args->B == 0) return BCNF_OK;
-  CUDA_TRY(cudaSetDevice(device));
+  DEVICE_GUARD(device);
   TrainPostArgs a;
   memcpy(&a, args, sizeof(a));
   int kt = 0;
@@ -1848,7 +1578,7 @@ extern "C" int bcnf_train_post_bwd(const bcnf_train_post_bwd_args_t* args, int32
     if (args->ops[o].type == GLUE_ACTNORM && (!args->ops[o].save || !args->ops[o].g0 || !args->ops[o].g1))
       return fail(BCNF_E_ARG, "bcnf_train_post_bwd: ActNorm op %d lacks save / gradient buffers", o);
   if (args->B == 0) return BCNF_OK;
-  CUDA_TRY(cudaSetDevice(device));
+  DEVICE_GUARD(device);
   TrainPostBwdArgs a;
   memcpy(&a, args, sizeof(a));
   int kt = 0;
@@ -1863,7 +1593,7 @@ extern "C" int bcnf_train_pre_bwd(const bcnf_train_pre_bwd_args_t* args, int32_t
   if (!args || !args->d_pre || !args->W1 || !args->dz) return fail(BCNF_E_ARG, "bcnf_train_pre_bwd: null argument");
   if (int rc = check_glue_dims("bcnf_train_pre_bwd", args->B, args->D, args->H, args->src0, args->din, 0)) return rc;
   if (args->B == 0) return BCNF_OK;
-  CUDA_TRY(cudaSetDevice(device));
+  DEVICE_GUARD(device);
   TrainPreBwdArgs a;
   memcpy(&a, args, sizeof(a));
   const int wp = a.din > 0 ? a.din : 1;    // lanes = consecutive columns: any pitch is conflict-free

@@ -63,8 +63,7 @@ struct TcHalfLayout {
 
 struct TcDims {
   TcHalfLayout half[2];
-  int kw;              // K columns per weight tile: 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B: half-size stages, so the
-                       // 3-pass mode can double-buffer every issuing warp within the same shared memory)
+  int kw;              // K columns per weight tile: 64 (SWIZZLE_128B)
   int a_chunks;        // 64-column activation tiles per part
   int stage_bytes;     // bytes of one weight stage (hi [+ lo] of the largest half tile)
   int n_stages;
@@ -135,16 +134,6 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
   return d;
 }
-__device__ __forceinline__ uint64_t make_smem_desc_b(uint32_t saddr, int kw) {
-  // weight tiles: 128-byte rows / SWIZZLE_128B (kw = 64) or 64-byte rows / SWIZZLE_64B (kw = 32)
-  if (kw == 64) return make_smem_desc(saddr);
-  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(512 >> 4) << 32;        // 8 rows x 64 bytes
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)4 << 61;                 // SWIZZLE_64B
-  return d;
-}
 __device__ __forceinline__ uint32_t make_idesc(int n) {
   // kind::f16, A = B = bf16 (1), D = f32 (1), both K-major, M = 128 over the CTA pair
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -162,20 +151,6 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
           smem_u32(bar)),
       "h"(cta_mask)
-      : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_nctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
-  return r;
-}
-// TMA bulk copy global -> the same shared-memory offset of every CTA in cta_mask; each destination's
-// mbarrier (same offset) receives the complete_tx
-__device__ __forceinline__ void tma_bulk_g2s_mc(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
-          smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
       : "memory");
 }
 // issue a TMEM load of 8 consecutive columns of this thread's lane (no wait)
@@ -214,9 +189,6 @@ __device__ __forceinline__ void store_act8(unsigned char* a_hi, unsigned char* a
                    pack_bf16x2(v[4] - hi[4], v[5] - hi[5]), pack_bf16x2(v[6] - hi[6], v[7] - hi[7]));
 }
 
-// Launched with a cluster of CS = 2, 4 or 8 CTAs = CS/2 CTA pairs.  Each pair owns its own 128-row tile;
-// the pairs of a cluster walk the same weight stream in lockstep, and every weight half-tile is fetched
-// from L2 once per cluster and multicast to the same-rank CTA of every pair.
 // (+ add) -> GELU -> bf16 hi/lo split of 8 accumulator columns, packed two values per instruction, stored as
 // one 16-byte chunk per part into the swizzled activation tiles
 template <int NPASS>
@@ -271,23 +243,18 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
   // uniform registers instead of wrapping every tcgen05.mma in a uniformisation loop (tools/mma_probe.cu:
   // 139 -> 106 cycles per issue)
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
-  const uint32_t cta = cluster_ctarank();         // rank in the cluster
-  const uint32_t csize = cluster_nctarank();
-  const uint32_t n_pairs = csize >> 1, pair = cta >> 1, prank = cta & 1u, lead_rank = cta & ~1u;
-  const bool leader = prank == 0;                 // even rank of a pair issues the MMAs
+  const uint32_t cta = cluster_ctarank();         // rank in the CTA pair
+  const uint32_t prank = cta & 1u, lead_rank = 0u;
+  const bool leader = prank == 0;                 // rank 0 of the pair issues the MMAs
   const int n_stages = td.n_stages;
   const long long n_tiles = (a.n_rows + 2 * kTcRows - 1) / (2 * kTcRows);
-  const long long n_clusters = gridDim.x / csize, cluster_id = blockIdx.x / csize;
-  // every pair of every cluster runs the same number of iterations (the weight stream is shared);
+  const long long n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
   // iterations whose tile index is past the end run on padding rows and store nothing
-  const long long n_iter = (n_tiles + n_clusters * n_pairs - 1) / (n_clusters * n_pairs);
-  const uint16_t mask_all = (uint16_t)((1u << csize) - 1u);
-  const uint16_t mask_pair = (uint16_t)(3u << (2u * pair));
-  uint16_t mask_same_rank = 0;
-  for (uint32_t p2 = 0; p2 < n_pairs; ++p2) mask_same_rank |= (uint16_t)(1u << (2u * p2 + prank));
+  const long long n_iter = (n_tiles + n_clusters - 1) / n_clusters;
+  const uint16_t mask_all = 3, mask_pair = 3;
 
   if (tid == 0) {
-    for (int s = 0; s < n_stages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_peer[s], 1); mbar_init(&w_empty[s], (int)n_pairs); }
+    for (int s = 0; s < n_stages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_peer[s], 1); mbar_init(&w_empty[s], 1); }
     for (int j = 0; j < kTcIssuers; ++j) mbar_init(&acc_full[j], 1);
     mbar_init(a_ready, 2);
     for (int j = 0; j < kTcIssuers; ++j) mbar_init(&a_chunk[j], 2);
@@ -326,8 +293,7 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
                 mbar_expect_tx(&w_full[s], bytes);     // every CTA arms its own barrier for every tile
                 unsigned char* dst = stage0 + (size_t)s * td.stage_bytes;
                 const unsigned char* half = src + (size_t)prank * 2u * rows_b;
-                if (n_pairs == 1) tma_bulk_g2s(dst, half, bytes, &w_full[s]);
-                else if (it % n_pairs == pair) tma_bulk_g2s_mc(dst, half, bytes, &w_full[s], mask_same_rank);
+                tma_bulk_g2s(dst, half, bytes, &w_full[s]);
                 src += 4u * rows_b;
               }
             }
@@ -424,8 +390,8 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
                 const int g0 = kc * steps_per_tile;                 // first K=16 step of this weight tile
                 const uint64_t ah = make_smem_desc(a_hi_addr + (g0 >> 2) * kTcATile) + 2 * (g0 & 3);
                 const uint64_t al = make_smem_desc(a_lo_addr + (g0 >> 2) * kTcATile) + 2 * (g0 & 3);
-                const uint64_t wh = make_smem_desc_b(st_addr + sj * td.stage_bytes, td.kw);
-                const uint64_t wl = make_smem_desc_b(st_addr + sj * td.stage_bytes + rows_b, td.kw);
+                const uint64_t wh = make_smem_desc(st_addr + sj * td.stage_bytes);
+                const uint64_t wl = make_smem_desc(st_addr + sj * td.stage_bytes + rows_b);
                 for (int k = 0; k < ksteps; ++k) {
                   const uint32_t first = (kc | k) == 0 ? 0u : 1u;
                   umma_2sm(tmem_base + col, ah + 2 * k, wh + 2 * k, idesc, first);
@@ -434,7 +400,7 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
                     umma_2sm(tmem_base + col, ah + 2 * k, wl + 2 * k, idesc, 1u);
                   }
                 }
-                umma_commit_2sm(&w_empty[sj], mask_all);   // one of n_pairs arrivals that free the stage cluster-wide
+                umma_commit_2sm(&w_empty[sj], mask_all);   // frees the stage in both CTAs
                 s += nch;
                 while (s >= n_stages) { s -= n_stages; par ^= 1; }
               }
@@ -463,7 +429,7 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
     const uint32_t a_chunk_leader = mapa_u32(smem_u32(a_chunk), lead_rank);
 
     for (long long iter = 0; iter < n_iter; ++iter) {
-      const long long tile = (iter * n_clusters + cluster_id) * n_pairs + pair;   // >= n_tiles: padding iteration
+      const long long tile = iter * n_clusters + cluster_id;   // >= n_tiles: padding iteration
       const long long row0 = tile * (2 * kTcRows) + (long long)prank * kTcRows;
       if (et < kTcRows) {
         const long long r = row0 + et;

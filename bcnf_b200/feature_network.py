@@ -21,6 +21,16 @@ __all__ = ["FeatureNetwork", "FeatureNetworkStack", "ConcatenateCondition", "FrE
            "Transformer"]
 
 
+def _inference_call(x: torch.Tensor) -> bool:
+    """Eval-mode calls take the tensor-core path unless the caller is differentiating with respect to the INPUT.
+
+    The kernels return tensors without autograd history.  In eval mode the coupling stack itself runs without history
+    (CondRealNVP_v2.forward), so a history on h would reach nothing; keying on ``torch.is_grad_enabled()`` alone made
+    ``model.log_prob(...)`` called outside ``torch.no_grad()`` seven times slower than inside it.
+    """
+    return not (torch.is_grad_enabled() and x.requires_grad)
+
+
 class FeatureNetwork(nn.Module):
     """Base class: records ``input_size`` / ``output_size`` (reference feature_network.py:10-25)."""
     input_size: int
@@ -112,7 +122,7 @@ class FullyConnectedFeatureNetwork(FeatureNetwork):
     tc_passes: int = 0      # set by CondRealNVP_v2 on tensor-core handles: 3 = bf16x3 (fp32-class), 1 = bf16, 0 = PyTorch
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        if self.tc_passes and x.is_cuda and not self.training and not torch.is_grad_enabled():
+        if self.tc_passes and x.is_cuda and not self.training and _inference_call(x):
             from . import feature_tc
             if x.size(0) >= feature_tc.MIN_ROWS and feature_tc.supported(self):
                 return feature_tc.forward(self, x, self.tc_passes)
@@ -146,7 +156,7 @@ class LSTMFeatureNetwork(FeatureNetwork):
     tc_passes: int = 0      # set by CondRealNVP_v2 on tensor-core handles: 3 = bf16x3 (fp32-class), 1 = bf16, 0 = PyTorch
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        if self.tc_passes and x.is_cuda and x.ndim == 3 and not self.training and not torch.is_grad_enabled():
+        if self.tc_passes and x.is_cuda and x.ndim == 3 and not self.training and _inference_call(x):
             from . import feature_tc
             if x.size(0) >= feature_tc.MIN_ROWS_LSTM and feature_tc.lstm_supported(self):
                 return feature_tc.lstm_forward(self, x, self.tc_passes)

@@ -114,3 +114,42 @@ def test_other_large_baseline_configs_run_and_match_the_oracle_at_h(name):
     assert s.shape == (7, 5, 19) and torch.isfinite(s).all()
     lp = model.log_prob(y, cond)
     assert lp.shape == (64,) and torch.isfinite(lp).all()
+
+
+def test_projection_and_flow_capture_in_a_cuda_graph_at_a_grown_instance_count():
+    """bcnf_cond_project + bcnf_flow_forward make no hidden synchronisation or allocation (include/bcnf_b200.h): after a
+    warm-up on the capturing stream with FEW instances, a CUDA graph of project + forward captures at MANY instances
+    (the projection's scratch image is sized once, by set_params) and replays to the eager result."""
+    model = _stack(19, [128, 128], 3, 12, precision="bf16x3")
+    flow = model._flow()
+    g = torch.Generator().manual_seed(4)
+    h_small, y_small = torch.randn(5, 12, generator=g).to(DEV), torch.randn(5, 19, generator=g).to(DEV)
+    h_big, y_big = torch.randn(3000, 12, generator=g).to(DEV), torch.randn(3000, 19, generator=g).to(DEV)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        flow.run(False, y_small, flow.project(h_small), want_logdet=True)     # per-stream activation scratch exists now
+    s.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=s):
+        z_g, ld_g = flow.run(False, y_big, flow.project(h_big), want_logdet=True)
+    z_g.zero_(); ld_g.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    z_e, ld_e = flow.run(False, y_big, flow.project(h_big), want_logdet=True)
+    assert torch.equal(z_g, z_e) and torch.equal(ld_g, ld_e)
+
+
+def test_entry_points_leave_the_current_device_alone():
+    """Every ABI entry point restores the caller's current CUDA device; only meaningful with >= 2 devices,
+    but the single-device path must at least keep device 0 current after create / run / destroy."""
+    before = torch.cuda.current_device()
+    model = _stack(19, [16] * 2, 2, 4)
+    model(torch.zeros(3, 19), torch.zeros(3, 4))
+    del model
+    assert torch.cuda.current_device() == before
+    if torch.cuda.device_count() >= 2:
+        with torch.cuda.device(1):
+            m0 = _stack(19, [16] * 2, 2, 4)            # lives on cuda:0
+            m0(torch.zeros(3, 19), torch.zeros(3, 4))
+            assert torch.cuda.current_device() == 1

@@ -1,4 +1,4 @@
-"""tcgen05 path (bcnf_b200/csrc/flow_tc.cuh) against the CPU oracle, smallest shapes first.
+"""tcgen05 path (bcnf_b200/csrc/flow_tc2.cuh; flow_tc.cuh with BCNF_FLOW_TC=1) against the CPU oracle, smallest shapes first.
 
 Tolerances (relative to max|ref|, SURVEY.md section 8d "correctness gates"):
   bf16x3 (3-term bf16 split, fp32 accumulate): the fp32 gate of conftest.assert_parity, 1e-5.
@@ -48,6 +48,8 @@ SHAPES = [
     (19, [526] * 5, 3, 1360, False, 300),       # trajectory_*_large conditioner
     (21, [175, 175, 175], 3, 107, True, 129),   # D=21, two-way, odd width
     (19, [206, 206, 206], 3, 40, False, 513),
+    (19, [1024, 1024, 1024], 2, 64, False, 260),  # four 256-column N chunks (BASELINE config 5 corner)
+    (19, [336, 336], 2, 32, False, 1000),         # 256 + 80 columns, width a multiple of 16: bias added in the epilogue
 ]
 
 
@@ -81,45 +83,6 @@ def test_tensorcore_matches_oracle(shape, precision):
     else:
         for k, tol in BF16_TOL.items():
             assert errs[k] < tol, (k, errs)
-
-
-LAYERED_SHAPES = [s for s in SHAPES if not s[4]]     # the layer-by-layer schedule covers one-way stacks
-
-
-@pytest.mark.parametrize("shape", LAYERED_SHAPES, ids=lambda s: f"D{s[0]}_H{s[1][0]}x{len(s[1])}_K{s[2]}_C{s[3]}_B{s[5]}")
-def test_layered_schedule_matches_oracle_and_fused_kernel(shape, monkeypatch):
-    """BCNF_FLOW_LAYERED=1: the same stack, one layer at a time on the CTA-pair GEMM (csrc/flow_layered.cuh).  Same
-    arithmetic as the fused kernel (3-pass bf16 split, fp32 elsewhere; the first Linear is exact fp32 FMA here), so
-    the same 1e-5 gate on z and x; the log-det gate is 2e-5 of max|ref| (for a single block the log-det is a sum of
-    nine tanh values of order 0.1, and both schedules sit at ~1e-5 of it)."""
-    size, nested, blocks, n_cond, two_way, rows = shape
-    model = _model(size, nested, blocks, n_cond, "bf16x3", two_way)
-    g = torch.Generator().manual_seed(11)
-    y = torch.randn(rows, size, generator=g)
-    h = torch.randn(rows, n_cond, generator=g)
-    z_in = torch.randn(rows, size, generator=g)
-    z_f = model(y, h, log_det_J=True)
-    ld_f = model.log_det_J
-    x_f = model.inverse(z_in, h)
-    monkeypatch.setenv("BCNF_FLOW_LAYERED", "1")
-    z = model(y, h, log_det_J=True)
-    ld = model.log_det_J
-    x = model.inverse(z_in, h)
-    monkeypatch.delenv("BCNF_FLOW_LAYERED")
-    assert not torch.equal(z, z_f)                   # a different schedule really ran
-    sd = {k: v.cpu().numpy() for k, v in model.state_dict().items()}
-    l32 = fo.layers_from_state_dict(sd)
-    l64 = fo.layers_from_state_dict(sd, convert=lambda v: np.asarray(v, dtype=np.float64))
-    z32, ld32 = fo.stack_forward(l32, y.numpy(), h.numpy())
-    x32 = fo.stack_inverse(l32, z_in.numpy(), h.numpy())
-    z64, _ = fo.stack_forward(l64, y.numpy().astype(np.float64), h.numpy().astype(np.float64))
-    x64 = fo.stack_inverse(l64, z_in.numpy().astype(np.float64), h.numpy().astype(np.float64))
-    assert_parity(z.cpu().numpy(), z32, z64, what="z")
-    assert_parity(x.cpu().numpy(), x32, x64, what="x")
-    assert rel_err(ld.cpu().numpy(), ld32) < 2e-5
-    # and the two schedules agree with each other far inside the gate
-    assert rel_err(z.cpu().numpy(), z_f.cpu().numpy()) < 1e-5 and rel_err(x.cpu().numpy(), x_f.cpu().numpy()) < 1e-5
-    assert rel_err(ld.cpu().numpy(), ld_f.cpu().numpy()) < 2e-5
 
 
 def test_fc_feature_network_on_tensor_cores_matches_pytorch():
@@ -217,28 +180,6 @@ def test_tensorcore_agrees_with_fp32_kernels_on_golden_large_batch():
     assert rel_err(lb.cpu().numpy(), la.cpu().numpy()) < 1e-5
 
 
-@pytest.mark.parametrize("cluster", ["2", "4", "8"])
-@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
-def test_cluster_multicast_sizes_agree(cluster, precision, monkeypatch):
-    # 2, 4 and 8-CTA clusters (1, 2, 4 CTA pairs on one multicast weight stream) give bit-identical results,
-    # including ragged tile counts where some pairs run padding iterations
-    monkeypatch.setenv("BCNF_TC_CLUSTER", "2")
-    ref_model = _model(19, [176, 176, 176], 3, 24, precision)
-    g = torch.Generator().manual_seed(21)
-    outs = {}
-    for rows in (1, 129, 128 * 5 + 3, 128 * 40 + 77):
-        y = torch.randn(rows, 19, generator=g).to(DEV)
-        h = torch.randn(rows, 24, generator=g).to(DEV)
-        monkeypatch.setenv("BCNF_TC_CLUSTER", "2")
-        z2 = ref_model(y, h, log_det_J=True).clone(); l2 = ref_model.log_det_J.clone()
-        monkeypatch.setenv("BCNF_TC_CLUSTER", cluster)
-        zc = ref_model(y, h, log_det_J=True); lc = ref_model.log_det_J
-        assert torch.equal(z2, zc) and torch.equal(l2, lc), (rows, cluster)
-        xc = ref_model.inverse(zc, h)
-        monkeypatch.setenv("BCNF_TC_CLUSTER", "2")
-        assert torch.equal(xc, ref_model.inverse(z2, h))
-
-
 @pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
 @pytest.mark.parametrize("shape", [(19, [526] * 2, 3, 1360, False, 300), (21, [175, 175], 2, 107, True, 129),
                                    (19, [64], 1, 8, False, 5)], ids=["large", "two_way_odd", "tiny"])
@@ -250,8 +191,10 @@ def test_tensorcore_projection_matches_torch(shape, precision, monkeypatch):
     g = torch.Generator().manual_seed(31)
     h = torch.randn(n_inst, n_cond, generator=g).to(DEV)
     P = flow.project(h)
-    monkeypatch.setenv("BCNF_PROJ_FMA", "1")
-    P_fma = flow.project(h)                      # the fp32 FMA projection kernel of the same handle
+    monkeypatch.setenv("BCNF_PROJ_FMA", "1")     # (switches are read once, when a handle is created)
+    model._packed = None
+    P_fma = model._flow().project(h)             # the fp32 FMA projection kernel on a handle of the same parameters
+    monkeypatch.delenv("BCNF_PROJ_FMA")
     hp = -(-nested[0] // 16) * 16
     col, da = 0, (size + 1) // 2
     for layer in model.layers:
@@ -273,5 +216,35 @@ def test_tensorcore_projection_matches_torch(shape, precision, monkeypatch):
 def test_auto_precision_picks_the_kernel_family():
     assert _model(19, [16] * 3, 2, 8, "auto")._flow().kernel == "rowthread"
     assert _model(19, [128] * 3, 2, 8, "auto")._flow().kernel == "tcgen05"
-    assert _model(19, [1024] * 2, 2, 8, "auto")._flow().kernel == "tiled"   # 3-pass tiles do not fit in smem
+    # width 1024 in the fp32-class 3-pass mode: the second-generation kernel streams activations through L2, so the
+    # shared-memory limit of the first generation (which sent this shape to the fp32 tiled kernel) no longer applies
+    assert _model(19, [1024] * 2, 2, 8, "auto")._flow().kernel == "tcgen05"
     assert _model(19, [1024] * 2, 2, 8, "bf16")._flow().kernel == "tcgen05"
+    assert _model(19, [1024] * 2, 2, 8, "auto")._flow().info.rows_per_cta == 128
+
+
+@pytest.mark.parametrize("shape", [s for s in SHAPES if max(s[1]) <= 526],
+                         ids=lambda s: f"D{s[0]}_H{s[1][0]}x{len(s[1])}_K{s[2]}_C{s[3]}_tw{int(s[4])}_B{s[5]}")
+def test_both_kernel_generations_agree(shape, monkeypatch):
+    """flow_tc2.cuh (default: 128 rows per CTA, activations through L2) and flow_tc.cuh (BCNF_FLOW_TC=1: 64 rows per CTA,
+    activations in shared memory) run the same arithmetic; they differ only where a bias is folded into the GEMM
+    (widths that are not multiples of 16), by the rounding of its bf16 hi / lo split."""
+    size, nested, blocks, n_cond, two_way, rows = shape
+    new = _model(size, nested, blocks, n_cond, "bf16x3", two_way)
+    assert new._flow().info.rows_per_cta == 128
+    monkeypatch.setenv("BCNF_FLOW_TC", "1")
+    old = _model(size, nested, blocks, n_cond, "bf16x3", two_way)
+    assert old._flow().info.rows_per_cta == 64
+    monkeypatch.delenv("BCNF_FLOW_TC")
+    g = torch.Generator().manual_seed(11)
+    y = torch.randn(rows, size, generator=g)
+    h = torch.randn(rows, n_cond, generator=g)
+    for inverse in (False, True):
+        fn = (lambda m: m.inverse(y, h)) if inverse else (lambda m: m(y, h, log_det_J=True))
+        a, b = fn(new), fn(old)
+        if all(w % 16 == 0 for w in nested):
+            assert torch.equal(a, b)
+            if not inverse:
+                assert torch.equal(new.log_det_J, old.log_det_J)
+        else:
+            assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 3e-6

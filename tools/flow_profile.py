@@ -1,5 +1,5 @@
 """Kernel-level timeline (torch.profiler / CUPTI) of one inverse pass of the trajectory_FC_large stack.
-Usage (GPU box): [BCNF_FLOW_LAYERED=1] python tools/flow_profile.py [rows]"""
+Usage (GPU box): [BCNF_FLOW_TC=1] python tools/flow_profile.py [rows]"""
 import os
 import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -33,7 +33,10 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 e0.record(); flow.run(True, z, P, inst_period=n_inst, out=out); e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1)
 print(f"inverse of {rows} rows: {ms:.3f} ms = {rows / ms / 1e3:.3f} M rows/s")
-os.environ["BCNF_TC2_TRACE"] = path
+os.environ["BCNF_TC2_TRACE"] = path              # read once, when the handle is created
+model._packed = None
+flow = model._flow()
+P = flow.project(h)
 flow.run(True, z, P, inst_period=n_inst, out=out)
 torch.cuda.synchronize()
 del os.environ["BCNF_TC2_TRACE"]

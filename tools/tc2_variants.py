@@ -18,7 +18,10 @@ P = flow.project(h)
 z = torch.randn(rows, mk["size"], device=dev)
 out = torch.empty_like(z)
 for v in variants:
-    os.environ["BCNF_TC2_DEBUG"] = str(v)
+    os.environ["BCNF_TC2_DEBUG"] = str(v)        # read once, when the handle is created
+    model._packed = None
+    flow = model._flow()
+    P = flow.project(h)
     for _ in range(2):
         flow.run(True, z, P, inst_period=n_inst, out=out)
     torch.cuda.synchronize()
