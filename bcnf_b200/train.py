@@ -80,16 +80,58 @@ class _PoolLease:
             pass
 
 
-_IMGS: dict[tuple, _Img] = {}
+import collections
+
+_IMGS: "collections.OrderedDict[tuple, _Img]" = collections.OrderedDict()
+_IMG_OWNERS: dict[tuple, Any] = {}      # key -> weakref of the tensor the image belongs to (entry dies with it)
+_SCRATCH_CAP = 256                      # ownerless (row-scratch) images kept; least recently used ones are dropped
 
 
-def _img(dev: torch.device, tag: Any, rows: int, k: int, align: int = 128) -> _Img:
-    """Cached scratch image: (device, tag, shape) -> buffer.  Scratch images are reused in stream order."""
+def _img(dev: torch.device, tag: Any, rows: int, k: int, align: int = 128, owner: torch.Tensor | None = None) -> _Img:
+    """Cached scratch image: (device, tag, shape) -> buffer.  Scratch images are reused in stream order.
+
+    ``owner``: the parameter an image is made from.  The entry is then dropped when that tensor is garbage-collected
+    (a weakref callback), so that building and discarding models -- k-fold runs, hyper-parameter searches -- does not
+    pin two bf16 hi/lo copies of every weight matrix for the life of the process.
+    """
     key = (dev.index or 0, tag, rows, k, align)
     im = _IMGS.get(key)
-    if im is None:
+    if im is not None:
+        _IMGS.move_to_end(key)
+    else:
         im = _IMGS[key] = _Img(dev, rows, k, align)
+        if owner is None and len(_IMGS) - len(_IMG_OWNERS) > _SCRATCH_CAP:
+            # a new batch / chunk size every call must not pin device memory forever: drop the scratch image that has
+            # not been used for longest (its memory returns to the caching allocator, stream-ordered like any tensor)
+            for old in _IMGS:
+                if old not in _IMG_OWNERS:
+                    del _IMGS[old]
+                    break
+        if owner is not None:
+            import weakref
+
+            def _drop(_ref, key=key):
+                _IMGS.pop(key, None)
+                _IMG_OWNERS.pop(key, None)
+            try:
+                _IMG_OWNERS[key] = weakref.ref(owner, _drop)
+            except TypeError:
+                pass
     return im
+
+
+def clear_caches() -> None:
+    """Release every cached operand image and image pool of this process (``Trainer.close()`` calls it)."""
+    _IMGS.clear()
+    _IMG_OWNERS.clear()
+    _PoolLease._free.clear()
+    try:
+        from . import feature_tc
+        clear = getattr(feature_tc, "clear_caches", None)
+        if clear is not None:
+            clear()
+    except Exception:      # interpreter shutdown
+        pass
 
 
 def _pack_images(descs: list[tuple[torch.Tensor, int, int, int, int, int, _Img]], dev: torch.device) -> None:
@@ -278,8 +320,10 @@ class _StackFn(torch.autograd.Function):
                 ws = params[u.w0: u.w0 + spec.n_lin]
                 w1, b1 = ws[0], params[u.w0 + spec.n_lin]
                 H1, pitch1 = w1.shape[0], w1.stride(0)
-                fwd = [_img(dev, ("wf", w1.data_ptr()), H1, Cn)] + [_img(dev, ("wf", w.data_ptr()), *w.shape) for w in ws[1:L]]
-                bwd = [_img(dev, ("wb", w1.data_ptr()), Cn, H1)] + [_img(dev, ("wb", w.data_ptr()), w.shape[1], w.shape[0]) for w in ws[1:L]]
+                fwd = [_img(dev, ("wf", w1.data_ptr()), H1, Cn, owner=w1)] + \
+                      [_img(dev, ("wf", w.data_ptr()), *w.shape, owner=w) for w in ws[1:L]]
+                bwd = [_img(dev, ("wb", w1.data_ptr()), Cn, H1, owner=w1)] + \
+                      [_img(dev, ("wb", w.data_ptr()), w.shape[1], w.shape[0], owner=w) for w in ws[1:L]]
                 descs = [(w1, u.din, pitch1, 1, H1, Cn, fwd[0]), (w1, u.din, 1, pitch1, Cn, H1, bwd[0])]
                 for l in range(1, L):
                     w = ws[l]
@@ -345,6 +389,10 @@ class _StackFn(torch.autograd.Function):
             y = y_out
         main.wait_stream(side)
         ctx.spec, ctx.params, ctx.h = spec, params, h
+        # The parameters are held as plain attributes (their bf16 images, not the tensors, are what the backward reads),
+        # so autograd's own version check does not see them: remember the versions and refuse a backward after an
+        # in-place update (optimizer.step between forward and backward) instead of returning wrong gradients.
+        ctx.param_versions = [t._version for t in params]
         ctx.plan = (lead, units, lead_saves, saved_units)
         ctx.wimg = wimg
         ctx.h_img = h_img
@@ -355,6 +403,13 @@ class _StackFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dz: torch.Tensor, dld: torch.Tensor):
         spec, params, h = ctx.spec, ctx.params, ctx.h
+        if not torch.cuda.is_current_stream_capturing():
+            for i, (t, v) in enumerate(zip(params, ctx.param_versions)):
+                if t._version != v:
+                    raise RuntimeError(
+                        f"one of the variables needed for gradient computation has been modified by an inplace operation: "
+                        f"parameter {i} of the coupling stack is at version {t._version}; expected version {v} "
+                        "(an optimizer step between forward and backward?)")
         lead, units, lead_saves, saved_units = ctx.plan
         D, L = spec.size, spec.n_lin - 1
         dz = dz.contiguous().float()
@@ -542,8 +597,7 @@ class Trainer:
         self.mse_loss = torch.nn.MSELoss()
         self.cuda_graph = cuda_graph
         self.process_group = process_group
-        self._graph: Any = None
-        self._static: Any = None
+        self._graphs: dict[tuple, dict[str, Any]] = {}      # one captured step per batch shape
         if cuda_graph:
             if hasattr(model, "module"):
                 raise NotImplementedError("cuda_graph=True with a DistributedDataParallel wrapper is not supported: pass the "
@@ -568,8 +622,12 @@ class Trainer:
     def close(self) -> None:
         """Drop the captured graph.  With process_group= the graph holds NCCL kernels of the group's communicator:
         call this (and synchronize) before ``torch.distributed.destroy_process_group()``, which otherwise waits for it."""
-        self._graph, self._static = None, None
+        self._graphs.clear()
         self._flat = None
+        net = self._net()
+        if getattr(net, "_dropout_seed_word", None) is not None:
+            net._dropout_seed_word = None       # eager train-mode forwards draw their own seeds again
+        clear_caches()
 
     def _allreduce_grads(self) -> None:
         """Average the gradients over the process group through one flat buffer (one NCCL call)."""
@@ -605,20 +663,43 @@ class Trainer:
         loss = (nll + mse * self.hybrid_weight) / (1 + self.hybrid_weight)
         return loss, nll, mse, z
 
+    def _seed_word(self, net: Any, dev: torch.device) -> torch.Tensor:
+        """Device-resident dropout counter, created ONCE per model: it keeps counting across graph captures (a reset
+        would replay the same mask sequence after every new batch shape) and starts from a random base mixed with the
+        rank, so that replicas draw different masks (nn.Dropout under DistributedDataParallel does too)."""
+        w = getattr(net, "_dropout_seed_word", None)
+        if w is None or w.device != dev:
+            rank = 0
+            if self.process_group is not None:
+                import torch.distributed as dist
+                rank = dist.get_rank(self.process_group)
+            base = int(torch.randint(0, 2 ** 40, (1,)).item())            # consumes the CPU generator, like nn.Dropout
+            w = net._dropout_seed_word = torch.tensor([base + (rank << 44)], dtype=torch.int64, device=dev)
+        return w
+
     def _graphed_step(self, y: torch.Tensor, *conditions: torch.Tensor):
         net = self._net()
         dev = torch.device(net.device)
         shapes = (tuple(y.shape),) + tuple(tuple(c.shape) for c in conditions)
-        if self._graph is None or self._static["shapes"] != shapes:
-            net._dropout_seed_word = torch.zeros(1, dtype=torch.int64, device=dev)
+        st = self._graphs.get(shapes)
+        if st is None:
+            seed_word = self._seed_word(net, dev)
             st = {"shapes": shapes, "y": torch.empty_like(y, device=dev),
                   "c": [torch.empty_like(c, device=dev) for c in conditions]}
             st["y"].copy_(y)
             for d, c in zip(st["c"], conditions):
                 d.copy_(c)
+            # Warm-up off the capture stream (allocator, lazy initialisations incl. the optimizer's state tensors).
+            # It must not count as training: parameters, optimizer state and the seed word are put back afterwards --
+            # a partial last batch would otherwise give the model four extra Adam updates per epoch.
+            params = [p for p in net.parameters()]
+            snap_p = [p.detach().clone() for p in params]
+            snap_o = {id(t): t.detach().clone() for stt in self.optimizer.state.values() for t in stt.values()
+                      if torch.is_tensor(t)}
+            snap_w = seed_word.clone()
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(side):              # warm-up off the capture stream (allocator, lazy inits)
+            with torch.cuda.stream(side):
                 for _ in range(3):
                     self.optimizer.zero_grad(set_to_none=True)
                     loss, _, _, _ = self._losses(st["y"], *st["c"])
@@ -626,7 +707,15 @@ class Trainer:
                     if self.process_group is not None:
                         self._allreduce_grads()
                     self.optimizer.step()
-                    net._dropout_seed_word.add_(1)
+                    seed_word.add_(1)
+                with torch.no_grad():
+                    for p, q in zip(params, snap_p):
+                        p.copy_(q)
+                    for stt in self.optimizer.state.values():
+                        for t in stt.values():
+                            if torch.is_tensor(t):
+                                t.copy_(snap_o[id(t)]) if id(t) in snap_o else t.zero_()   # created by the warm-up: as new
+                    seed_word.copy_(snap_w)
             torch.cuda.current_stream(dev).wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             self.optimizer.zero_grad(set_to_none=True)
@@ -638,14 +727,13 @@ class Trainer:
                 if self.process_group is not None:
                     self._allreduce_grads()
                 self.optimizer.step()
-                net._dropout_seed_word.add_(1)          # fresh dropout masks on every replay
-            st.update(loss=loss, nll=nll, mse=mse)
-            self._graph, self._static = graph, st
-        st = self._static
+                seed_word.add_(1)                       # fresh dropout masks on every replay
+            st.update(loss=loss, nll=nll, mse=mse, graph=graph)
+            self._graphs[shapes] = st
         st["y"].copy_(y, non_blocking=True)
         for d, c in zip(st["c"], conditions):
             d.copy_(c, non_blocking=True)
-        self._graph.replay()
+        st["graph"].replay()
         return st["loss"], st["nll"], st["mse"]
 
     def train_batch(self, y: torch.Tensor, *conditions: torch.Tensor) -> tuple[float, float, float]:

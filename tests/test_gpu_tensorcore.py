@@ -49,7 +49,7 @@ SHAPES = [
     (21, [175, 175, 175], 3, 107, True, 129),   # D=21, two-way, odd width
     (19, [206, 206, 206], 3, 40, False, 513),
     (19, [1024, 1024, 1024], 2, 64, False, 260),  # four 256-column N chunks (BASELINE config 5 corner)
-    (19, [336, 336], 2, 32, False, 1000),         # 256 + 80 columns, width a multiple of 16: bias added in the epilogue
+    (19, [336, 336, 336], 3, 32, False, 700),     # 256 + 80 columns, width a multiple of 16: bias added in the epilogue
 ]
 
 
