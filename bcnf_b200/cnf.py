@@ -53,6 +53,7 @@ PRECISIONS = {"auto": -1, "fp32": _cabi.PREC_FP32, "bf16x3": _cabi.PREC_BF16X3, 
 # ------------------------------------------------------------------------------------------
 class PackedFlow:
     """A ``bcnf_flow_t`` built from a list of layer modules; repacks when parameters change."""
+    check_row_map = True     # validate explicit row2inst indices against P (one device reduction + sync per call)
 
     def __init__(self, layers: Sequence[nn.Module], size: int, n_conditions: int, nested_sizes: Sequence[int],
                  two_way: bool, device: torch.device, precision: str = "fp32") -> None:
@@ -181,6 +182,23 @@ class PackedFlow:
         if x.ndim != 2 or x.shape[1] != self.size:
             raise ValueError(f"expected input of shape (B, {self.size}), got {tuple(x.shape)}")
         n = x.shape[0]
+        # the ABI takes raw pointers: the row -> instance map is checked here, against the projection it indexes
+        n_inst = P.shape[0]
+        if P.ndim != 2 or P.shape[1] != max(self.proj_width, 1) or P.dtype != torch.float32 or not P.is_contiguous():
+            raise ValueError(f"P must be a contiguous float32 (n_inst, {max(self.proj_width, 1)}) tensor, got "
+                             f"{tuple(P.shape)} {P.dtype}")
+        if row2inst is not None:
+            if row2inst.numel() != n:
+                raise ValueError(f"row2inst has {row2inst.numel()} entries for {n} rows")
+            if n and self.check_row_map:
+                lo, hi = int(row2inst.min()), int(row2inst.max())
+                if lo < 0 or hi >= n_inst:
+                    raise IndexError(f"row2inst entries must lie in [0, {n_inst}), got [{lo}, {hi}]")
+        elif inst_period > 0:
+            if inst_period > n_inst:
+                raise IndexError(f"inst_period={inst_period} exceeds the {n_inst} instances of P")
+        elif n > n_inst:
+            raise IndexError(f"{n} rows but P holds {n_inst} instances (identity row -> instance map)")
         if out is None:
             out = torch.empty_like(x)
         ld = torch.empty(n, dtype=torch.float32, device=self.device) if want_logdet else None

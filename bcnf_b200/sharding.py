@@ -42,11 +42,26 @@ def shard_conditions(conditions: Sequence[torch.Tensor], group: Any = None) -> t
     return [c[lo:hi] for c in conditions], lo, hi
 
 
+def _collective_device(block: torch.Tensor, group: Any = None) -> torch.device:
+    """Device the backend of ``group`` moves tensors on: NCCL needs CUDA tensors, gloo takes CPU ones."""
+    backend = str(dist.get_backend(group)).lower()
+    if "nccl" in backend and block.device.type != "cuda":
+        return torch.device("cuda", torch.cuda.current_device())
+    return block.device
+
+
 def gather_instance_blocks(block: torch.Tensor, n_total: int, dim: int, group: Any = None) -> torch.Tensor:
-    """all_gather blocks of unequal length along ``dim`` (instance axis) into the full tensor."""
+    """all_gather blocks of unequal length along ``dim`` (instance axis) into the full tensor.
+
+    A CPU block under the NCCL backend is moved to this rank's GPU for the collective and the result returned on the
+    block's own device (prefer ``output_device=<the model's device>`` in that case: ``sample_sharded`` does)."""
     rank, world = _group_info(group)
     if world == 1:
         return block
+    home = block.device
+    cdev = _collective_device(block, group)
+    if cdev != home:
+        return gather_instance_blocks(block.to(cdev), n_total, dim, group).to(home)
     sizes = [shard_bounds(n_total, r, world) for r in range(world)]
     longest = max(hi - lo for lo, hi in sizes)
     moved = block.movedim(dim, 0).contiguous()
@@ -66,6 +81,12 @@ def sample_sharded(sample_fn: Callable[..., torch.Tensor], n_samples: int, *cond
     (n_samples, N, D) on every rank when ``gather=True``.
     """
     mine, lo, hi = shard_conditions(conditions, group)
+    want = kwargs.get("output_device", None)
+    if gather and want is None and dist.is_available() and dist.is_initialized() \
+            and "nccl" in str(dist.get_backend(group)).lower():
+        # model.sample defaults to output_device="cpu": gathering that over NCCL would round-trip the samples through
+        # host memory (and all_gather of a CPU tensor raises).  Keep the block on the GPU for the collective.
+        kwargs["output_device"] = torch.device("cuda", torch.cuda.current_device())
     out = sample_fn(n_samples, *mine, outer=True, **kwargs)
     if gather:
         out = gather_instance_blocks(out, conditions[0].shape[0], dim=1, group=group)

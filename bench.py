@@ -70,6 +70,11 @@ def perturb_actnorm(model, seed: int = 1) -> None:
                 layer.bias.copy_((0.1 * torch.randn(layer.bias.shape, generator=g)).to(layer.bias.device))
 
 
+# (kernel family, config) -> (DRAM bytes per row from one ncu --set full capture, the committed summary it comes from)
+NCU_DRAM_BYTES_PER_ROW = {("tcgen05", "trajectory_FC_large"): (19.66e9 / 75776, "profiles/r02_flow_tc2.txt"),
+                          ("rowthread", "trajectory_FC_small"): (40.8e6 / 5.0e5, "profiles/r01_rowthread_lds.txt")}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -166,6 +171,58 @@ def oracle_cpu_rate(cfg: dict, kind: str, samples: int, budget_s: float = 12.0) 
                       f"back end incl. per-row feature network as the reference does"}
 
 
+def reference_cpu_rate(cfg: dict, kind: str, samples: int, budget_s: float = 12.0) -> dict:
+    """Time the UNMODIFIED reference (oracle/_ref: byte-identical copy of /root/reference/src/bcnf made by
+    oracle/build_ref.py, imported through oracle/ref_shim.py) on the host cores: its own CondRealNVP_v2.sample /
+    forward in eval mode under no_grad, fp32, all threads, BASELINE.md section 2 protocol.  Falls back to the oracle port
+    where the reference cannot run the workload (its LSTM encoder only accepts batch == 30) or is absent."""
+    try:
+        from oracle.ref_shim import import_reference, reference_available
+        fn_types = [f["type"] for f in cfg["feature_networks"]]
+        if not reference_available() or any("LSTM" in t for t in fn_types):
+            raise RuntimeError("reference not usable for this workload")
+        ref = import_reference()
+    except Exception as e:  # noqa: BLE001
+        out = oracle_cpu_rate(cfg, kind, samples, budget_s)
+        out["sample"] += f" [port: {e}]"
+        return out
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    model = ref.CondRealNVP_v2.from_config(cfg).eval()
+    gen = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for layer in model.layers:
+            if isinstance(layer, ref.ActNorm):
+                layer.scale.copy_(0.75 + 0.5 * torch.rand(layer.scale.shape, generator=gen))
+                layer.bias.copy_(0.1 * torch.randn(layer.bias.shape, generator=gen))
+    mk = cfg["model"]["kwargs"]
+    d, big = mk["size"], mk["nested_sizes"][0] > 64
+    if kind == "sample":
+        m, n_inst = (256, 8) if big else (256, 64)
+    else:
+        m, n_inst = 1, (2048 if big else 16384)
+    rows = m * n_inst
+    g = torch.Generator().manual_seed(3)
+    cond = torch.randn(n_inst, 30, 3, generator=g)
+    y = torch.randn(rows, d, generator=g)
+
+    def once():
+        with torch.no_grad():
+            if kind == "sample":       # cnf.py:510-538: tiles the conditions, re-runs the encoder per row, draws z on the CPU
+                return model.sample(m, cond, outer=True, batch_size=n_inst, sample_batch_size=m)
+            return model.forward(y, cond, log_det_J=True)
+
+    once()
+    best, t_end, reps = float("inf"), time.perf_counter() + budget_s, 0
+    while reps < 3 or (time.perf_counter() < t_end and reps < 50):
+        t0 = time.perf_counter(); once(); best = min(best, time.perf_counter() - t0); reps += 1
+    call = f"model.sample({m}, cond[{n_inst}], outer=True)" if kind == "sample" else f"model.forward(y[{rows}], cond, log_det_J=True)"
+    return {"value": rows / best, "unit": "samples/s" if kind == "sample" else "evals/s", "cores": torch.get_num_threads(),
+            "kind": "reference",
+            "sample": f"{kind} {m} x {n_inst} instances = {rows} rows, best of {reps}: the unmodified reference "
+                      f"(oracle/_ref, src/bcnf/models/cnf.py) {call}, eval mode, no_grad, fp32"}
+
+
 def oracle_cpu_train_rate(cfg: dict, batch: int, budget_s: float = 15.0) -> dict:
     """One optimisation step (forward NLL + backward + Adam) of the oracle port on the host cores."""
     from bcnf_b200 import CondRealNVP_v2
@@ -220,11 +277,31 @@ def main_train(args, cfg, cfg_key, batch, rank, world, local_rank) -> None:
     torch.cuda.set_device(device)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+    line = measure_train(args, cfg, cfg_key, batch, rank, world, local_rank, args.steps, args.warmup, e2e=True)
+    if rank == 0:
+        line.update({"metric": metric, "unit": unit, "n_gpus": world, "higher_is_better": True, "scaling": "weak",
+                     "vs_baseline": None, "dtype": "f32", "data": "synthetic"})
+        line["config"]["workload"] = workload_name
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = oracle_cpu_train_rate(cfg, batch)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def measure_train(args, cfg, cfg_key, batch, rank, world, local_rank, steps, warmup, e2e=True) -> dict:
+    """Time Trainer.train_batch (forward NLL + backward + Adam; with world > 1 the NCCL all-reduce of the gradients inside
+    the step's CUDA graph) on an initialised process group; returns the fields of the bench line (rank 0: complete)."""
+    import torch.distributed as dist
+    import bcnf_b200
+    mk = cfg["model"]["kwargs"]
+    unit = "samples/s"
+    device = torch.device("cuda", local_rank)
     torch.manual_seed(0)
     model = bcnf_b200.CondRealNVP_v2.from_config(cfg)
     perturb_actnorm(model)
     model = model.to(device).train()
-    net = model
     # default: the whole step (incl. the NCCL all-reduce of the flat gradient buffer) is one CUDA graph;
     # BCNF_TRAIN_DDP=1: eager steps under torch's DistributedDataParallel; BCNF_NO_TRAIN_GRAPH=1: eager steps
     use_ddp = world > 1 and bool(os.environ.get("BCNF_TRAIN_DDP"))
@@ -244,10 +321,10 @@ def main_train(args, cfg, cfg_key, batch, rank, world, local_rank) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, n):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier(); ev0.record()
-        for _ in range(steps):
+        for _ in range(n):
             fn()
         ev1.record(); barrier()
         ms = ev0.elapsed_time(ev1)
@@ -260,56 +337,49 @@ def main_train(args, cfg, cfg_key, batch, rank, world, local_rank) -> None:
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         trainer.train_batch(y_dev, c_dev)
-    ms_total = timed(lambda: trainer.train_batch(y_dev, c_dev), args.steps)
+    ms_total = timed(lambda: trainer.train_batch(y_dev, c_dev), steps)
     clocks = sampler.stop() if rank == 0 else {}
-    e2e_steps = max(1, min(args.steps, 5))
-    ms_e2e = timed(lambda: trainer.train_batch(y_host, c_host), e2e_steps)
-    value = world * batch * args.steps / (ms_total * 1e-3)
+    e2e_steps = max(1, min(steps, 5))
+    ms_e2e = timed(lambda: trainer.train_batch(y_host, c_host), e2e_steps) if e2e else None
+    value = world * batch * steps / (ms_total * 1e-3)
     n_lin = len(mk["nested_sizes"]) + 1
     n_coupling = mk["n_blocks"] * (2 if mk.get("two_way") else 1)
     from oracle.flow_oracle import macs_per_row
     flops_step = 3 * 2.0 * macs_per_row(mk["size"], mk["nested_sizes"], mk["n_blocks"], mk["n_conditions"], hoisted=False) * batch
     peaks, peak_src = measured_peaks()
-    achieved = flops_step / (ms_total / args.steps * 1e-3) / 1e12
-    if rank == 0:
-        line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload_name, "size": mk["size"], "nested_sizes": mk["nested_sizes"],
-                           "n_blocks": mk["n_blocks"], "n_conditions": mk["n_conditions"],
-                           "kernel": "train_tc2_gemm (tcgen05, TMA-fed bf16 hi/lo operand images) + fused pre/post kernels; "
-                                     "weight gradients train_tc_gemm (tcgen05, fp32 operands)",
-                           "precision": "bf16x3 (3-pass split, fp32 accumulate: fp32-class)", "optimizer": "torch.optim.Adam(fused=True)", "cuda_graph": use_graph, "l2": "weights (195 MB) exceed nothing; "
-                           "each step touches every parameter, gradient and Adam moment",
-                           "parallelism": f"data parallel over {world} GPU(s), " + ("torch DistributedDataParallel (eager)" if use_ddp else
-                                           "one NCCL all-reduce of the flat gradient buffer inside the step's CUDA graph")},
-                "e2e": {"value": world * batch * e2e_steps / (ms_e2e * 1e-3), "unit": unit,
-                        "h2d_bytes_per_step": (y_host.numel() + c_host.numel()) * 4, "d2h_bytes_per_step": 12,
-                        "ms_per_step": ms_e2e / e2e_steps},
-                # per conditioner network: pre, hidden GEMMs, post; post_bwd, data-gradient GEMMs, pre_bwd; weight-gradient
-                # GEMMs, P and d h GEMMs, two column sums, the operand-image pack (bcnf_b200/train.py)
-                "gpu_launches": args.steps * (n_coupling * (4 * (n_lin - 2) + 8) + 3),
-                "roofline": {"bound": "tensor", "achieved": achieved, "peak": float(peaks["bf16_tflops"]), "unit": "TFLOP/s",
-                             "frac": achieved / float(peaks["bf16_tflops"]), "traffic": None,
-                             "peak_source": f"{peak_src} bf16 dense", "kernel": "train_tc2_gemm_kernel / train_tc_gemm_kernel (all launches of the step)",
-                             "note": "algorithmic FLOPs (3 x forward) of the step / step time; at batch 256 the step is a chain of ~310 "
-                                     "dependent launches of ~10 us each plus the PyTorch feature network and Adam (SURVEY 8d: latency-, not "
-                                     "throughput-bound); --instances-per-step 4096 / 32768 shows the tensor-core rate"},
-                "clocks": clocks}
-        if not args.no_cpu_baseline:
-            line["cpu_baseline"] = oracle_cpu_train_rate(cfg, batch)
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        # the step's CUDA graph holds kernels of the NCCL communicator: release it before the group goes away
-        trainer.close()
-        del trainer
-        import gc
-        gc.collect()
-        torch.cuda.synchronize()
-        dist.barrier()
-        dist.destroy_process_group()
+    achieved = flops_step / (ms_total / steps * 1e-3) / 1e12
+    line = {"value": value, "steps": steps, "warmup": max(warmup, 3), "ms_per_step": ms_total / steps,
+            "config": {"size": mk["size"], "nested_sizes": mk["nested_sizes"],
+                       "n_blocks": mk["n_blocks"], "n_conditions": mk["n_conditions"],
+                       "kernel": "train_tc2_gemm (tcgen05, TMA-fed bf16 hi/lo operand images) + fused pre/post kernels; "
+                                 "weight gradients train_tc3_dw (tcgen05, MN-major images)",
+                       "precision": "bf16x3 (3-pass split, fp32 accumulate: fp32-class)", "optimizer": "torch.optim.Adam(fused=True)",
+                       "cuda_graph": use_graph, "l2": "each step touches every parameter, gradient and Adam moment (4 x 195 MB)",
+                       "parallelism": f"data parallel over {world} GPU(s), " + ("torch DistributedDataParallel (eager)" if use_ddp else
+                                       "one NCCL all-reduce of the flat gradient buffer inside the step's CUDA graph")},
+            # per conditioner network: pre, hidden GEMMs, post; post_bwd, data-gradient GEMMs, pre_bwd; weight-gradient
+            # GEMMs, P and d h GEMMs, two column sums, the operand-image pack (bcnf_b200/train.py)
+            "gpu_launches": steps * (n_coupling * (4 * (n_lin - 2) + 8) + 3),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": float(peaks["bf16_tflops"]), "unit": "TFLOP/s",
+                         "frac": achieved / float(peaks["bf16_tflops"]), "traffic": None,
+                         "peak_source": f"{peak_src} bf16 dense", "kernel": "train_tc2_gemm_kernel / train_tc3_dw_kernel (all launches of the step)",
+                         "note": "algorithmic FLOPs (3 x forward) of the step / step time; at batch 256 the step is a chain of ~310 "
+                                 "dependent launches of ~10 us each plus the PyTorch feature network and Adam (SURVEY 8d: latency-, not "
+                                 "throughput-bound); --instances-per-step 4096 / 32768 shows the tensor-core rate"},
+            "clocks": clocks}
+    if e2e:
+        line["e2e"] = {"value": world * batch * e2e_steps / (ms_e2e * 1e-3), "unit": unit,
+                       "h2d_bytes_per_step": (y_host.numel() + c_host.numel()) * 4, "d2h_bytes_per_step": 12,
+                       "ms_per_step": ms_e2e / e2e_steps}
+    # the step's CUDA graph holds kernels of the NCCL communicator: release it before the group goes away
+    trainer.close()
+    del trainer
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    return line
 
 
 def main() -> None:
@@ -345,7 +415,7 @@ def main() -> None:
         # the host cores (the Python reference tree does not exist on the GPU box)
         if rank != 0:
             return
-        base = oracle_cpu_rate(cfg, kind, m_samples, budget_s=20.0)
+        base = reference_cpu_rate(cfg, kind, m_samples, budget_s=20.0)
         rows_step = int(base["sample"].split("=")[1].split()[0])
         line = {"impl": "reference", "metric": metric, "value": base["value"], "unit": unit, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * rows_step / base["value"],
@@ -370,8 +440,13 @@ def main() -> None:
     flow = model._flow()
     d = mk["size"]
     g = torch.Generator().manual_seed(100 + rank)
-    # each rank owns its own block of instances (shard by instance, no collective)
-    cond_host = torch.randn(inst_step, 30, 3, generator=g).pin_memory()
+    # shard by conditioning instance, no collective on the data path.  One step of the whole job holds
+    # world x inst_step instances; bcnf_b200.sharding hands this rank its contiguous block of them.
+    from bcnf_b200 import sharding
+    cond_global = torch.randn(world * inst_step, 30, 3, generator=torch.Generator().manual_seed(99))
+    (cond_block,), lo, hi = sharding.shard_conditions([cond_global])
+    assert hi - lo == inst_step
+    cond_host = cond_block.contiguous().pin_memory()
     cond_dev = cond_host.to(device)
     rows_step = m_samples * inst_step
     launches = [0]
@@ -445,15 +520,14 @@ def main() -> None:
     achieved_tf = flops_launch / (ms_kernel * 1e-3) / 1e12
     peak_tf = float(peaks.get("bf16_tflops_sustained" if ms_kernel > 500 else "bf16_tflops"))
     fma_peak_tf = 148 * 128 * 2 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12
-    # DRAM bytes per row of the flow kernel from the committed ncu --set full captures (profiles/r01_*), scaled to
-    # this launch; for the tensor-core kernel almost all of it is the weight tile stream (re-read once per wave)
-    ncu_bytes_per_row = {("tcgen05", "trajectory_FC_large"): 1.588e9 / 1.0e5,
-                         ("rowthread", "trajectory_FC_small"): 40.8e6 / 5.0e5}.get((flow.kernel, cfg_key))
-    traffic = ncu_bytes_per_row * rows_step if ncu_bytes_per_row else None
+    # DRAM bytes per row of the flow kernel from the committed ncu --set full captures (profiles/), scaled to this
+    # launch.  flow_tc2 (r02): dirty lines of the L2-resident activation scratch that are written back before they
+    # are overwritten, plus the weight images and the projection slices (profiles/r02_flow_tc2.txt)
+    ncu = NCU_DRAM_BYTES_PER_ROW.get((flow.kernel, cfg_key))
+    traffic = ncu[0] * rows_step if ncu else None
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved_tf / peak_tf, "traffic": traffic,
-                "traffic_source": "ncu dram__bytes_read+write per row (profiles/r01_tcgen05_v3.txt, r01_rowthread_lds.txt) x rows"
-                                  if traffic else None,
+                "traffic_source": f"ncu dram__bytes_read+write per row ({ncu[1]}) x rows" if traffic else None,
                 "peak_source": f"{peak_src} bf16 dense",
                 "kernel": f"flow_{flow.kernel}", "kernel_ms": ms_kernel,
                 "fp32_fma_peak_tflops": fma_peak_tf, "fp32_fma_frac": achieved_tf / fma_peak_tf,
@@ -466,6 +540,45 @@ def main() -> None:
     e2e_value = world * rows_step * e2e_steps / (ms_e2e * 1e-3)
     h2d = cond_host.numel() * 4 + (0 if kind == "sample" else rows_step * d * 4)
     d2h = rows_step * d * 4 if kind == "sample" else rows_step * 4
+
+    # auxiliary measurements carried by the default line (not the headline; each names its own workload):
+    #   train_*     BASELINE config 4, trajectory_TRF_large training step, batch 256 per GPU -- the one multi-GPU
+    #               workload that communicates (NCCL all-reduce of 195 MB of gradients per step), so that the driver's
+    #               1/2/4/8-GPU runs record a curve with a collective on it;
+    #   fc_small_*  BASELINE config 1, trajectory_FC_small sampling on the fp32 row-per-thread kernel.
+    aux = None
+    if args.workload == "fc_large_sample" and not os.environ.get("BCNF_BENCH_NO_AUX"):
+        aux = {}
+        try:
+            del zbuf, P
+            torch.cuda.empty_cache()
+            tcfg = load_run_config("trajectory_TRF_large")
+            tl = measure_train(args, tcfg, "trajectory_TRF_large", 256, rank, world, local_rank, steps=20, warmup=5, e2e=False)
+            aux.update({"train_workload": "trajectory_TRF_large training step (forward NLL + backward + Adam), batch 256 per GPU, "
+                                          "dropout on; gradients averaged by one NCCL all-reduce inside the step's CUDA graph",
+                        "train_ms_per_step": tl["ms_per_step"], "train_samples_per_s": tl["value"], "train_n_gpus": world})
+        except Exception as e:  # noqa: BLE001   (the headline must not depend on the auxiliary run)
+            aux["train_error"] = repr(e)[:300]
+        try:
+            scfg = load_run_config("trajectory_FC_small")
+            small = build_model(scfg, device, "auto")
+            sflow = small._flow()
+            sc = torch.randn(inst_step, 30, 3, device=device)
+            with torch.no_grad():
+                sP = sflow.project(small.features(sc))
+                sz = torch.randn((rows_step, scfg["model"]["kwargs"]["size"]), device=device)
+                def small_step():
+                    sflow.run(True, sz, sP, inst_period=inst_step)
+                for _ in range(3):
+                    small_step()
+                ms_small = timed(small_step, 10) / 10
+            aux.update({"fc_small_workload": f"trajectory_FC_small posterior sampling, {m_samples} x {inst_step} rows per launch, "
+                                             f"{sflow.kernel} kernel (fp32 FMA)",
+                        "fc_small_samples_per_s": world * rows_step / (ms_small * 1e-3),
+                        "fc_small_tflops": 2.0 * int(sflow.info.macs_per_row) * rows_step / (ms_small * 1e-3) / 1e12,
+                        "fc_small_fp32_fma_frac": 2.0 * int(sflow.info.macs_per_row) * rows_step / (ms_small * 1e-3) / 1e12 / fma_peak_tf})
+        except Exception as e:  # noqa: BLE001
+            aux["fc_small_error"] = repr(e)[:300]
 
     if rank == 0:
         line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
@@ -483,8 +596,10 @@ def main() -> None:
                 "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / e2e_steps},
                 "gpu_launches": n_launch, "roofline": roofline, "clocks": clocks}
+        if aux is not None:
+            line["aux"] = aux
         if not args.no_cpu_baseline:
-            line["cpu_baseline"] = oracle_cpu_rate(cfg, kind, m_samples)
+            line["cpu_baseline"] = reference_cpu_rate(cfg, kind, m_samples)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

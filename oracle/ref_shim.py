@@ -1,8 +1,9 @@
 """Live import of the reference (psaegert/bcnf) -- build-container only, test infrastructure.
 
-``/root/reference`` exists in the build container and NOT on the GPU box, so this module is
-used only by ``tests/golden/make_golden.py`` (fixture generation) and by not-gpu tests
-that are skipped when the tree is absent.  Recipe from SURVEY.md Appendix A:
+``/root/reference`` exists in the build container and NOT on the GPU box.  This module is used by
+``tests/golden/make_golden.py`` (fixture generation), by not-gpu tests that are skipped when no tree is
+present, and by ``bench.py --impl reference`` / its ``cpu_baseline`` leg, which time the reference's own
+``CondRealNVP_v2`` from the vendored copy ``oracle/_ref`` (``oracle/build_ref.py``) on the GPU box's host cores.  Recipe from SURVEY.md Appendix A:
 ``bcnf/__init__.py`` pulls in matplotlib and ``bcnf/utils.py`` imports dynaconf, neither
 of which is installed, so the package is registered by hand and dynaconf is stubbed.
 """
@@ -12,7 +13,18 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("BCNF_REFERENCE_ROOT", "/root/reference")
+VENDORED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")   # oracle/build_ref.py: unmodified copy
+
+
+def _default_root() -> str:
+    """/root/reference in the build container; the vendored, byte-identical copy (oracle/_ref) where that is absent
+    (the GPU box)."""
+    if os.path.isdir(os.path.join("/root/reference", "src", "bcnf")):
+        return "/root/reference"
+    return VENDORED_ROOT
+
+
+REFERENCE_ROOT = os.environ.get("BCNF_REFERENCE_ROOT") or _default_root()
 
 
 def reference_available() -> bool:

@@ -153,3 +153,25 @@ def test_entry_points_leave_the_current_device_alone():
             m0 = _stack(19, [16] * 2, 2, 4)            # lives on cuda:0
             m0(torch.zeros(3, 19), torch.zeros(3, 4))
             assert torch.cuda.current_device() == 1
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_instance_shards_reproduce_the_unsharded_samples(world):
+    """sharding by conditioning instance must not change any instance's samples.  The N ranks of a
+    node are emulated one after the other on this GPU (the blocks of bcnf_b200.sharding.shard_bounds, the z rows of
+    each block injected): every (sample, instance) row is bit-identical to the unsharded launch, for the tensor-core
+    and the fp32 kernel.  tools/shard_equiv_check.py is the same check with real ranks under torchrun."""
+    from bcnf_b200 import sharding
+    for precision, nested in (("bf16x3", [128, 128]), ("fp32", [16, 16])):
+        model = _stack(19, nested, 3, 12, precision=precision)
+        g = torch.Generator().manual_seed(6)
+        n_inst, m = 37, 5
+        cond = torch.randn(n_inst, 12, generator=g)
+        z = torch.randn(m, n_inst, 19, generator=g)
+        full = model._sample(m, cond, outer=True, z=z.reshape(-1, 19))
+        parts = []
+        for r in range(world):
+            lo, hi = sharding.shard_bounds(n_inst, r, world)
+            if hi > lo:
+                parts.append(model._sample(m, cond[lo:hi], outer=True, z=z[:, lo:hi].reshape(-1, 19)))
+        assert torch.equal(torch.cat(parts, dim=1), full)
