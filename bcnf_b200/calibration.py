@@ -2,8 +2,9 @@
 
 Adjacent to the hot path: ``compute_y_hat_ranks`` is the main caller of
 ``model.sample`` in the reference.  There every (M, N, D) sample tensor is copied to the host and
-reduced there; here the reduction ``sum_m [y_hat_m < y]`` runs on the device chunk by chunk, so
-only the (N, D) ranks ever leave the GPU.  Same signature and return value as the reference.
+reduced there; here the reduction ``sum_m [y_hat_m < y]`` is the output stage of the inverse kernel
+itself (``bcnf_flow_sample_ranks``: Philox z in, int32 counters out), so the samples are never written
+anywhere and only the (N, D) ranks ever leave the GPU.  Same signature and return value as the reference.
 """
 from __future__ import annotations
 
@@ -44,13 +45,21 @@ def compute_y_hat_ranks(model: Any, y: torch.Tensor, *conditions: torch.Tensor, 
         return torch.sum(y_hat_all < y_out.unsqueeze(0), dim=0)
     dev = torch.device(model.device)
     n = conditions[0].shape[0]
-    ranks = torch.empty((n, model.size), dtype=torch.int64, device=dev)
-    chunk = max(1, min(n, (1 << 26) // max(M_samples * model.size, 1)))     # <= 64 Mi sample values resident
-    for b in range(0, n, chunk):
-        cs = [c[b: b + chunk] for c in conditions]
-        y_hat = model._sample_device(M_samples, *cs, sigma=1, output_device=dev)      # (M, chunk, D) on the device
-        ranks[b: b + chunk] = (y_hat < y[b: b + chunk].to(dev).unsqueeze(0)).sum(dim=0)
-    return ranks.to(output_device)
+    flow = model._flow()
+    ranks = torch.zeros((n, model.size), dtype=torch.int32, device=dev)
+    yd = y.to(device=dev, dtype=torch.float32).contiguous()
+    # The comparison and the sum over the M samples happen in the output stage of the inverse kernel
+    # (bcnf_flow_sample_ranks): z is drawn in the kernel, the (M, chunk, D) samples are never written, only the
+    # (N, D) counters exist in memory.  Chunked over instances so that one launch stays below 2^24 rows.
+    chunk = max(1, min(n, (1 << 24) // max(M_samples, 1)))
+    with torch.no_grad():
+        for b in range(0, n, chunk):
+            cs = [c[b: b + chunk] for c in conditions]
+            nb = cs[0].shape[0]
+            P = flow.project(model.features(*cs))
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            flow.sample_ranks(M_samples * nb, P, yd[b: b + nb], ranks[b: b + nb], seed=seed, sigma=1.0, inst_period=nb)
+    return ranks.to(device=output_device, dtype=torch.int64)
 
 
 def compute_CDF_residuals(y_hat_all_sorted_ranks: torch.Tensor, M_samples: int, t_divisions: int = 100,

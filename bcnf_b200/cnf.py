@@ -182,7 +182,53 @@ class PackedFlow:
         if x.ndim != 2 or x.shape[1] != self.size:
             raise ValueError(f"expected input of shape (B, {self.size}), got {tuple(x.shape)}")
         n = x.shape[0]
-        # the ABI takes raw pointers: the row -> instance map is checked here, against the projection it indexes
+        r2i = self._check_map(P, n, row2inst, inst_period)
+        if out is None:
+            out = torch.empty_like(x)
+        ld = torch.empty(n, dtype=torch.float32, device=self.device) if want_logdet else None
+        fn = self.lib.bcnf_flow_inverse if inverse else self.lib.bcnf_flow_forward
+        _cabi.check(fn(self._handle, x.data_ptr(), P.data_ptr(), r2i, int(inst_period), n, out.data_ptr(),
+                       ld.data_ptr() if ld is not None else 0, _stream_ptr(self.device)),
+                    "bcnf_flow_inverse" if inverse else "bcnf_flow_forward")
+        return out, ld
+
+
+    def sample(self, n_rows: int, P: torch.Tensor, *, seed: int, sigma: float = 1.0, row2inst: torch.Tensor | None = None,
+               inst_period: int = 0, out: torch.Tensor | None = None) -> torch.Tensor:
+        """Inverse pass on a latent drawn INSIDE the kernel (``bcnf_flow_sample``): z = sigma * N(0, 1) from
+        Philox4x32-10 at counter row * D + j under ``seed``.  No z array is allocated, written or read."""
+        self.sync_params()
+        if out is None:
+            out = torch.empty((n_rows, self.size), dtype=torch.float32, device=self.device)
+        r2i = self._check_map(P, n_rows, row2inst, inst_period)
+        _cabi.check(self.lib.bcnf_flow_sample(self._handle, int(seed) & (2 ** 64 - 1), float(sigma), P.data_ptr(), r2i,
+                                              int(inst_period), n_rows, out.data_ptr(), 0, _stream_ptr(self.device)),
+                    "bcnf_flow_sample")
+        return out
+
+    def sample_ranks(self, n_rows: int, P: torch.Tensor, y: torch.Tensor, ranks: torch.Tensor, *, seed: int = 0,
+                     sigma: float = 1.0, z: torch.Tensor | None = None, row2inst: torch.Tensor | None = None,
+                     inst_period: int = 0) -> torch.Tensor:
+        """``ranks[i, j] += #{rows of instance i : x[row, j] < y[i, j]}`` (``bcnf_flow_sample_ranks``): the reduction of
+        calibration.py:44-48 in the kernel's output stage; the samples are never written.  ``z`` given: read instead of drawn."""
+        self.sync_params()
+        y = _dev_f32(y, self.device, "y")
+        if y.shape != (P.shape[0], self.size) or ranks.shape != y.shape or ranks.dtype != torch.int32 or not ranks.is_contiguous():
+            raise ValueError(f"y and ranks must be (n_inst, {self.size}) = {(P.shape[0], self.size)}, ranks int32 contiguous")
+        zp = 0
+        if z is not None:
+            z = _dev_f32(z, self.device, "z")
+            if z.shape != (n_rows, self.size):
+                raise ValueError(f"expected z of shape ({n_rows}, {self.size}), got {tuple(z.shape)}")
+            zp = z.data_ptr()
+        r2i = self._check_map(P, n_rows, row2inst, inst_period)
+        _cabi.check(self.lib.bcnf_flow_sample_ranks(self._handle, zp, int(seed) & (2 ** 64 - 1), float(sigma), P.data_ptr(), r2i,
+                                                    int(inst_period), n_rows, y.data_ptr(), ranks.data_ptr(),
+                                                    _stream_ptr(self.device)), "bcnf_flow_sample_ranks")
+        return ranks
+
+    def _check_map(self, P: torch.Tensor, n: int, row2inst: torch.Tensor | None, inst_period: int) -> int:
+        """The ABI takes raw pointers: the row -> instance map is checked here, against the projection it indexes."""
         n_inst = P.shape[0]
         if P.ndim != 2 or P.shape[1] != max(self.proj_width, 1) or P.dtype != torch.float32 or not P.is_contiguous():
             raise ValueError(f"P must be a contiguous float32 (n_inst, {max(self.proj_width, 1)}) tensor, got "
@@ -194,23 +240,14 @@ class PackedFlow:
                 lo, hi = int(row2inst.min()), int(row2inst.max())
                 if lo < 0 or hi >= n_inst:
                     raise IndexError(f"row2inst entries must lie in [0, {n_inst}), got [{lo}, {hi}]")
-        elif inst_period > 0:
+            self._r2i_keep = row2inst.to(device=self.device, dtype=torch.int32).contiguous()
+            return self._r2i_keep.data_ptr()
+        if inst_period > 0:
             if inst_period > n_inst:
                 raise IndexError(f"inst_period={inst_period} exceeds the {n_inst} instances of P")
         elif n > n_inst:
             raise IndexError(f"{n} rows but P holds {n_inst} instances (identity row -> instance map)")
-        if out is None:
-            out = torch.empty_like(x)
-        ld = torch.empty(n, dtype=torch.float32, device=self.device) if want_logdet else None
-        r2i = 0
-        if row2inst is not None:
-            row2inst = row2inst.to(device=self.device, dtype=torch.int32).contiguous()
-            r2i = row2inst.data_ptr()
-        fn = self.lib.bcnf_flow_inverse if inverse else self.lib.bcnf_flow_forward
-        _cabi.check(fn(self._handle, x.data_ptr(), P.data_ptr(), r2i, int(inst_period), n, out.data_ptr(),
-                       ld.data_ptr() if ld is not None else 0, _stream_ptr(self.device)),
-                    "bcnf_flow_inverse" if inverse else "bcnf_flow_forward")
-        return out, ld
+        return 0
 
 
 # ------------------------------------------------------------------------------------------
@@ -681,10 +718,11 @@ class CondRealNVP_v2(ConditionalInvertibleLayer):
                 nb = cs[0].shape[0]
                 h = self.features(*cs)
                 P = flow.project(h)
-                z = torch.randn((n_samples * nb, self.size), dtype=torch.float32, device=dev, generator=generator)
-                if sigma != 1:
-                    z.mul_(sigma)
-                x, _ = flow.run(True, z, P, inst_period=nb, out=z)
+                # z = sigma * N(0, 1) is drawn inside the kernel (Philox keyed by one seed per chunk, taken from the
+                # generator like a torch.randn call would advance it): no z tensor, no torch.randn launch
+                seed = int(torch.randint(0, 2 ** 62, (1,), generator=generator).item()) if generator is not None \
+                    else int(torch.randint(0, 2 ** 62, (1,)).item())
+                x = flow.sample(n_samples * nb, P, seed=seed, sigma=sigma, inst_period=nb)
                 out[:, b: b + nb].copy_(x.view(n_samples, nb, self.size), non_blocking=True)
         if out_dev.type == "cpu":
             torch.cuda.current_stream(dev).synchronize()

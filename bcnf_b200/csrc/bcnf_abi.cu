@@ -1181,13 +1181,24 @@ static int launch_tc2(bcnf_flow* f, const FlowArgs& a, int dir, cudaStream_t str
   return BCNF_OK;
 }
 
+// what bcnf_flow_sample / bcnf_flow_sample_ranks add to a plain forward / inverse call
+struct FlowExtra {
+  bool draw = false;                 // in == null: z is drawn inside the kernel
+  unsigned long long seed = 0;
+  float sigma = 1.f;
+  const float* rank_y = nullptr;     // rank reduction instead of the output
+  int* rank_out = nullptr;
+};
+
 static int run_flow(bcnf_flow_t* f, int dir, const float* in, const float* P, const int32_t* row2inst,
-                    int64_t inst_period, int64_t n_rows, float* out, float* logdet, void* stream_) {
+                    int64_t inst_period, int64_t n_rows, float* out, float* logdet, void* stream_,
+                    const FlowExtra& ex = FlowExtra()) {
   if (!f) return fail(BCNF_E_ARG, "bcnf_flow_%s: null handle", dir ? "inverse" : "forward");
   if (n_rows < 0 || inst_period < 0) return fail(BCNF_E_ARG, "negative size");
   if (!f->params_set) return fail(BCNF_E_STATE, "bcnf_flow_set_params has not been called");
   if (n_rows == 0) return BCNF_OK;   // empty batch: nothing to read or write
-  if (!in || !P || !out) return fail(BCNF_E_ARG, "bcnf_flow_%s: null argument", dir ? "inverse" : "forward");
+  if ((!in && !ex.draw) || !P || (!out && !ex.rank_out))
+    return fail(BCNF_E_ARG, "bcnf_flow_%s: null argument", dir ? "inverse" : "forward");
   cudaStream_t stream = (cudaStream_t)stream_;
   DEVICE_GUARD(f->desc.device);
   const Program& p = f->prog[dir];
@@ -1198,6 +1209,7 @@ static int run_flow(bcnf_flow_t* f, int dir, const float* in, const float* P, co
   a.chunks = p.d_chunks; a.n_chunks = (int)p.chunks.size();
   a.trace = nullptr;
   a.blob_floats = p.blob_floats;
+  a.seed = ex.seed; a.sigma = ex.sigma; a.rank_y = ex.rank_y; a.rank_out = ex.rank_out;
   if (const char* tp = f->kernel == BCNF_KERNEL_TCGEN05 && f->s2_use && !f->env_tc2_trace.empty() ? f->env_tc2_trace.c_str() : nullptr) {
     // debug aid: dump the clock64 stamps of block 0's issuer / epilogue / producer to the named file (synchronises!)
     const size_t n = 4 * 8192;
@@ -1257,6 +1269,26 @@ static int run_flow(bcnf_flow_t* f, int dir, const float* in, const float* P, co
   }
   if (f->tiled_R == 32) return launch_tiled<32>(f, a, stream);
   return launch_tiled<16>(f, a, stream);
+}
+
+// Posterior sampling with the latent drawn inside the kernel (bcnf_b200.h): inverse pass on z = sigma * N(0, 1).
+extern "C" int bcnf_flow_sample(bcnf_flow_t* f, uint64_t seed, float sigma, const float* P, const int32_t* row2inst,
+                                int64_t inst_period, int64_t n_rows, float* x, float* logdet, void* stream) {
+  if (!x) return fail(BCNF_E_ARG, "bcnf_flow_sample: null output");
+  FlowExtra ex;
+  ex.draw = true; ex.seed = seed; ex.sigma = sigma;
+  return run_flow(f, 1, nullptr, P, row2inst, inst_period, n_rows, x, logdet, stream, ex);
+}
+
+// Calibration ranks fused behind the sampler: ranks[i, j] += #{rows r of instance i : x[r, j] < y[i, j]}; the samples
+// themselves are never written.  z drawn inside the kernel as in bcnf_flow_sample, or read from `z` if it is not null.
+extern "C" int bcnf_flow_sample_ranks(bcnf_flow_t* f, const float* z, uint64_t seed, float sigma, const float* P,
+                                      const int32_t* row2inst, int64_t inst_period, int64_t n_rows, const float* y,
+                                      int32_t* ranks, void* stream) {
+  if (!y || !ranks) return fail(BCNF_E_ARG, "bcnf_flow_sample_ranks: null argument");
+  FlowExtra ex;
+  ex.draw = z == nullptr; ex.seed = seed; ex.sigma = sigma; ex.rank_y = y; ex.rank_out = ranks;
+  return run_flow(f, 1, z, P, row2inst, inst_period, n_rows, nullptr, nullptr, stream, ex);
 }
 
 extern "C" int bcnf_flow_forward(bcnf_flow_t* f, const float* y, const float* P, const int32_t* row2inst,

@@ -162,12 +162,64 @@ struct FlowArgs {
   int n_chunks;
   long long* trace;       // debug: clock64 stamps of the tensor-core pipeline (null in normal runs)
   long long blob_floats;  // size of `blob` (floats)
+  // in == null: the input is drawn inside the kernel, z[row, j] = sigma * N(0, 1) from Philox4x32-10 keyed by `seed` at
+  // counter row * D + j (cnf.py:566,578,584 draw it with torch.randn on the CPU and copy it over)
+  unsigned long long seed;
+  float sigma;
+  // rank_out != null: the result is not written; instead rank_out[inst, j] += (x[row, j] < rank_y[inst, j]), the
+  // reduction of compute_y_hat_ranks (src/bcnf/eval/calibration.py:44-48), inst = the row's conditioning instance
+  const float* rank_y;    // (n_inst, D)
+  int* rank_out;          // (n_inst, D), zeroed by the caller
 };
+
+// ---- counter-based normal deviates: Philox4x32-10 (Salmon et al. 2011) + Box-Muller ----------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// element e of the (n_rows, D) standard-normal field of `seed`: word e & 3 of the Philox block at counter e >> 2
+// (two Box-Muller pairs per block).  A pure function of (seed, e): the same value in every kernel, tile and launch.
+__device__ __forceinline__ float philox_normal(unsigned long long seed, unsigned long long e) {
+  uint32_t w[4];
+  const unsigned long long ctr = e >> 2;
+  philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), 0x6263u, 0x6e66u, (uint32_t)seed, (uint32_t)(seed >> 32), w);
+  const int lane = (int)(e & 3ull);
+  const uint32_t a = w[lane & 2], b = w[(lane & 2) + 1];
+  const float u1 = ((float)(a >> 8) + 1.0f) * (1.0f / 16777216.0f);        // (0, 1]
+  const float u2 = (float)(b >> 8) * (1.0f / 16777216.0f);                  // [0, 1)
+  const float r = sqrtf(-2.0f * logf(u1));
+  float sn, cs;
+  sincospif(2.0f * u2, &sn, &cs);
+  return r * ((lane & 1) ? sn : cs);
+}
+// input element (row, j): read, or drawn in place when the caller passed no input
+__device__ __forceinline__ float flow_input(const FlowArgs& a, long long row, int j, int D) {
+  const long long e = row * D + j;
+  return a.in ? __ldg(a.in + e) : a.sigma * philox_normal(a.seed, (unsigned long long)e);
+}
 
 __device__ __forceinline__ long long row_instance(const FlowArgs& a, long long r) {
   if (a.row2inst) return (long long)a.row2inst[r];
   if (a.inst_period > 0) return r % a.inst_period;
   return r;
+}
+
+// result element (row, j): written, or folded into the rank counters of its conditioning instance
+__device__ __forceinline__ void flow_output(const FlowArgs& a, long long row, int j, int D, float v) {
+  if (a.rank_out) {
+    const long long i = row_instance(a, row) * D + j;
+    if (v < __ldg(a.rank_y + i)) atomicAdd(a.rank_out + i, 1);
+  } else {
+    a.out[row * D + j] = v;
+  }
 }
 
 }  // namespace bcnf

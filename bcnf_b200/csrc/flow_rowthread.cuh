@@ -194,9 +194,8 @@ flow_rowthread_kernel(const FlowArgs a, const StackDims sd, const int chunk_cap_
     float ld = 0.f;
     const float* prow = a.P;
     if (valid) {
-      const float* src = a.in + row * D;
 #pragma unroll
-      for (int j = 0; j < D; ++j) y[j] = __ldg(src + j);
+      for (int j = 0; j < D; ++j) y[j] = flow_input(a, row, j, D);
       prow = a.P + row_instance(a, row) * (long long)sd.PW;
     } else {
 #pragma unroll
@@ -246,9 +245,8 @@ flow_rowthread_kernel(const FlowArgs a, const StackDims sd, const int chunk_cap_
     }
 
     if (valid) {
-      float* dst = a.out + row * D;
 #pragma unroll
-      for (int j = 0; j < D; ++j) dst[j] = y[j];
+      for (int j = 0; j < D; ++j) flow_output(a, row, j, D, y[j]);
       if (a.logdet) a.logdet[row] = ld;
     }
   }

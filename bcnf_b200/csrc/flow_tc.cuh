@@ -434,7 +434,7 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
       if (et < kTcRows) {
         const long long r = row0 + et;
         const bool valid = r < a.n_rows;
-        for (int j = 0; j < td.yp; ++j) y_s[et * td.yp + j] = (valid && j < D) ? __ldg(a.in + r * D + j) : 0.f;
+        for (int j = 0; j < td.yp; ++j) y_s[et * td.yp + j] = (valid && j < D) ? flow_input(a, r, j, D) : 0.f;
         ld_s[et] = 0.f;
         prow_s[et] = a.P + (valid ? row_instance(a, r) : 0) * (long long)sd.PW;
       }
@@ -577,7 +577,7 @@ flow_tc_kernel(const FlowArgs a, const StackDims sd, const TcDims td, const unsi
       if (et < kTcRows) {
         const long long r = row0 + et;
         if (r < a.n_rows) {
-          for (int j = 0; j < D; ++j) a.out[r * D + j] = y_s[et * td.yp + j];
+          for (int j = 0; j < D; ++j) flow_output(a, r, j, D, y_s[et * td.yp + j]);
           if (a.logdet) a.logdet[r] = ld_s[et];
         }
       }

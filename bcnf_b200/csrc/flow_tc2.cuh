@@ -458,7 +458,7 @@ flow_tc2_kernel(const FlowArgs a, const StackDims sd, const S2Dims d2, const uns
         const int e = et + kS2EpiThreads * u;
         if (e < kS2Rows * D) {
           const int r = e / D;
-          y_s[r * kS2YPitch + (e - r * D)] = e < lim ? __ldg(a.in + row_base * D + e) : 0.f;
+          y_s[r * kS2YPitch + (e - r * D)] = e < lim ? flow_input(a, row_base + r, e - r * D, D) : 0.f;
         }
       }
       if (part == 0) {
@@ -512,7 +512,7 @@ flow_tc2_kernel(const FlowArgs a, const StackDims sd, const S2Dims d2, const uns
 #pragma unroll
       for (int u = 0; u < kYPer; ++u) {
         const int e = et + kS2EpiThreads * u;
-        if (e < kS2Rows * D && e < lim) { const int r = e / D; a.out[row_base * D + e] = y_s[r * kS2YPitch + (e - r * D)]; }
+        if (e < kS2Rows * D && e < lim) { const int r = e / D; flow_output(a, row_base + r, e - r * D, D, y_s[r * kS2YPitch + (e - r * D)]); }
       }
       if (part == 0 && valid && a.logdet) a.logdet[row_g] = ld_acc;
     };

@@ -118,7 +118,7 @@ flow_tiled_kernel(const FlowArgs a, const StackDims sd, const TiledSmem lay) {
     for (int e = tid; e < R * lay.YP; e += kTiledThreads) {
       const int r = e / lay.YP, j = e - r * lay.YP;
       const long long row = row0 + r;
-      y_s[e] = (row < a.n_rows && j < D) ? __ldg(a.in + row * D + j) : 0.f;
+      y_s[e] = (row < a.n_rows && j < D) ? flow_input(a, row, j, D) : 0.f;
     }
     if (tid < R) {
       const long long row = row0 + tid;
@@ -199,7 +199,7 @@ flow_tiled_kernel(const FlowArgs a, const StackDims sd, const TiledSmem lay) {
     for (int e = tid; e < R * D; e += kTiledThreads) {
       const int r = e / D, j = e - r * D;
       const long long row = row0 + r;
-      if (row < a.n_rows) a.out[row * D + j] = y_s[r * lay.YP + j];
+      if (row < a.n_rows) flow_output(a, row, j, D, y_s[r * lay.YP + j]);
     }
     if (a.logdet && tid < R && row0 + tid < a.n_rows) a.logdet[row0 + tid] = ld_s[tid];
     __syncthreads();

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define BCNF_ABI_VERSION 1
+#define BCNF_ABI_VERSION 2
 #define BCNF_MAX_HIDDEN_LAYERS 8
 #define BCNF_MAX_SIZE 64         /* largest supported flow dimension D */
 #define BCNF_MAX_HIDDEN 1024     /* largest supported conditioner width */
@@ -136,6 +136,23 @@ int bcnf_flow_forward(bcnf_flow_t* flow, const float* y, const float* P, const i
  * receives the log|det| of the forward map at x (i.e. minus the inverse's own). */
 int bcnf_flow_inverse(bcnf_flow_t* flow, const float* z, const float* P, const int32_t* row2inst,
                       int64_t inst_period, int64_t n_rows, float* x, float* logdet, void* stream);
+
+/* Posterior sampling with the latent drawn INSIDE the kernel: x = inverse(sigma * z), z ~ N(0, 1) from Philox4x32-10
+ * keyed by `seed` at counter row * D + j -- a pure function of (seed, row, j), independent of tiling and launch.
+ * Replaces `sigma * torch.randn(...)` on the CPU generator plus the host-to-device copy of z in
+ * CondRealNVP_v2._sample (cnf.py:566, :578, :584) and the z read of bcnf_flow_inverse (no z array exists at all).
+ * The reference's own draw order is still available: pass its z to bcnf_flow_inverse. */
+int bcnf_flow_sample(bcnf_flow_t* flow, uint64_t seed, float sigma, const float* P, const int32_t* row2inst,
+                     int64_t inst_period, int64_t n_rows, float* x, float* logdet, void* stream);
+
+/* Calibration ranks fused behind the sampler (compute_y_hat_ranks, src/bcnf/eval/calibration.py:33-48):
+ *   ranks[i, j] += #{ rows r whose instance is i : x[r, j] < y[i, j] }
+ * with x the inverse pass as above; the (M, N, D) sample tensor the reference materialises, copies to the host and
+ * reduces there is never written.  z == NULL: drawn in the kernel (seed, sigma); else read (n_rows, D).
+ *   y: (n_inst, D)   ranks: int32 (n_inst, D), zeroed (or carrying earlier chunks' counts) by the caller. */
+int bcnf_flow_sample_ranks(bcnf_flow_t* flow, const float* z, uint64_t seed, float sigma, const float* P,
+                           const int32_t* row2inst, int64_t inst_period, int64_t n_rows, const float* y,
+                           int32_t* ranks, void* stream);
 
 /* ---- training primitives (Trainer._train_batch, src/bcnf/train/trainer.py:244-277) ------------------
  * The conditioner's Linear -> GELU -> Dropout chain (cnf.py:78-83) forward and backward as one strided

@@ -20,7 +20,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert declared == set(_cabi.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.bcnf_abi_version() == 1
+    assert lib.bcnf_abi_version() == 2
 
 
 def test_abi_validation_errors_without_gpu():
