@@ -230,6 +230,8 @@ class PackedFlow:
     def _check_map(self, P: torch.Tensor, n: int, row2inst: torch.Tensor | None, inst_period: int) -> int:
         """The ABI takes raw pointers: the row -> instance map is checked here, against the projection it indexes."""
         n_inst = P.shape[0]
+        if self.proj_width == 0:        # no conditioner network in this (sub-)stack: P is a placeholder nobody reads
+            return 0
         if P.ndim != 2 or P.shape[1] != max(self.proj_width, 1) or P.dtype != torch.float32 or not P.is_contiguous():
             raise ValueError(f"P must be a contiguous float32 (n_inst, {max(self.proj_width, 1)}) tensor, got "
                              f"{tuple(P.shape)} {P.dtype}")
@@ -720,8 +722,8 @@ class CondRealNVP_v2(ConditionalInvertibleLayer):
                 P = flow.project(h)
                 # z = sigma * N(0, 1) is drawn inside the kernel (Philox keyed by one seed per chunk, taken from the
                 # generator like a torch.randn call would advance it): no z tensor, no torch.randn launch
-                seed = int(torch.randint(0, 2 ** 62, (1,), generator=generator).item()) if generator is not None \
-                    else int(torch.randint(0, 2 ** 62, (1,)).item())
+                seed = int(torch.randint(0, 2 ** 62, (1,), generator=generator, device=generator.device).item()) \
+                    if generator is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
                 x = flow.sample(n_samples * nb, P, seed=seed, sigma=sigma, inst_period=nb)
                 out[:, b: b + nb].copy_(x.view(n_samples, nb, self.size), non_blocking=True)
         if out_dev.type == "cpu":
