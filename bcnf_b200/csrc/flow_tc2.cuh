@@ -82,7 +82,8 @@ struct S2Dims {
   int stg_off, misc_off, smem_bytes;
   long long cta_bytes;          // scratch bytes per CTA: 2 buffers x planes x a_plane
   int debug;                    // timing experiments only (results are wrong): 1 skip the GELU arithmetic, 2 skip the
-                                // activation stores, 4 skip the release of the output groups, 8 skip the TMEM loads
+                                // activation stores, 4 skip the release of the output groups, 8 skip the TMEM loads,
+                                // 16 keep dead activation lines in L2 (no discard)
 };
 
 // ---- waits with a watchdog: a protocol bug traps (the launch fails) instead of hanging the GPU --------------------
@@ -118,6 +119,12 @@ __device__ __forceinline__ void s2_wait(uint64_t* bar, uint32_t parity, unsigned
 // debug trace (FlowArgs::trace, block 0 only): role r writes stamp k of its event idx at trace[r * 8192 + idx * 4 + k]
 __device__ __forceinline__ void s2_stamp(long long* trace, int role, uint32_t idx, int k) {
   if (trace && blockIdx.x == 0 && idx < 2048u) trace[role * 8192 + idx * 4 + k] = clock64();
+}
+// The input image of a layer is dead once the layer's MMAs have completed: drop its (dirty) lines from L2 instead of
+// letting them be written back to HBM before the next-but-one layer overwrites them (ncu: 16.9 GB of DRAM writes per
+// 75 776 rows, 77 % of all activation bytes, before this).  One 128-byte line = one row of one image chunk.
+__device__ __forceinline__ void discard_line(const unsigned char* p) {
+  asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
 }
 __device__ __forceinline__ bool elect_one_sync() {
   uint32_t pred;
@@ -175,7 +182,7 @@ __device__ __forceinline__ void s2_gelu_pack8(const uint32_t* r, const float4& b
     if (NPASS == 3) {
       const f32x2 h = pack2(__uint_as_float(hi[O + i] << 16), __uint_as_float(hi[O + i] & 0xffff0000u));
       float l0, l1;
-      unpack2(add2(v[i], h ^ 0x8000000080000000ull), l0, l1);
+      unpack2(fma2(h, pack2(-1.0f, -1.0f), v[i]), l0, l1);      // v - hi in one packed FMA (no sign-flip LOP3s)
       lo[O + i] = pack_bf16x2(l0, l1);
     }
   }
@@ -643,6 +650,17 @@ flow_tc2_kernel(const FlowArgs a, const StackDims sd, const S2Dims d2, const uns
                 for (int u = 0; u < 4; ++u) b[u] = bn[u];
               }
             }
+            if (c == ly.n_chunks - 1 && part == 0 && !(d2.debug & 16)) {
+              // every MMA of this layer has completed (its last accumulator is what we have just drained): the input
+              // image is dead -- this thread drops its own row of every chunk of it (ordered before the next writes to
+              // these lines by the release below and the accumulator hand-off of the layer after next)
+              const unsigned char* ibuf = act_cta + (long long)(job & 1u) * buf_bytes + row * 128;
+              const int in_img = l == 0 ? 1 : tl.layer[l - 1].n_img;
+              for (int kc = 0; kc < in_img; ++kc) {
+                discard_line(ibuf + (long long)kc * kS2Tile);
+                if (NPASS == 3) discard_line(ibuf + d2.a_plane + (long long)kc * kS2Tile);
+              }
+            }
             // slot drained, group written: release the accumulator, make the group visible to the producer
             tc_fence_before();
             publish_group();
@@ -659,6 +677,13 @@ flow_tc2_kernel(const FlowArgs a, const StackDims sd, const S2Dims d2, const uns
           s2_wait<false>(&acc_full[slot], (nchunk >> 1) & 1u, dbg, 0x502u);
           tc_fence_after();
           if (et == 0) s2_stamp(a.trace, 1, nchunk, 1);
+          if (part == 0 && !(d2.debug & 16)) {          // the last Linear's input image is dead too
+            const unsigned char* ibuf = act_cta + (long long)(job & 1u) * buf_bytes + row * 128;
+            for (int kc = 0; kc < tl.layer[L - 1].n_img; ++kc) {
+              discard_line(ibuf + (long long)kc * kS2Tile);
+              if (NPASS == 3) discard_line(ibuf + d2.a_plane + (long long)kc * kS2Tile);
+            }
+          }
           if (part == 0) {
             uint32_t r0[16], r1[16];
             tmem_ld16_issue(lane_addr + slot * (uint32_t)kS2SlotCols, r0);
