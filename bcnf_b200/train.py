@@ -427,11 +427,26 @@ class _StackFn(torch.autograd.Function):
         n_zero += sum(params[u.w0 + spec.n_lin + j].numel() for u in units for j in range(spec.n_lin))
         zero_buf, zero_at = torch.zeros(n_zero, device=dev), 0
 
+        sink = _SINK if _SINK is not None and _SINK.active else None
+        direct = [False] * len(params)          # gradient written straight into the parameter's .grad view: autograd gets None
+
         def zeros_like(t):
             nonlocal zero_at
+            v = sink.view(t) if sink is not None else None      # (the sink's buffer was zeroed when the step began)
+            if v is not None:
+                return v
             v = zero_buf[zero_at: zero_at + t.numel()].view(t.shape)
             zero_at += t.numel()
             return v
+
+        def empty_like(t):
+            v = sink.view(t) if sink is not None else None
+            return v if v is not None else torch.empty_like(t)
+
+        if sink is not None:
+            for i, t in enumerate(params):
+                direct[i] = sink.view(t) is not None
+            buckets = {u0: (lo, hi) for u0, lo, hi in sink.bucket_bounds(units, params)}
 
         for ops in [lead] + [u.ops for u in units]:
             for typ, po in ops:
@@ -453,7 +468,7 @@ class _StackFn(torch.autograd.Function):
             no = 2 * u.dout
             d_pre = [new(B, _pitch(n)) for n in widths]
             d_o, dz_new = new(B, no), new(B, D)
-            dws = [torch.empty_like(w) for w in ws]
+            dws = [empty_like(w) for w in ws]
             dbs = [zeros_like(params[u.w0 + spec.n_lin + j]) for j in range(spec.n_lin)]
             a = _cabi.TrainPostBwdArgs()
             a.dz_in, a.dz_out, a.dld = dz.data_ptr(), dz_new.data_ptr(), dld.data_ptr()
@@ -512,6 +527,9 @@ class _StackFn(torch.autograd.Function):
                 grads[u.w0 + spec.n_lin + j] = dbs[j]
             keep += [d_pre, d_o, dz]
             dz = dz_new
+            if sink is not None and ui in buckets and ui != 0:
+                # every gradient of units >= ui is enqueued: all-reduce their range underneath the rest of the backward
+                sink.reduce_range(*buckets[ui], [main] + list(sides))
         if lead:
             dz_new = new(B, D)
             a = _cabi.TrainPostBwdArgs()
@@ -522,9 +540,96 @@ class _StackFn(torch.autograd.Function):
             dz = dz_new
         for sd in sides:
             main.wait_stream(sd)
+        if sink is not None:
+            sink.reduce_range(*buckets[0], [main])          # the first bucket (incl. the leading ActNorm) closes the backward
         del keep
-        out_params = [g if needs[3 + i] else None for i, g in enumerate(grads)]
+        out_params = [g if needs[3 + i] and not direct[i] else None for i, g in enumerate(grads)]
         return (None, dz if needs[1] else None, dh if needs[2] and not first_dh else None, *out_params)
+
+
+
+# ------------------------------------------------------------------------------------------
+# gradient sink: parameter gradients as views of ONE flat buffer, all-reduced bucket by bucket during the backward
+# ------------------------------------------------------------------------------------------
+class _GradSink:
+    """Data-parallel gradient plumbing of the stack (48.8 M fp32 = 195 MB per step).
+
+    Every stack parameter's ``.grad`` is a view of one flat buffer.  While the sink is active the stack's backward
+    writes each gradient straight into its view (and hands autograd ``None`` for it): no per-parameter AccumulateGrad
+    nodes, no gather into / scatter out of a communication buffer.  The flat buffer is cut into ``n_buckets``
+    contiguous ranges of coupling layers; the backward walks the layers from last to first, so a range is complete
+    while earlier layers are still back-propagating, and its NCCL all-reduce runs on a side stream underneath them
+    (captured with the rest of the step when the Trainer replays a CUDA graph).  The loss is pre-scaled by 1 / world,
+    so the SUM all-reduce yields the mean without another pass over the buffer.
+    """
+
+    def __init__(self, params: list[torch.Tensor], process_group: Any, n_buckets: int = 4) -> None:
+        self.group = process_group
+        self.n_buckets = n_buckets
+        self.params = [t for t in params if t.requires_grad]
+        dev = self.params[0].device
+        offs, at = {}, 0
+        for t in self.params:
+            offs[id(t)] = at
+            at += (t.numel() + 63) // 64 * 64              # 256-byte aligned views (vector stores of the GEMM epilogues)
+        self.offs, self.total = offs, at
+        self.flat = torch.zeros(at, device=dev)
+        for t in self.params:
+            t.grad = self.view(t)
+        self.comm = torch.cuda.Stream(device=dev)
+        self.active = False
+        self._pending = False
+
+    def view(self, t: torch.Tensor) -> torch.Tensor | None:
+        o = self.offs.get(id(t))
+        return None if o is None else self.flat[o: o + t.numel()].view(t.shape)
+
+    def begin(self) -> None:
+        self.flat.zero_()                                   # bias / ActNorm gradients are accumulated with atomics
+        self.active, self._pending = True, False
+
+    def bucket_bounds(self, units: list[Any], params: list[torch.Tensor]) -> list[tuple[int, int, int]]:
+        """(first unit, element lo, element hi) of each bucket; a bucket is complete when its first unit is done."""
+        n = len(units)
+        nb = max(1, min(self.n_buckets, n))
+        firsts = sorted({(b * n) // nb for b in range(nb)})
+        starts = [0 if u == 0 else self.offs[id(params[units[u].w0])] for u in firsts]
+        ends = starts[1:] + [self.total]
+        return [(u, lo, hi) for u, lo, hi in zip(firsts, starts, ends)]
+
+    def reduce_range(self, lo: int, hi: int, streams: list[torch.cuda.Stream]) -> None:
+        """All-reduce flat[lo:hi] on the communication stream once everything enqueued so far on `streams` is done."""
+        if self.group is None or hi <= lo:
+            return
+        import torch.distributed as dist
+        for st in streams:
+            self.comm.wait_stream(st)
+        with torch.cuda.stream(self.comm):
+            dist.all_reduce(self.flat[lo:hi], group=self.group)
+        self._pending = True
+
+    def end(self, main: torch.cuda.Stream) -> None:
+        if self._pending:
+            main.wait_stream(self.comm)
+        self.active, self._pending = False, False
+
+
+_SINK: _GradSink | None = None      # set by Trainer for the duration of its backward
+
+def stack_parameters(model: Any) -> list[torch.Tensor]:
+    """The parameters of ``model.layers`` in the order stack_forward_train hands them to the autograd function."""
+    from .cnf import ActNorm, ConditionalAffineCouplingLayer, OrthonormalTransformation
+    out: list[torch.Tensor] = []
+    for layer in getattr(model, "layers", []):
+        if isinstance(layer, ActNorm):
+            out += [layer.scale, layer.bias]
+        elif isinstance(layer, OrthonormalTransformation):
+            out.append(layer.orthonormal_matrix)
+        elif isinstance(layer, ConditionalAffineCouplingLayer):
+            for net in ([layer.nn_a, layer.nn_b] if layer.two_way else [layer.nn_a]):
+                lin = net.linears()
+                out += [m.weight for m in lin] + [m.bias for m in lin]
+    return out
 
 
 def stack_forward_train(model: Any, y: torch.Tensor, h: torch.Tensor, seed: int | None = None,
@@ -598,6 +703,8 @@ class Trainer:
         self.cuda_graph = cuda_graph
         self.process_group = process_group
         self._graphs: dict[tuple, dict[str, Any]] = {}      # one captured step per batch shape
+        self._sink: _GradSink | None = None
+        self._other: list[torch.Tensor] = []
         if cuda_graph:
             if hasattr(model, "module"):
                 raise NotImplementedError("cuda_graph=True with a DistributedDataParallel wrapper is not supported: pass the "
@@ -609,6 +716,14 @@ class Trainer:
             if hasattr(model, "module"):
                 raise ValueError("process_group= replaces the DistributedDataParallel wrapper: pass the bare model")
             self._world = dist.get_world_size(process_group)
+            # the stack's gradients live in one flat buffer and are all-reduced bucket by bucket during the backward
+            # (CUDA models with a coupling stack; anything else -- the gloo tests of this plumbing -- takes the generic
+            # one-buffer path of _allreduce_grads after the backward)
+            sp = [t for t in stack_parameters(model) if t.requires_grad and t.is_cuda]
+            if sp:
+                self._sink = _GradSink(sp, process_group)
+                sunk = {id(t) for t in self._sink.params}
+                self._other = [t for t in model.parameters() if t.requires_grad and id(t) not in sunk]
             with torch.no_grad():
                 src = dist.get_global_rank(process_group, 0)
                 for t in list(model.parameters()) + list(model.buffers()):
@@ -650,6 +765,49 @@ class Trainer:
 
     def _net(self) -> Any:
         return self.model.module if hasattr(self.model, "module") else self.model
+
+    def _zero_grad(self) -> None:
+        if self._sink is None:
+            self.optimizer.zero_grad(set_to_none=True)
+            return
+        for t in self._other:                    # the stack's .grad views stay: the sink zeroes their buffer in one fill
+            t.grad = None
+
+    def _backward(self, loss: torch.Tensor) -> None:
+        """loss.backward(), with the stack's gradients written into the sink and all-reduced underneath the backward."""
+        global _SINK
+        if self._sink is None:
+            loss.backward()
+            if self.process_group is not None:
+                self._allreduce_grads()
+            return
+        dev = self._sink.flat.device
+        self._sink.begin()
+        _SINK = self._sink
+        try:
+            (loss / self._world).backward()       # SUM all-reduce of pre-scaled gradients = their mean
+        finally:
+            _SINK = None
+        self._sink.end(torch.cuda.current_stream(dev))
+        if self._world > 1:
+            self._allreduce_other()
+
+    def _allreduce_other(self) -> None:
+        import torch.distributed as dist
+        grads = [p.grad for p in self._other if p.grad is not None]
+        if not grads:
+            return
+        n = sum(g.numel() for g in grads)
+        flat = getattr(self, "_flat", None)
+        if flat is None or flat.numel() != n:
+            flat = self._flat = torch.empty(n, device=grads[0].device)
+        views, at = [], 0
+        for g in grads:
+            views.append(flat[at: at + g.numel()].view(g.shape))
+            at += g.numel()
+        torch._foreach_copy_(views, grads)
+        dist.all_reduce(flat, group=self.process_group)      # (already scaled by 1 / world through the loss)
+        torch._foreach_copy_(grads, views)
 
     def _losses(self, y: torch.Tensor, *conditions: torch.Tensor):
         net = self._net()
@@ -701,11 +859,9 @@ class Trainer:
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
                 for _ in range(3):
-                    self.optimizer.zero_grad(set_to_none=True)
+                    self._zero_grad()
                     loss, _, _, _ = self._losses(st["y"], *st["c"])
-                    loss.backward()
-                    if self.process_group is not None:
-                        self._allreduce_grads()
+                    self._backward(loss)
                     self.optimizer.step()
                     seed_word.add_(1)
                 with torch.no_grad():
@@ -718,14 +874,12 @@ class Trainer:
                     seed_word.copy_(snap_w)
             torch.cuda.current_stream(dev).wait_stream(side)
             graph = torch.cuda.CUDAGraph()
-            self.optimizer.zero_grad(set_to_none=True)
+            self._zero_grad()
             # NCCL's watchdog thread polls events while the capture is open: keep the capture check thread-local
             mode = {"capture_error_mode": "thread_local"} if self.process_group is not None else {}
             with torch.cuda.graph(graph, **mode):
                 loss, nll, mse, _ = self._losses(st["y"], *st["c"])
-                loss.backward()
-                if self.process_group is not None:
-                    self._allreduce_grads()
+                self._backward(loss)
                 self.optimizer.step()
                 seed_word.add_(1)                       # fresh dropout masks on every replay
             st.update(loss=loss, nll=nll, mse=mse, graph=graph)
@@ -740,11 +894,9 @@ class Trainer:
         if self.cuda_graph:
             loss, nll, mse = self._graphed_step(y, *conditions)
             return loss.item(), nll.item(), mse.item()
-        self.optimizer.zero_grad()
+        self._zero_grad() if self._sink is not None else self.optimizer.zero_grad()
         loss, nll, mse, _ = self._losses(y, *conditions)
-        loss.backward()
-        if self.process_group is not None:
-            self._allreduce_grads()
+        self._backward(loss)
         self.optimizer.step()
         torch.nn.utils.clip_grad_norm_(self._net().parameters(), max_norm=1.0)
         return loss.item(), nll.item(), mse.item()

@@ -326,3 +326,76 @@ def test_operand_image_layout_is_bit_exact(rows, k):
     im2 = train._Img(dev, rows, k)
     train._pack_images([(xt, 0, 1, rows, rows, k, im2)], dev)
     assert np.array_equal(im2.buf.cpu().numpy(), ref)
+
+
+def test_gradient_sink_matches_plain_backward_and_graphs_per_shape():
+    """Trainer(process_group=...): the stack's gradients are written into views of one flat buffer and all-reduced in
+    buckets during the backward (single-rank NCCL group here: the reduction is the identity).  They must equal the
+    gradients of the plain autograd path bit for bit (dropout off), feature-network parameters included; the captured
+    step keeps one graph per batch shape and a warm-up that does not train."""
+    import torch.distributed as dist
+    import os, socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device(DEV))
+    try:
+        torch.manual_seed(0)
+        fc = bcnf_b200.FullyConnectedFeatureNetwork(sizes=[12, 24, 8], dropout=0.0)
+        def make():
+            torch.manual_seed(3)
+            m = CondRealNVP_v2(size=19, nested_sizes=[64, 64], n_blocks=9, n_conditions=8,
+                               feature_networks=[bcnf_b200.ConcatenateCondition(None, 12),
+                                                 bcnf_b200.FullyConnectedFeatureNetwork(sizes=[12, 24, 8], dropout=0.0)],
+                               dropout=0.0, act_norm=True)
+            return m.to(DEV).train()
+        a, b = make(), make()
+        g = torch.Generator().manual_seed(4)
+        y, c = torch.randn(96, 19, generator=g), torch.randn(96, 12, generator=g)
+        # plain autograd
+        ta = bcnf_b200.Trainer(a, torch.optim.SGD(a.parameters(), lr=0.0))
+        loss_a, _, _, _ = ta._losses(y, c)
+        loss_a.backward()
+        # through the sink
+        tb = bcnf_b200.Trainer(b, torch.optim.SGD(b.parameters(), lr=0.0), process_group=dist.group.WORLD)
+        assert tb._sink is not None and len(tb._other) == 4            # two Linear layers of the feature network
+        tb._zero_grad()
+        loss_b, _, _, _ = tb._losses(y, c)
+        tb._backward(loss_b)
+        torch.cuda.synchronize()
+        assert torch.equal(loss_a, loss_b)
+        for (n, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+            if pa.grad is None:
+                assert pb.grad is None or float(pb.grad.abs().max()) == 0.0, n
+                continue
+            assert torch.equal(pa.grad, pb.grad), n
+        flat = tb._sink.flat
+        assert all(p.grad.data_ptr() >= flat.data_ptr() and p.grad.data_ptr() < flat.data_ptr() + 4 * flat.numel()
+                   for p in tb._sink.params)                               # .grad really is a view of the flat buffer
+        assert len(tb._sink.bucket_bounds(*_units_of(b))) == 4
+        # captured steps: one graph per shape, warm-up leaves parameters and Adam state untouched
+        m = make()
+        opt = torch.optim.Adam(m.parameters(), lr=1e-3, capturable=True)
+        tr = bcnf_b200.Trainer(m, opt, cuda_graph=True, process_group=dist.group.WORLD)
+        before = [p.detach().clone() for p in m.parameters()]
+        tr.train_batch(y, c)                                               # capture (3 warm-up iterations) + ONE replay
+        steps = {int(st["step"].item()) for st in opt.state.values() if "step" in st}
+        assert steps == {1}
+        tr.train_batch(y[:40], c[:40])                                     # a second shape: its own graph
+        tr.train_batch(y, c)
+        assert len(tr._graphs) == 2
+        assert {int(st["step"].item()) for st in opt.state.values() if "step" in st} == {3}
+        assert any(not torch.equal(p, q) for p, q in zip(m.parameters(), before))
+        tr.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def _units_of(model):
+    from bcnf_b200.train import _Spec, _plan, stack_parameters
+    kinds = []
+    for layer in model.layers:
+        kinds.append("actnorm" if isinstance(layer, bcnf_b200.ActNorm) else
+                     "ortho" if isinstance(layer, bcnf_b200.OrthonormalTransformation) else "coupling")
+    spec = _Spec(kinds, len(model.nested_sizes) + 1, model.two_way, model.size, model.n_conditions, 0.0, 0, None)
+    return _plan(spec)[1], stack_parameters(model)
