@@ -855,15 +855,29 @@ class Trainer:
             snap_o = {id(t): t.detach().clone() for stt in self.optimizer.state.values() for t in stt.values()
                       if torch.is_tensor(t)}
             snap_w = seed_word.clone()
-            side = torch.cuda.Stream(device=dev)
+            # Warm-up and capture run on ONE stream: autograd's AccumulateGrad nodes remember the stream they were created
+            # on, they outlive the warm-up (model.log_det_J keeps its graph alive), and a captured backward that has to
+            # synchronise with a different, uncaptured stream fails with cudaErrorStreamCaptureIsolation.
+            side = getattr(self, "_cap_stream", None)
+            if side is None:
+                side = self._cap_stream = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
-                for _ in range(3):
+                def warm_step():
+                    # (a function of its own: nothing of the warm-up's autograd graph -- loss, nll, mse, z -- may outlive
+                    # it.  The parameters' AccumulateGrad nodes remember the stream they were created on, and nodes
+                    # kept alive by such a reference would make the captured backward synchronise with this
+                    # (uncaptured) warm-up stream: cudaErrorStreamCaptureIsolation when no defined gradient reaches
+                    # them, which is the case for every stack parameter behind the sink.)
                     self._zero_grad()
-                    loss, _, _, _ = self._losses(st["y"], *st["c"])
+                    loss = self._losses(st["y"], *st["c"])[0]
                     self._backward(loss)
                     self.optimizer.step()
                     seed_word.add_(1)
+                for _ in range(3):
+                    warm_step()
+                import gc
+                gc.collect()
                 with torch.no_grad():
                     for p, q in zip(params, snap_p):
                         p.copy_(q)
@@ -877,7 +891,7 @@ class Trainer:
             self._zero_grad()
             # NCCL's watchdog thread polls events while the capture is open: keep the capture check thread-local
             mode = {"capture_error_mode": "thread_local"} if self.process_group is not None else {}
-            with torch.cuda.graph(graph, **mode):
+            with torch.cuda.graph(graph, stream=side, **mode):
                 loss, nll, mse, _ = self._losses(st["y"], *st["c"])
                 self._backward(loss)
                 self.optimizer.step()

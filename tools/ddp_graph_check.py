@@ -12,7 +12,8 @@ dev = torch.device("cuda", local)
 torch.cuda.set_device(dev)
 dist.init_process_group("nccl", device_id=dev)
 torch.manual_seed(rank)          # different initial weights per rank: the trainer must broadcast rank 0's
-model = bcnf_b200.CondRealNVP_v2(size=19, nested_sizes=[64, 64], n_blocks=3, n_conditions=32,
+n_blocks = int(os.environ.get("BCNF_CHECK_BLOCKS", "3"))
+model = bcnf_b200.CondRealNVP_v2(size=19, nested_sizes=[64, 64], n_blocks=n_blocks, n_conditions=32,
                                  feature_networks=[bcnf_b200.ConcatenateCondition(None, 32)], dropout=0.1, act_norm=True).to(dev).train()
 opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True, fused=True)
 tr = bcnf_b200.Trainer(model, opt, cuda_graph=True, process_group=dist.group.WORLD)
