@@ -7,6 +7,7 @@ from .feature_network import (ConcatenateCondition, FeatureNetwork, FeatureNetwo
                               FrExpFeatureNetwork, FullyConnectedFeatureNetwork, LSTMFeatureNetwork,
                               Transformer)
 from .calibration import compute_CDF_residuals, compute_y_hat_ranks  # noqa: F401
+from .resimulation import physics_ODE_simulation_batch, resimulate  # noqa: F401
 from .train import Trainer  # noqa: F401
 from .utils import ParameterIndexMapping, inn_nll_loss, load_config  # noqa: F401
 

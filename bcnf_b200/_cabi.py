@@ -24,7 +24,7 @@ KERNEL_NAMES = {0: "rowthread", 1: "tiled", 2: "tcgen05"}
 
 EXPORTS = ["bcnf_abi_version", "bcnf_last_error", "bcnf_flow_create", "bcnf_flow_destroy",
            "bcnf_flow_info", "bcnf_flow_debug_words", "bcnf_flow_set_params", "bcnf_cond_project", "bcnf_flow_forward",
-           "bcnf_flow_inverse", "bcnf_flow_sample", "bcnf_flow_sample_ranks", "bcnf_train_gemm", "bcnf_train_colsum", "bcnf_train_dropout_mask",
+           "bcnf_flow_inverse", "bcnf_flow_sample", "bcnf_flow_sample_ranks", "bcnf_resimulate", "bcnf_train_gemm", "bcnf_train_colsum", "bcnf_train_dropout_mask",
            "bcnf_train_set_gemm_mode", "bcnf_train_gemm_trace", "bcnf_train_pre", "bcnf_train_post",
            "bcnf_train_post_bwd", "bcnf_train_pre_bwd", "bcnf_img_pack", "bcnf_gemm_img", "bcnf_gemm_img_gelu", "bcnf_gemm_img_set_trace", "bcnf_lstm_step"]
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU_DROP, EPI_DGELU_DROP = 0, 1, 2, 3
@@ -160,6 +160,8 @@ def lib() -> C.CDLL:
                  C.c_void_p, C.c_void_p]
     L.bcnf_flow_forward.argtypes = flow_args
     L.bcnf_flow_inverse.argtypes = flow_args
+    L.bcnf_resimulate.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_int32, C.c_int32, C.c_void_p,
+                                  C.c_int32, C.c_void_p]
     L.bcnf_flow_sample.argtypes = [C.c_void_p, C.c_uint64, C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                    C.c_void_p, C.c_void_p, C.c_void_p]
     L.bcnf_flow_sample_ranks.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_float, C.c_void_p, C.c_void_p, C.c_int64,

@@ -20,6 +20,7 @@
 #include "train_glue.cuh"
 #include "gemm_img2.cuh"
 #include "flow_tc2.cuh"
+#include "resim.cuh"
 
 using namespace bcnf;
 
@@ -1289,6 +1290,21 @@ extern "C" int bcnf_flow_sample_ranks(bcnf_flow_t* f, const float* z, uint64_t s
   FlowExtra ex;
   ex.draw = z == nullptr; ex.seed = seed; ex.sigma = sigma; ex.rank_y = y; ex.rank_out = ranks;
   return run_flow(f, 1, z, P, row2inst, inst_period, n_rows, nullptr, nullptr, stream, ex);
+}
+
+// Re-simulation of n parameter sets (bcnf_b200.h; reference src/bcnf/simulation/physics.py:53-165).
+extern "C" int bcnf_resimulate(const double* params, int64_t n, int32_t n_steps, double dt, int32_t substeps,
+                               int32_t break_on_impact, double* x_out, int32_t device, void* stream) {
+  if (n < 0 || n_steps < 1 || substeps < 1 || !(dt > 0.0)) return fail(BCNF_E_ARG, "bcnf_resimulate: bad size");
+  if (n == 0) return BCNF_OK;
+  if (!params || !x_out) return fail(BCNF_E_ARG, "bcnf_resimulate: null argument");
+  DEVICE_GUARD(device);
+  const int threads = 128;
+  const long long blocks = (n + threads - 1) / threads;
+  if (blocks > 0x7fffffffLL) return fail(BCNF_E_UNSUPPORTED, "bcnf_resimulate: too many trajectories for one launch");
+  resim_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(params, n, n_steps, dt, substeps, break_on_impact, x_out);
+  CUDA_TRY(cudaGetLastError());
+  return BCNF_OK;
 }
 
 extern "C" int bcnf_flow_forward(bcnf_flow_t* f, const float* y, const float* P, const int32_t* row2inst,

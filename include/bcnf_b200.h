@@ -154,6 +154,16 @@ int bcnf_flow_sample_ranks(bcnf_flow_t* flow, const float* z, uint64_t seed, flo
                            const int32_t* row2inst, int64_t inst_period, int64_t n_rows, const float* y,
                            int32_t* ranks, void* stream);
 
+/* Re-simulation of sampled parameter sets: physics_ODE_simulation
+ * (src/bcnf/simulation/physics.py:53-165) for n parameter rows at once, one thread per trajectory, instead of one
+ * scipy.integrate.odeint call per trajectory in a process pool (resimulation.py:21-59).
+ *   params: (n, 19) fp64, columns in the keyword order of physics_ODE_simulation:
+ *           x0_x x0_y x0_z v0_x v0_y v0_z g_x g_y g_z w_x w_y w_z b m rho r a_x a_y a_z
+ *   x_out:  (n, n_steps, 3) fp64, n_steps = len(np.arange(0, T, dt)); x_out[:, 0] = x0
+ *   substeps: RK4 steps per output interval (16 leaves < 1e-9 of scale vs the reference's LSODA at 1.49e-8). */
+int bcnf_resimulate(const double* params, int64_t n, int32_t n_steps, double dt, int32_t substeps,
+                    int32_t break_on_impact, double* x_out, int32_t device, void* stream);
+
 /* ---- training primitives (Trainer._train_batch, src/bcnf/train/trainer.py:244-277) ------------------
  * The conditioner's Linear -> GELU -> Dropout chain (cnf.py:78-83) forward and backward as one strided
  * SGEMM with fused epilogues; parameters and gradients stay in the reference's (out, in) layout. */
