@@ -146,6 +146,7 @@ struct bcnf_flow {
   // second-generation fused kernel (flow_tc2.cuh): weight images of every Linear of every conditioner network, the
   // per-direction table of their offsets, and one activation scratch per stream that has run the kernel
   // switches read from the environment ONCE, at create (tests / A-B timing / debugging; never on the launch path)
+  int env_rowthread_r = 0;                    // BCNF_ROWTHREAD_R: rows per thread of the row-per-thread kernel (1 or 2)
   bool env_proj_fma = false;                  // BCNF_PROJ_FMA=1: fp32 FMA projection kernel on a tensor-core handle
   int env_tc2_debug = 0;                      // BCNF_TC2_DEBUG: timing experiments of flow_tc2 (wrong results)
   std::string env_tc2_trace, env_tc_trace;    // BCNF_TC2_TRACE / BCNF_TC_TRACE: file that receives a pipeline trace
@@ -547,7 +548,9 @@ extern "C" int bcnf_flow_create(const bcnf_flow_desc_t* desc, const int32_t* op_
     if (f->s2_use) f->rows_per_cta = kS2Rows;
   } else if (rowthread_ok) {
     f->kernel = BCNF_KERNEL_ROWTHREAD;
-    f->rows_per_cta = kRowThreadBlock;
+    if (const char* e = getenv("BCNF_ROWTHREAD_R")) f->env_rowthread_r = atoi(e) == 1 ? 1 : (atoi(e) == 2 ? 2 : 0);
+    const int R = f->env_rowthread_r > 0 ? f->env_rowthread_r : (hp0 == 16 ? 2 : 1);
+    f->rows_per_cta = R * kRowThreadBlock;
   } else {
     f->kernel = BCNF_KERNEL_TILED;
     int hpmax = 0;
@@ -1090,18 +1093,18 @@ extern "C" int bcnf_cond_project(bcnf_flow_t* f, const float* h, int64_t n_inst,
   return BCNF_OK;
 }
 
-template <int D, int HP>
+template <int D, int HP, int R>
 static int launch_rowthread(bcnf_flow* f, const FlowArgs& a, int dir, cudaStream_t stream) {
   const Program& p = f->prog[dir];
   const int cap = round_up(std::max(f->prog[0].max_chunk_bytes, f->prog[1].max_chunk_bytes), 128);
   const size_t smem = 2 * (size_t)cap + 16;
-  auto kern = flow_rowthread_kernel<D, HP>;
+  auto kern = flow_rowthread_kernel<D, HP, R>;
   static size_t configured[64] = {};
   if (int rc = opt_in_smem_once(kern, smem, configured)) return rc;
   int occ = 0;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kRowThreadBlock, smem));
   if (occ < 1) return fail(BCNF_E_UNSUPPORTED, "row-per-thread kernel does not fit on an SM");
-  const long long tiles = (a.n_rows + kRowThreadBlock - 1) / kRowThreadBlock;
+  const long long tiles = (a.n_rows + R * kRowThreadBlock - 1) / (R * kRowThreadBlock);
   const int grid = (int)std::min<long long>(tiles, (long long)f->num_sms * occ);
   (void)p;
   kern<<<grid, kRowThreadBlock, smem, stream>>>(a, f->sd, cap);
@@ -1262,10 +1265,12 @@ static int run_flow(bcnf_flow_t* f, int dir, const float* in, const float* P, co
   }
   if (f->kernel == BCNF_KERNEL_ROWTHREAD) {
     const int hp = f->sd.half[0].hp[0];
-    if (f->sd.D == 19 && hp == 16) return launch_rowthread<19, 16>(f, a, dir, stream);
-    if (f->sd.D == 19 && hp == 32) return launch_rowthread<19, 32>(f, a, dir, stream);
-    if (f->sd.D == 21 && hp == 16) return launch_rowthread<21, 16>(f, a, dir, stream);
-    if (f->sd.D == 21 && hp == 32) return launch_rowthread<21, 32>(f, a, dir, stream);
+    // rows per thread: 2 where the registers allow it (width 16), 1 for width 32; BCNF_ROWTHREAD_R (read at create) overrides
+    const int R = f->env_rowthread_r > 0 ? f->env_rowthread_r : (hp == 16 ? 2 : 1);
+    if (f->sd.D == 19 && hp == 16) return R == 2 ? launch_rowthread<19, 16, 2>(f, a, dir, stream) : launch_rowthread<19, 16, 1>(f, a, dir, stream);
+    if (f->sd.D == 19 && hp == 32) return R == 2 ? launch_rowthread<19, 32, 2>(f, a, dir, stream) : launch_rowthread<19, 32, 1>(f, a, dir, stream);
+    if (f->sd.D == 21 && hp == 16) return R == 2 ? launch_rowthread<21, 16, 2>(f, a, dir, stream) : launch_rowthread<21, 16, 1>(f, a, dir, stream);
+    if (f->sd.D == 21 && hp == 32) return R == 2 ? launch_rowthread<21, 32, 2>(f, a, dir, stream) : launch_rowthread<21, 32, 1>(f, a, dir, stream);
     return fail(BCNF_E_STATE, "internal: no row-per-thread instance for D=%d HP=%d", f->sd.D, hp);
   }
   if (f->tiled_R == 32) return launch_tiled<32>(f, a, stream);

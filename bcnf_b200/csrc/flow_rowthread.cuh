@@ -92,7 +92,118 @@ __device__ __forceinline__ void axpy_row2(f32x2 (&acc)[N / 2], float x, uint32_t
   }
 }
 
-// One conditioner network + affine update of the other half (cnf.py:98-107, :178-190, :203-204).
+// R rows per thread: every weight load (a warp-wide broadcast from shared memory) feeds R packed FMAs per pair of
+// columns instead of one -- the first version of this kernel was issue-bound on those loads (ncu r01: FMA pipe 53 %,
+// issue 70 %, LSU 35 %; one LDS.128 per two FFMA2).
+template <int N, int R>
+__device__ __forceinline__ void axpy_rows2(f32x2 (&acc)[R][N / 2], const float (&x)[R], uint32_t w) {
+  f32x2 xx[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) xx[r] = pack2(x[r], x[r]);
+#pragma unroll
+  for (int j = 0; j < N; j += 4) {
+    f32x2 w01, w23;
+    lds2x2(w + 4 * j, w01, w23);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      acc[r][j / 2] = fma2(xx[r], w01, acc[r][j / 2]);
+      acc[r][j / 2 + 1] = fma2(xx[r], w23, acc[r][j / 2 + 1]);
+    }
+  }
+}
+
+// One conditioner network + affine update of the other half (cnf.py:98-107, :178-190, :203-204), R rows at once.
+template <int D, int HP, int SRC, int R>
+__device__ __forceinline__ void half_coupling_rows(float (&y)[R][D], float (&ld)[R], uint32_t w, const HalfLayout& hl,
+                                                   const float* const (&prow)[R], int proj_off, int inverse) {
+  constexpr int DA = (D + 1) / 2, DB = D / 2;
+  constexpr int DIN = SRC == 0 ? DA : DB;
+  constexpr int DOUT = SRC == 0 ? DB : DA;
+  constexpr int IN0 = SRC == 0 ? 0 : DA;
+  constexpr int OUT0 = SRC == 0 ? DA : 0;
+  constexpr int DOP = (DOUT + 3) / 4 * 4;
+
+  f32x2 acc[R][HP / 2];
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int j = 0; j < HP; j += 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(prow[r] + proj_off + j));
+      acc[r][j / 2] = pack2(v.x, v.y);
+      acc[r][j / 2 + 1] = pack2(v.z, v.w);
+    }
+  {
+    const uint32_t w1 = w + 4u * hl.off_w[0];
+#pragma unroll
+    for (int i = 0; i < DIN; ++i) {
+      float x[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) x[r] = y[r][IN0 + i];
+      axpy_rows2<HP, R>(acc, x, w1 + 4u * (i * HP));
+    }
+  }
+  const int L = hl.L;
+  for (int l = 1;; ++l) {
+    float hcur[R][HP];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int j = 0; j < HP; j += 2) unpack2(gelu_erf_fast2(acc[r][j / 2]), hcur[r][j], hcur[r][j + 1]);
+    if (l >= L) {
+      f32x2 ts2[R][DOP];
+      const uint32_t wo = w + 4u * hl.off_wout;
+      const uint32_t bo = w + 4u * hl.off_bout;
+#pragma unroll
+      for (int j = 0; j < 2 * DOP; j += 4) {
+        f32x2 b01, b23;
+        lds2x2(bo + 4 * j, b01, b23);
+#pragma unroll
+        for (int r = 0; r < R; ++r) { ts2[r][j / 2] = b01; ts2[r][j / 2 + 1] = b23; }
+      }
+#pragma unroll
+      for (int k = 0; k < HP; ++k) {
+        float x[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) x[r] = hcur[r][k];
+        axpy_rows2<2 * DOP, R>(ts2, x, wo + 4u * (k * (2 * DOP)));
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        float ts[2 * DOP];
+#pragma unroll
+        for (int j = 0; j < 2 * DOP; j += 2) unpack2(ts2[r][j / 2], ts[j], ts[j + 1]);
+        float ls_sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < DOUT; ++j) {
+          float ls = tanhf(ts[DOP + j]);                                       // cnf.py:107
+          ls_sum += ls;
+          if (!inverse) y[r][OUT0 + j] = fmaf(expf(ls), y[r][OUT0 + j], ts[j]);   // cnf.py:179
+          else          y[r][OUT0 + j] = (y[r][OUT0 + j] - ts[j]) * expf(-ls);    // cnf.py:204
+        }
+        ld[r] += ls_sum;                                                       // cnf.py:190, :488
+      }
+      return;
+    }
+    const uint32_t wl = w + 4u * hl.off_w[l];
+    const uint32_t bl = w + 4u * hl.off_b[l];
+#pragma unroll
+    for (int j = 0; j < HP; j += 4) {
+      f32x2 b01, b23;
+      lds2x2(bl + 4 * j, b01, b23);
+#pragma unroll
+      for (int r = 0; r < R; ++r) { acc[r][j / 2] = b01; acc[r][j / 2 + 1] = b23; }
+    }
+#pragma unroll
+    for (int k = 0; k < HP; ++k) {
+      float x[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) x[r] = hcur[r][k];
+      axpy_rows2<HP, R>(acc, x, wl + 4u * (k * HP));
+    }
+  }
+}
+
+// (single-row form kept for reference / A-B timing: BCNF_ROWTHREAD_R=1)
 template <int D, int HP, int SRC>
 __device__ __forceinline__ void half_coupling(float (&y)[D], float& ld, uint32_t w,
                                               const HalfLayout& hl, const float* __restrict__ prow,
@@ -157,17 +268,18 @@ __device__ __forceinline__ void half_coupling(float (&y)[D], float& ld, uint32_t
 
 constexpr int kRowThreadBlock = 128;
 
-template <int D, int HP>
+template <int D, int HP, int R>
 __global__ void __launch_bounds__(kRowThreadBlock)
 flow_rowthread_kernel(const FlowArgs a, const StackDims sd, const int chunk_cap_bytes) {
   constexpr int DP = (D + 3) / 4 * 4;
+  constexpr int kTileRows = R * kRowThreadBlock;         // a thread owns rows tid, tid + 128, ... of its tile
   extern __shared__ __align__(128) unsigned char smem_rt[];
   float* buf[2] = {reinterpret_cast<float*>(smem_rt), reinterpret_cast<float*>(smem_rt + chunk_cap_bytes)};
   const uint32_t buf_addr0 = smem_u32(smem_rt);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_rt + 2 * (size_t)chunk_cap_bytes);
 
   const int tid = threadIdx.x;
-  const long long n_tiles = (a.n_rows + kRowThreadBlock - 1) / kRowThreadBlock;
+  const long long n_tiles = (a.n_rows + kTileRows - 1) / kTileRows;
   if ((long long)blockIdx.x >= n_tiles) return;
   const long long my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
   const long long total = my_tiles * a.n_chunks;   // chunk instances this CTA consumes
@@ -188,18 +300,25 @@ flow_rowthread_kernel(const FlowArgs a, const StackDims sd, const int chunk_cap_
 
   long long g = 0;
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long row = tile * kRowThreadBlock + tid;
-    const bool valid = row < a.n_rows;
-    float y[D];
-    float ld = 0.f;
-    const float* prow = a.P;
-    if (valid) {
+    long long row[R];
+    bool valid[R];
+    float y[R][D];
+    float ld[R];
+    const float* prow[R];
 #pragma unroll
-      for (int j = 0; j < D; ++j) y[j] = flow_input(a, row, j, D);
-      prow = a.P + row_instance(a, row) * (long long)sd.PW;
-    } else {
+    for (int r = 0; r < R; ++r) {
+      row[r] = tile * kTileRows + r * kRowThreadBlock + tid;
+      valid[r] = row[r] < a.n_rows;
+      ld[r] = 0.f;
+      prow[r] = a.P;
+      if (valid[r]) {
 #pragma unroll
-      for (int j = 0; j < D; ++j) y[j] = 0.f;
+        for (int j = 0; j < D; ++j) y[r][j] = flow_input(a, row[r], j, D);
+        prow[r] = a.P + row_instance(a, row[r]) * (long long)sd.PW;
+      } else {
+#pragma unroll
+        for (int j = 0; j < D; ++j) y[r][j] = 0.f;
+      }
     }
 
     for (int ci = 0; ci < a.n_chunks; ++ci, ++g) {
@@ -211,28 +330,50 @@ flow_rowthread_kernel(const FlowArgs a, const StackDims sd, const int chunk_cap_
         const DevOp op = a.ops[c.first_op + oi];
         const uint32_t w = base + 4u * (uint32_t)(op.off - c.off);
         if (op.type == DOP_HALF) {
-          if (op.src == 0) half_coupling<D, HP, 0>(y, ld, w, sd.half[0], prow + op.proj_off, op.inverse);
-          else             half_coupling<D, HP, 1>(y, ld, w, sd.half[1], prow + op.proj_off, op.inverse);
+          if (op.src == 0) half_coupling_rows<D, HP, 0, R>(y, ld, w, sd.half[0], prow, op.proj_off, op.inverse);
+          else             half_coupling_rows<D, HP, 1, R>(y, ld, w, sd.half[1], prow, op.proj_off, op.inverse);
         } else if (op.type == DOP_MIX) {
           // y <- y @ M, M = Q (forward, cnf.py:335) or Q^T (inverse, cnf.py:339)
-          f32x2 o2[DP / 2];
+          f32x2 o2[R][DP / 2];
 #pragma unroll
-          for (int j = 0; j < DP / 2; ++j) o2[j] = 0ull;
+          for (int r = 0; r < R; ++r)
 #pragma unroll
-          for (int i = 0; i < D; ++i) axpy_row2<DP>(o2, y[i], w + 4u * (i * DP));
-          float o[DP];
+            for (int j = 0; j < DP / 2; ++j) o2[r][j] = 0ull;
 #pragma unroll
-          for (int j = 0; j < DP; j += 2) unpack2(o2[j / 2], o[j], o[j + 1]);
+          for (int i = 0; i < D; ++i) {
+            float x[R];
 #pragma unroll
-          for (int j = 0; j < D; ++j) y[j] = o[j];
+            for (int r = 0; r < R; ++r) x[r] = y[r][i];
+            axpy_rows2<DP, R>(o2, x, w + 4u * (i * DP));
+          }
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            float o[DP];
+#pragma unroll
+            for (int j = 0; j < DP; j += 2) unpack2(o2[r][j / 2], o[j], o[j + 1]);
+#pragma unroll
+            for (int j = 0; j < D; ++j) y[r][j] = o[j];
+          }
         } else if (op.type == DOP_ACTNORM_FWD) {
 #pragma unroll
-          for (int j = 0; j < D; ++j) y[j] = fmaf(lds1(w + 4 * j), y[j], lds1(w + 4 * (DP + j)));   // cnf.py:349
-          ld += lds1(w + 4 * (2 * DP));                                                              // cnf.py:350
+          for (int j = 0; j < D; ++j) {
+            const float sc = lds1(w + 4 * j), bi = lds1(w + 4 * (DP + j));
+#pragma unroll
+            for (int r = 0; r < R; ++r) y[r][j] = fmaf(sc, y[r][j], bi);                               // cnf.py:349
+          }
+          const float c0 = lds1(w + 4 * (2 * DP));
+#pragma unroll
+          for (int r = 0; r < R; ++r) ld[r] += c0;                                                     // cnf.py:350
         } else {  // DOP_ACTNORM_INV
 #pragma unroll
-          for (int j = 0; j < D; ++j) y[j] = __fdiv_rn(y[j] - lds1(w + 4 * (DP + j)), lds1(w + 4 * j));   // cnf.py:354
-          ld += lds1(w + 4 * (2 * DP));
+          for (int j = 0; j < D; ++j) {
+            const float sc = lds1(w + 4 * j), bi = lds1(w + 4 * (DP + j));
+#pragma unroll
+            for (int r = 0; r < R; ++r) y[r][j] = __fdiv_rn(y[r][j] - bi, sc);                         // cnf.py:354
+          }
+          const float c0 = lds1(w + 4 * (2 * DP));
+#pragma unroll
+          for (int r = 0; r < R; ++r) ld[r] += c0;
         }
       }
       __syncthreads();   // every thread is done reading buf[b]
@@ -244,11 +385,13 @@ flow_rowthread_kernel(const FlowArgs a, const StackDims sd, const int chunk_cap_
       }
     }
 
-    if (valid) {
 #pragma unroll
-      for (int j = 0; j < D; ++j) flow_output(a, row, j, D, y[j]);
-      if (a.logdet) a.logdet[row] = ld;
-    }
+    for (int r = 0; r < R; ++r)
+      if (valid[r]) {
+#pragma unroll
+        for (int j = 0; j < D; ++j) flow_output(a, row[r], j, D, y[r][j]);
+        if (a.logdet) a.logdet[row[r]] = ld[r];
+      }
   }
 }
 
