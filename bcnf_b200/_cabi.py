@@ -115,7 +115,7 @@ class LstmStep(C.Structure):
 def nvcc_command(out_path: str = LIB_PATH) -> list[str]:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-            "-shared", "-Xcompiler", "-fPIC", "-o", out_path] + SOURCES
+            "-shared", "-Xcompiler", "-fPIC", "-o", out_path] + SOURCES + ["-ldl"]
 
 
 def needs_build() -> bool:

@@ -10,6 +10,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.cuh"
 #include "cond_project.cuh"
 #include "flow_rowthread.cuh"
@@ -36,6 +38,16 @@ static int fail(int code, const char* fmt, ...) {
   va_end(ap);
   return code;
 }
+// NVTX range around each data-path entry point (header-only nvtx3: a no-op unless a profiler injects itself), so a
+// timeline shows the C-ABI calls by name above the kernels they launch.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
+#define NVTX_RANGE(name) NvtxRange nvtx_range_(name)
+
 // Entry points run on the handle's (or the caller-named) device and restore the caller's current device on the way out:
 // torch keeps its own notion of the current device, and bcnf_flow_destroy is reached from Python's garbage collector.
 struct DeviceGuard {
@@ -457,6 +469,7 @@ static int opt_in_smem_once(K kernel, size_t bytes, size_t (&configured)[64]) {
 }
 
 extern "C" int bcnf_flow_create(const bcnf_flow_desc_t* desc, const int32_t* op_types, bcnf_flow_t** out) {
+  NVTX_RANGE("bcnf_flow_create");
   if (!desc || !op_types || !out) return fail(BCNF_E_ARG, "bcnf_flow_create: null argument");
   *out = nullptr;
   if (desc->size < 2 || desc->size > BCNF_MAX_SIZE)
@@ -847,6 +860,7 @@ static int s2_scratch_for(bcnf_flow* f, cudaStream_t stream, unsigned char** out
 }
 
 extern "C" int bcnf_flow_set_params(bcnf_flow_t* f, const bcnf_op_params_t* ops, void* stream_) {
+  NVTX_RANGE("bcnf_flow_set_params");
   if (!f || !ops) return fail(BCNF_E_ARG, "bcnf_flow_set_params: null argument");
   cudaStream_t stream = (cudaStream_t)stream_;
   DEVICE_GUARD(f->desc.device);
@@ -1048,6 +1062,7 @@ extern "C" int bcnf_gemm_img(const void* a_img, int64_t a_plane, int32_t a_rpad,
 static const long long kProjSlice = 32768;   // instances per launch of the projection GEMM (scratch image: one slice)
 
 extern "C" int bcnf_cond_project(bcnf_flow_t* f, const float* h, int64_t n_inst, float* P, void* stream_) {
+  NVTX_RANGE("bcnf_cond_project");
   if (!f || !h || !P) return fail(BCNF_E_ARG, "bcnf_cond_project: null argument");
   if (n_inst < 0) return fail(BCNF_E_ARG, "n_inst=%lld", (long long)n_inst);
   if (!f->params_set) return fail(BCNF_E_STATE, "bcnf_flow_set_params has not been called");
@@ -1280,6 +1295,7 @@ static int run_flow(bcnf_flow_t* f, int dir, const float* in, const float* P, co
 // Posterior sampling with the latent drawn inside the kernel (bcnf_b200.h): inverse pass on z = sigma * N(0, 1).
 extern "C" int bcnf_flow_sample(bcnf_flow_t* f, uint64_t seed, float sigma, const float* P, const int32_t* row2inst,
                                 int64_t inst_period, int64_t n_rows, float* x, float* logdet, void* stream) {
+  NVTX_RANGE("bcnf_flow_sample");
   if (!x) return fail(BCNF_E_ARG, "bcnf_flow_sample: null output");
   FlowExtra ex;
   ex.draw = true; ex.seed = seed; ex.sigma = sigma;
@@ -1291,6 +1307,7 @@ extern "C" int bcnf_flow_sample(bcnf_flow_t* f, uint64_t seed, float sigma, cons
 extern "C" int bcnf_flow_sample_ranks(bcnf_flow_t* f, const float* z, uint64_t seed, float sigma, const float* P,
                                       const int32_t* row2inst, int64_t inst_period, int64_t n_rows, const float* y,
                                       int32_t* ranks, void* stream) {
+  NVTX_RANGE("bcnf_flow_sample_ranks");
   if (!y || !ranks) return fail(BCNF_E_ARG, "bcnf_flow_sample_ranks: null argument");
   FlowExtra ex;
   ex.draw = z == nullptr; ex.seed = seed; ex.sigma = sigma; ex.rank_y = y; ex.rank_out = ranks;
@@ -1300,6 +1317,7 @@ extern "C" int bcnf_flow_sample_ranks(bcnf_flow_t* f, const float* z, uint64_t s
 // Re-simulation of n parameter sets (bcnf_b200.h; reference src/bcnf/simulation/physics.py:53-165).
 extern "C" int bcnf_resimulate(const double* params, int64_t n, int32_t n_steps, double dt, int32_t substeps,
                                int32_t break_on_impact, double* x_out, int32_t device, void* stream) {
+  NVTX_RANGE("bcnf_resimulate");
   if (n < 0 || n_steps < 1 || substeps < 1 || !(dt > 0.0)) return fail(BCNF_E_ARG, "bcnf_resimulate: bad size");
   if (n == 0) return BCNF_OK;
   if (!params || !x_out) return fail(BCNF_E_ARG, "bcnf_resimulate: null argument");
@@ -1314,11 +1332,13 @@ extern "C" int bcnf_resimulate(const double* params, int64_t n, int32_t n_steps,
 
 extern "C" int bcnf_flow_forward(bcnf_flow_t* f, const float* y, const float* P, const int32_t* row2inst,
                                  int64_t inst_period, int64_t n_rows, float* z, float* logdet, void* stream) {
+  NVTX_RANGE("bcnf_flow_forward");
   return run_flow(f, 0, y, P, row2inst, inst_period, n_rows, z, logdet, stream);
 }
 
 extern "C" int bcnf_flow_inverse(bcnf_flow_t* f, const float* z, const float* P, const int32_t* row2inst,
                                  int64_t inst_period, int64_t n_rows, float* x, float* logdet, void* stream) {
+  NVTX_RANGE("bcnf_flow_inverse");
   return run_flow(f, 1, z, P, row2inst, inst_period, n_rows, x, logdet, stream);
 }
 

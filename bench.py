@@ -71,7 +71,7 @@ def perturb_actnorm(model, seed: int = 1) -> None:
 
 
 # (kernel family, config) -> (DRAM bytes per row from one ncu --set full capture, the committed summary it comes from)
-NCU_DRAM_BYTES_PER_ROW = {("tcgen05", "trajectory_FC_large"): (11.21e9 / 75776, "profiles/r02_flow_tc2.txt"),
+NCU_DRAM_BYTES_PER_ROW = {("tcgen05", "trajectory_FC_large"): ((3.611e9 + 8.644e9) / 75776, "profiles/r02_flow_tc2.txt"),
                           ("rowthread", "trajectory_FC_small"): (40.8e6 / 5.0e5, "profiles/r01_rowthread_lds.txt")}
 
 
