@@ -376,13 +376,17 @@ static const char* tc_plan(bcnf_flow& f, int npass) {
 
 // ---- second-generation fused kernel (flow_tc2.cuh): layer / chunk structure, shared-memory carve-up ---------------
 static void s2_set_chunks(S2Layer& ly, int np) {
-  // Full 256-column chunks, then the remainder (528 -> 256, 256, 16).  The LAST chunk of a layer is the one whose
-  // epilogue the next layer's MMAs have to wait for: keeping it small keeps that wait short, and an M = 256, N = 16
-  // MMA costs the same shared-memory cycles per column as the balanced split (192, 192, 144) would.
-  const int n = (np + 255) / 256;
+  // N chunks of kS2ChunkCols columns, then the remainder.  Every tcgen05.mma re-reads its 128 A rows from shared
+  // memory whatever its N, so a layer costs (number of chunks) x A reads + one pass over B: the split only moves time
+  // between the chunks.  BCNF_TC2_CHUNK (64 / 128 / 192 / 256, read when the handle is created) selects the width for
+  // experiments; chunk starts stay multiples of 64 = image chunks.
+  int cw = 256;
+  if (const char* e = getenv("BCNF_TC2_CHUNK")) { const int v = atoi(e); if (v == 64 || v == 128 || v == 192 || v == 256) cw = v; }
+  const int n = (np + cw - 1) / cw;
   for (int i = 0; i < kS2MaxChunks; ++i) ly.chunk_n[i] = 0;
   ly.n_chunks = n;
-  for (int i = 0, left = np; i < n; ++i) { ly.chunk_n[i] = std::min(256, left); left -= ly.chunk_n[i]; }
+  if (n > kS2MaxChunks) return;
+  for (int i = 0, left = np; i < n; ++i) { ly.chunk_n[i] = std::min(cw, left); left -= ly.chunk_n[i]; }
 }
 
 // Returns 0 and fills f.s2 if the stack fits the kernel, else a reason string.

@@ -281,6 +281,7 @@ flow_tc2_kernel(const FlowArgs a, const StackDims sd, const S2Dims d2, const uns
             const S2Layer& ly = hl.layer[l];
             const unsigned char* abuf = act_cta + (long long)(job & 1u) * buf_bytes;
             const uint32_t in_groups = l == 0 ? 1u : (uint32_t)hl.layer[l - 1].n_chunks;
+            const int in_cw = l == 0 ? 64 : hl.layer[l - 1].chunk_n[0];      // width of the N chunks that wrote the input
             int n0 = 0;
             for (int c = 0; c < ly.n_chunks; ++c) {
               const int cn = ly.chunk_n[c];
@@ -289,9 +290,9 @@ flow_tc2_kernel(const FlowArgs a, const StackDims sd, const S2Dims d2, const uns
               for (int kc = 0; kc < ly.n_kst; ++kc, ++it) {
                 if (c == 0) {
                   // image chunk kc of the input was written by this CTA's own epilogue as part of output group
-                  // kc / 4 of the previous layer (N chunks are 256 columns = 4 image chunks): wait until all sixteen
-                  // epilogue warps have made that group visible
-                  const uint32_t need = (grp_base + (l == 0 ? 0u : (uint32_t)(kc >> 2)) + 1u) * (uint32_t)kS2EpiWarps;
+                  // (64 kc + 63) / chunk width of the previous layer (the last group if the chunk is the ragged one): wait
+                  // until all sixteen epilogue warps have made that group visible
+                  const uint32_t need = (grp_base + (l == 0 ? 0u : (uint32_t)((64 * kc + 63) / in_cw < (int)in_groups ? (64 * kc + 63) / in_cw : (int)in_groups - 1)) + 1u) * (uint32_t)kS2EpiWarps;
                   if (*reinterpret_cast<volatile unsigned int*>(done_warps) < need) {
                     const unsigned long long t0 = g2_now();
                     uint32_t n = 0;
