@@ -376,17 +376,26 @@ static const char* tc_plan(bcnf_flow& f, int npass) {
 
 // ---- second-generation fused kernel (flow_tc2.cuh): layer / chunk structure, shared-memory carve-up ---------------
 static void s2_set_chunks(S2Layer& ly, int np) {
-  // N chunks of kS2ChunkCols columns, then the remainder.  Every tcgen05.mma re-reads its 128 A rows from shared
-  // memory whatever its N, so a layer costs (number of chunks) x A reads + one pass over B: the split only moves time
-  // between the chunks.  BCNF_TC2_CHUNK (64 / 128 / 192 / 256, read when the handle is created) selects the width for
-  // experiments; chunk starts stay multiples of 64 = image chunks.
-  int cw = 256;
-  if (const char* e = getenv("BCNF_TC2_CHUNK")) { const int v = atoi(e); if (v == 64 || v == 128 || v == 192 || v == 256) cw = v; }
-  const int n = (np + cw - 1) / cw;
+  // N chunks: a pattern of widths (multiples of 64, so that every chunk starts on an image chunk), the last one taking
+  // what is left.  Every tcgen05.mma re-reads its 128 A rows whatever its N, so the split does not change the operand
+  // traffic of a layer; it decides what overlaps what (flow_tc2.cuh: the accumulator of chunk c + 2 needs the epilogue
+  // of chunk c, the next layer's last K stages need the epilogue of the last chunk).  BCNF_TC2_SPLIT="256,192" (read
+  // when the handle is created) overrides the default for experiments.
+  int pat[kS2MaxChunks] = {256, 256, 256, 256};
+  if (const char* e = getenv("BCNF_TC2_SPLIT")) {
+    int i = 0;
+    for (const char* q = e; *q && i < kS2MaxChunks; ++i) {
+      const int v = atoi(q);
+      if (v >= 64 && v <= 256 && v % 64 == 0) pat[i] = v;
+      while (*q && *q != ',') ++q;
+      if (*q == ',') ++q;
+    }
+    for (; i > 0 && i < kS2MaxChunks; ++i) pat[i] = pat[i - 1];
+  }
   for (int i = 0; i < kS2MaxChunks; ++i) ly.chunk_n[i] = 0;
-  ly.n_chunks = n;
-  if (n > kS2MaxChunks) return;
-  for (int i = 0, left = np; i < n; ++i) { ly.chunk_n[i] = std::min(cw, left); left -= ly.chunk_n[i]; }
+  int n = 0, left = np;
+  while (left > 0 && n < kS2MaxChunks) { ly.chunk_n[n] = std::min(pat[n], left); left -= ly.chunk_n[n]; ++n; }
+  ly.n_chunks = left > 0 ? kS2MaxChunks + 1 : n;       // too many chunks: s2_plan refuses
 }
 
 // Returns 0 and fills f.s2 if the stack fits the kernel, else a reason string.

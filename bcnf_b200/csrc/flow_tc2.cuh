@@ -281,7 +281,6 @@ flow_tc2_kernel(const FlowArgs a, const StackDims sd, const S2Dims d2, const uns
             const S2Layer& ly = hl.layer[l];
             const unsigned char* abuf = act_cta + (long long)(job & 1u) * buf_bytes;
             const uint32_t in_groups = l == 0 ? 1u : (uint32_t)hl.layer[l - 1].n_chunks;
-            const int in_cw = l == 0 ? 64 : hl.layer[l - 1].chunk_n[0];      // width of the N chunks that wrote the input
             int n0 = 0;
             for (int c = 0; c < ly.n_chunks; ++c) {
               const int cn = ly.chunk_n[c];
@@ -290,9 +289,14 @@ flow_tc2_kernel(const FlowArgs a, const StackDims sd, const S2Dims d2, const uns
               for (int kc = 0; kc < ly.n_kst; ++kc, ++it) {
                 if (c == 0) {
                   // image chunk kc of the input was written by this CTA's own epilogue as part of output group
-                  // (64 kc + 63) / chunk width of the previous layer (the last group if the chunk is the ragged one): wait
-                  // until all sixteen epilogue warps have made that group visible
-                  const uint32_t need = (grp_base + (l == 0 ? 0u : (uint32_t)((64 * kc + 63) / in_cw < (int)in_groups ? (64 * kc + 63) / in_cw : (int)in_groups - 1)) + 1u) * (uint32_t)kS2EpiWarps;
+                  // that holds its last column: wait until all sixteen epilogue warps have made that group visible
+                  uint32_t g_in = 0;        // output group of the previous layer that holds the last column of K stage kc
+                  if (l > 0) {
+                    const S2Layer& lp = hl.layer[l - 1];
+                    int end = lp.chunk_n[0];
+                    while (g_in + 1u < in_groups && end <= 64 * kc + 63) end += lp.chunk_n[++g_in];
+                  }
+                  const uint32_t need = (grp_base + g_in + 1u) * (uint32_t)kS2EpiWarps;
                   if (*reinterpret_cast<volatile unsigned int*>(done_warps) < need) {
                     const unsigned long long t0 = g2_now();
                     uint32_t n = 0;
@@ -412,7 +416,9 @@ flow_tc2_kernel(const FlowArgs a, const StackDims sd, const S2Dims d2, const uns
     // every thread has finished its stores of one output group: make them visible, count the warp
     // (a release at GPU scope by one lane, cumulative over the warp through __syncwarp: the stores are acknowledged by
     // L2 before the count moves.  No acquire, so no L1 invalidation -- a full __threadfence() per lane cost 11 % of the
-    // kernel's warp time in membar stalls and kept evicting the bias / mixing matrices from L1.)
+    // kernel's warp time in membar stalls and kept evicting the bias / mixing matrices from L1.  A CTA-scope release,
+    // with or without a writer-side fence.proxy.async.global, measured the same within run-to-run noise (111.6 / 110.9 /
+    // 111.8 ms per 500 000 rows): the GPU-scope form, whose L2 acknowledgement does not lean on request ordering, stays.)
     auto publish_group = [&]() {
       __syncwarp();
       if (d2.debug & 4) { if (lane == 0) atomicAdd(done_warps, 1u); return; }
