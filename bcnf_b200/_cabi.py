@@ -12,7 +12,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(HERE)
-LIB_PATH = os.path.join(HERE, "libbcnf_b200.so")
+# BCNF_B200_LIB: load another build of the library (A/B timing of two kernel versions on the same box)
+LIB_PATH = os.environ.get("BCNF_B200_LIB") or os.path.join(HERE, "libbcnf_b200.so")
 SOURCES = [os.path.join(HERE, "csrc", "bcnf_abi.cu")]
 HEADERS = sorted(os.path.join(HERE, "csrc", n) for n in os.listdir(os.path.join(HERE, "csrc"))
                  if n.endswith((".cuh", ".h"))) + [os.path.join(REPO, "include", "bcnf_b200.h")]

@@ -146,6 +146,47 @@ __device__ __forceinline__ f32x2 gelu_erf_fast2(f32x2 x) {
   return fma2(hx, erf_v, hx);
 }
 
+// The same on four pairs in lock step: every Horner step is written for all four pairs before the next one, so the
+// four dependent chains (10 packed FMAs each) are interleaved in the instruction stream instead of running one after the
+// other (an epilogue warp has three others on its scheduler: a chain issued alone waits for its own FMA latency most of
+// the time).  Same operations on every value as gelu_erf_fast2: identical results.
+__device__ __forceinline__ void gelu_erf_fast2x4(f32x2 (&v)[4]) {
+  float x0[4], x1[4];
+  f32x2 t[4], p[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    unpack2(v[i], x0[i], x1[i]);
+    t[i] = pack2(fminf(fabsf(x0[i]) * 0.70710678118654752440f, 4.0f), fminf(fabsf(x1[i]) * 0.70710678118654752440f, 4.0f));
+    p[i] = pack2(-7.638800192e-07f, -7.638800192e-07f);
+  }
+#define BCNF_GELU_STEP(c)                                      \
+  _Pragma("unroll") for (int i = 0; i < 4; ++i) p[i] = fma2(p[i], t[i], pack2(c, c));
+  BCNF_GELU_STEP(1.656447655e-05f)
+  BCNF_GELU_STEP(-1.540620985e-04f)
+  BCNF_GELU_STEP(7.796742463e-04f)
+  BCNF_GELU_STEP(-2.041655680e-03f)
+  BCNF_GELU_STEP(-2.589820766e-04f)
+  BCNF_GELU_STEP(2.797563118e-02f)
+  BCNF_GELU_STEP(-1.483925716e-01f)
+  BCNF_GELU_STEP(-9.184330629e-01f)
+  BCNF_GELU_STEP(-1.627907331e+00f)
+#undef BCNF_GELU_STEP
+  float e0[4], e1[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float a0, a1;
+    unpack2(mul2(p[i], t[i]), a0, a1);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0[i]) : "f"(a0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1[i]) : "f"(a1));
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const f32x2 erf_v = pack2(copysignf(1.0f - e0[i], x0[i]), copysignf(1.0f - e1[i], x1[i]));
+    const f32x2 hx = mul2(v[i], pack2(0.5f, 0.5f));
+    v[i] = fma2(hx, erf_v, hx);
+  }
+}
+
 // Launch arguments common to the flow kernels.
 struct FlowArgs {
   const float* in;        // (n_rows, D)

@@ -38,7 +38,8 @@ namespace bcnf {
 constexpr int kS2Stages = 3;
 constexpr int kS2EpiWarps = 16;
 constexpr int kS2EpiThreads = 32 * kS2EpiWarps;
-constexpr int kS2FirstEpi = 4;                  // warp 0 producer, 1 issuer (leader) / relay (peer), 2 store, 3 idle
+constexpr int kS2FirstEpi = 2;                  // warp 0 producer, 1 issuer (leader) / relay (peer); 18 warps = 576 threads,
+                                                // so a thread may use 112 registers (96 with two more, idle, warps)
 constexpr int kS2Threads = 32 * kS2FirstEpi + kS2EpiThreads;
 constexpr int kS2Rows = 128;                    // rows per CTA (256 per pair)
 constexpr int kS2Tile = kS2Rows * 128;          // bytes of one (128 rows x 64 k) bf16 tile / image chunk
@@ -139,6 +140,13 @@ __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+// wait for the loads issued so far; the destination registers are operands, so no use of them can move above the wait
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :: "memory");
+}
 // read of the projection slice P[instance, network]: 256-bit loads that bypass L1.  (An L2 evict-first hint was tried
 // and dropped: with M samples per instance the same slice is read by every tile that holds rows of the instance, and
 // the CTA pairs walk the networks roughly in step, so the reads after the first are L2 hits only if the line stays.)
@@ -165,14 +173,15 @@ template <int NPASS, bool ADD, int O>
 __device__ __forceinline__ void s2_gelu_pack8(const uint32_t* r, const float4& b0, const float4& b1, uint32_t (&hi)[8], uint32_t (&lo)[8]) {
   f32x2 v[4];
   if (ADD) {
-    v[0] = gelu_erf_fast2(add2(pack2(__uint_as_float(r[0]), __uint_as_float(r[1])), pack2(b0.x, b0.y)));
-    v[1] = gelu_erf_fast2(add2(pack2(__uint_as_float(r[2]), __uint_as_float(r[3])), pack2(b0.z, b0.w)));
-    v[2] = gelu_erf_fast2(add2(pack2(__uint_as_float(r[4]), __uint_as_float(r[5])), pack2(b1.x, b1.y)));
-    v[3] = gelu_erf_fast2(add2(pack2(__uint_as_float(r[6]), __uint_as_float(r[7])), pack2(b1.z, b1.w)));
+    v[0] = add2(pack2(__uint_as_float(r[0]), __uint_as_float(r[1])), pack2(b0.x, b0.y));
+    v[1] = add2(pack2(__uint_as_float(r[2]), __uint_as_float(r[3])), pack2(b0.z, b0.w));
+    v[2] = add2(pack2(__uint_as_float(r[4]), __uint_as_float(r[5])), pack2(b1.x, b1.y));
+    v[3] = add2(pack2(__uint_as_float(r[6]), __uint_as_float(r[7])), pack2(b1.z, b1.w));
   } else {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = gelu_erf_fast2(pack2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])));
+    for (int i = 0; i < 4; ++i) v[i] = pack2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
   }
+  gelu_erf_fast2x4(v);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     float x0, x1;
@@ -411,7 +420,9 @@ flow_tc2_kernel(const FlowArgs a, const StackDims sd, const S2Dims d2, const uns
     // byte offset, inside a 128-byte image row, of the 32-byte sector holding this thread's two 16-byte units
     // (logical units 2*part, 2*part + 1, XOR-swizzled by row & 7: always one aligned pair, swapped when row is odd)
     const int sec_off = row * 128 + ((((part * 2) ^ (row & 7)) >> 1) << 5);
-    const bool sec_swap = (row & 1) != 0;
+    uint32_t swap_u = (uint32_t)row & 1u;
+    asm volatile("" : "+r"(swap_u));             // kept in a register (the compiler re-read %tid for it in every chunk)
+    const bool sec_swap = swap_u != 0u;
 
     // every thread has finished its stores of one output group: make them visible, count the warp
     // (a release at GPU scope by one lane, cumulative over the warp through __syncwarp: the stores are acknowledged by
@@ -587,13 +598,18 @@ flow_tc2_kernel(const FlowArgs a, const StackDims sd, const S2Dims d2, const uns
               s2_wait<false>(&acc_full[slot], (nchunk >> 1) & 1u, dbg, 0x501u);
               tc_fence_after();
               if (et == 0) s2_stamp(a.trace, 1, nchunk, 1);
-              uint32_t r[16], rn[16];
-              if (part * 16 < cn && !(d2.debug & 8)) { tmem_ld16_issue(tcol, r); tmem_ld_wait(); }
-              for (int ic = 0; ic < n_ic; ++ic) {
+              // (tcgen05.ld takes a dozen cycles: the load of the next 16 columns is issued into the same registers once
+              // the arithmetic has consumed them, and completes behind the two sector stores; a second register set
+              // held across the whole GELU made the compiler serialise half of the Horner chains)
+              uint32_t r[16];
+              if (part * 16 < cn && !(d2.debug & 8)) tmem_ld16_issue(tcol, r);
+              unsigned char* dst = obuf + (long long)(n0 >> 6) * kS2Tile;
+              asm volatile("" : "+l"(dst));          // a live pointer, not re-derived from the kernel parameters per chunk
+              for (int ic = 0; ic < n_ic; ++ic, dst += kS2Tile) {
                 const int colc = ic * 64 + part * 16;
                 const bool more = ic + 1 < n_ic && colc + 64 < cn;
-                if (more && !(d2.debug & 8)) tmem_ld16_issue(tcol + (uint32_t)(ic + 1) * 64u, rn);
                 if (colc < cn) {
+                  if (!(d2.debug & 8)) tmem_ld16_wait(r);
                   uint32_t hw[8], lw[8];
                   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
                   if (d2.debug & 1) {
@@ -603,17 +619,12 @@ flow_tc2_kernel(const FlowArgs a, const StackDims sd, const S2Dims d2, const uns
                     s2_gelu_pack8<NPASS, false, 0>(r, z4, z4, hw, lw);
                     s2_gelu_pack8<NPASS, false, 4>(r + 8, z4, z4, hw, lw);
                   }
-                  unsigned char* dst = obuf + (long long)((n0 >> 6) + ic) * kS2Tile;
+                  if (more && !(d2.debug & 8)) tmem_ld16_issue(tcol + (uint32_t)(ic + 1) * 64u, r);
                   if (!(d2.debug & 2)) {
                   st_global_sector(dst, hw, sec_swap);
                   if (NPASS == 3) st_global_sector(dst + d2.a_plane, lw, sec_swap);
                   }
                   s2_store_one<NPASS>(ly.one_col - (n0 + colc), dst - sec_off, d2.a_plane, row, part);
-                }
-                if (more) {
-                  tmem_ld_wait();
-#pragma unroll
-                  for (int i = 0; i < 16; ++i) r[i] = rn[i];
                 }
               }
             } else {
@@ -637,18 +648,19 @@ flow_tc2_kernel(const FlowArgs a, const StackDims sd, const S2Dims d2, const uns
               s2_wait<false>(&acc_full[slot], (nchunk >> 1) & 1u, dbg, 0x501u);
               tc_fence_after();
               if (et == 0) s2_stamp(a.trace, 1, nchunk, 1);
-              for (int ic = 0; ic < n_ic; ++ic) {
+              unsigned char* dst = obuf + (long long)(n0 >> 6) * kS2Tile;
+              asm volatile("" : "+l"(dst));
+              for (int ic = 0; ic < n_ic; ++ic, dst += kS2Tile) {
                 const int colc = ic * 64 + part * 16;
                 float4 bn[4];
                 load_add(ic + 1, bn);
                 if (colc < cn) {
                   uint32_t r[16];
                   tmem_ld16_issue(tcol + (uint32_t)ic * 64u, r);
-                  tmem_ld_wait();
+                  tmem_ld16_wait(r);
                   uint32_t hw[8], lw[8];
                   s2_gelu_pack8<NPASS, true, 0>(r, b[0], b[1], hw, lw);
                   s2_gelu_pack8<NPASS, true, 4>(r + 8, b[2], b[3], hw, lw);
-                  unsigned char* dst = obuf + (long long)((n0 >> 6) + ic) * kS2Tile;
                   st_global_sector(dst, hw, sec_swap);
                   if (NPASS == 3) st_global_sector(dst + d2.a_plane, lw, sec_swap);
                   s2_store_one<NPASS>(ly.one_col - (n0 + colc), dst - sec_off, d2.a_plane, row, part);
@@ -657,13 +669,14 @@ flow_tc2_kernel(const FlowArgs a, const StackDims sd, const S2Dims d2, const uns
                 for (int u = 0; u < 4; ++u) b[u] = bn[u];
               }
             }
-            if (c == ly.n_chunks - 1 && part == 0 && !(d2.debug & 16)) {
+            if (c == ly.n_chunks - 1 && !(d2.debug & 16)) {
               // every MMA of this layer has completed (its last accumulator is what we have just drained): the input
-              // image is dead -- this thread drops its own row of every chunk of it (ordered before the next writes to
-              // these lines by the release below and the accumulator hand-off of the layer after next)
+              // image is dead -- the four threads of a row drop the row's line of every fourth chunk each (ordered
+              // before the next writes to these lines by the release below and the accumulator hand-off of the layer
+              // after next; one thread per row doing all of them put 2-3 k cycles into the layer's critical path)
               const unsigned char* ibuf = act_cta + (long long)(job & 1u) * buf_bytes + row * 128;
               const int in_img = l == 0 ? 1 : tl.layer[l - 1].n_img;
-              for (int kc = 0; kc < in_img; ++kc) {
+              for (int kc = part; kc < in_img; kc += 4) {
                 discard_line(ibuf + (long long)kc * kS2Tile);
                 if (NPASS == 3) discard_line(ibuf + d2.a_plane + (long long)kc * kS2Tile);
               }
@@ -684,9 +697,9 @@ flow_tc2_kernel(const FlowArgs a, const StackDims sd, const S2Dims d2, const uns
           s2_wait<false>(&acc_full[slot], (nchunk >> 1) & 1u, dbg, 0x502u);
           tc_fence_after();
           if (et == 0) s2_stamp(a.trace, 1, nchunk, 1);
-          if (part == 0 && !(d2.debug & 16)) {          // the last Linear's input image is dead too
+          if (!(d2.debug & 16)) {          // the last Linear's input image is dead too
             const unsigned char* ibuf = act_cta + (long long)(job & 1u) * buf_bytes + row * 128;
-            for (int kc = 0; kc < tl.layer[L - 1].n_img; ++kc) {
+            for (int kc = part; kc < tl.layer[L - 1].n_img; kc += 4) {
               discard_line(ibuf + (long long)kc * kS2Tile);
               if (NPASS == 3) discard_line(ibuf + d2.a_plane + (long long)kc * kS2Tile);
             }
