@@ -22,6 +22,8 @@ from .train import _Img, _img, _pack_images, _stream
 # below this many rows the launches cost more than the PyTorch modules (BCNF_FEATURE_TC_MIN_ROWS overrides)
 MIN_ROWS = int(os.environ.get("BCNF_FEATURE_TC_MIN_ROWS", "2048"))
 MIN_ROWS_LSTM = int(os.environ.get("BCNF_FEATURE_TC_MIN_ROWS", "512"))   # measured: ahead of cuDNN at 1000 sequences already
+# the two directions of a bidirectional LSTM layer as concurrent launch chains (BCNF_LSTM_ONE_STREAM=1: one after the other)
+_LSTM_TWO_STREAMS = os.environ.get("BCNF_LSTM_ONE_STREAM", "0") != "1"
 
 
 def supported(net: Any) -> bool:
@@ -201,14 +203,33 @@ def lstm_forward(net: Any, x: torch.Tensor, passes: int) -> torch.Tensor:
                     a.state_rows, a.M, a.N, a.passes = R, B, 4 * H, passes
                     for k, (ph, pl) in enumerate(chunks(out, hc)):
                         a.h_hi[k], a.h_lo[k] = ph, pl
-                    steps.append(a)
+                    steps.append((layer, d, a))
                     prev = out
         state["steps"], state["wkey"], state["keep"] = steps, wkey, wts
-    di, st = dev.index or 0, _stream(dev)
+    di = dev.index or 0
     step_fn = lib.bcnf_lstm_step
-    for a in state["steps"]:
-        rc = step_fn(C.byref(a), di, st)
-        if rc:
-            _cabi.check(rc, "bcnf_lstm_step")
+    # The two directions of a layer are independent chains of T launches: the reverse one runs on a side stream, so its
+    # launches fill the tail of the forward one's (192 tiles on 74 CTA pairs: the last wave is 60 % full) and the launch
+    # gaps of one chain are covered by the other.  Layers join: layer l + 1 reads both directions of layer l.
+    cur = torch.cuda.current_stream(dev)
+    side = state.get("side")
+    two = dirs == 2 and _LSTM_TWO_STREAMS
+    if two and side is None:
+        side = state["side"] = torch.cuda.Stream(device=dev)
+    by_chain: dict = {}
+    for layer, d, a in state["steps"]:
+        by_chain.setdefault((layer, d), []).append(a)
+    for layer in range(L):
+        if two:
+            side.wait_stream(cur)
+        chains = [by_chain[(layer, d)] for d in range(dirs)]
+        streams = [cur.cuda_stream] + ([side.cuda_stream if two else cur.cuda_stream] if dirs == 2 else [])
+        for i in range(T):
+            for d in range(dirs):
+                rc = step_fn(C.byref(chains[d][i]), di, streams[d])
+                if rc:
+                    _cabi.check(rc, "bcnf_lstm_step")
+        if two:
+            cur.wait_stream(side)
     pooled = hsum[:, :, :B, :].permute(2, 0, 1, 3).reshape(B, dirs * H) * (1.0 / T)
     return torch.nn.functional.linear(pooled, net.linear.weight, net.linear.bias)
