@@ -7,7 +7,7 @@
 // cannot hold 128 rows x 528 fp32 columns next to them) and therefore caps the tensor pipe at 58 % : an SS-mode
 // tcgen05.mma re-reads its A rows for every N chunk, and with 64 rows per CTA that read costs more shared-memory
 // cycles than the MMA lasts.  Here a CTA PAIR owns a 256-row tile (128 rows per CTA, the
-// M = 256 cta_group::2 MMA of gemm_img2.cuh: operand reads fit the 64 B/clk port for N >= 192) and a layer's
+// M = 256 cta_group::2 MMA of gemm_img2.cuh) and a layer's
 // activations are an OPERAND IMAGE (bf16 hi / lo planes, [K/64][128 rows][128 B], SWIZZLE_128B tile layout) in a
 // per-CTA scratch that never leaves L2:
 //
@@ -15,20 +15,23 @@
 //     activation image and of its half of the weight image tile into a 3-stage ring (64 KB per stage);
 //   * one issuing thread (leader CTA): tcgen05.mma.cta_group::2 M = 256, N = chunk, K = 16 into one of two
 //     256-column TMEM accumulators;
-//   * sixteen epilogue warps per CTA drain the other accumulator: + bias (or + the hoisted condition projection P
-//     for the first Linear) -> exact-erf GELU -> bf16 hi / lo split.  A thread owns a row and 16 columns of every
-//     64-column image chunk: its two 16-byte units are ONE aligned 32-byte sector of the swizzled image row, so it
+//   * sixteen epilogue warps per CTA drain the other accumulator: + bias (folded into the GEMM where the layer
+//     width leaves a padding column; else added here; + the hoisted condition projection P for the first Linear)
+//     -> exact-erf GELU, four value pairs in lock step (packed fp32x2) -> bf16 hi / lo split.  A thread owns a row
+//     and 16 columns of every 64-column image chunk: its two 16-byte units are ONE aligned 32-byte sector of the swizzled image row, so it
 //     stores them straight to the scratch (st.global.v8.b32, a full L2 sector per lane).  No staging, no barrier
 //     inside a layer; after an N chunk every warp fences and counts itself, and the producer starts the next
 //     layer's K stages as soon as the N chunk they read has been counted sixteen times, so the MMAs of layer l+1
 //     overlap the epilogue of the last N chunk of layer l (which is the short one: 528 = 256 + 256 + 16);
 //   * the last Linear (N = 2 x dout padded to 16) leaves t and s in TMEM; the epilogue warps apply tanh / exp, the
-//     affine update, the log-det row sum, ActNorm and the orthonormal mixing in fp32, keep y in the output buffer
+//     affine update, the log-det row sum, ActNorm and the orthonormal mixing in fp32, keep y in shared memory
 //     between networks, and stage the next network's own-half input as image chunk 0.
 //
-// A 528-wide layer is three N chunks (256, 256, 16): 322 shared-memory cycles per K = 16 step against 264 tensor
-// cycles, an 82 % ceiling instead of 58 %.  Per CTA and hidden layer the L2 traffic is 3 x 270 KB of activations +
-// 557 KB of weights in, 270 KB out; the live scratch of all 148 CTAs is ~ 60 MB of the 126 MB L2.
+// A 528-wide layer is three N chunks (256, 256, 16).  With 128 A rows per CTA an SS-mode MMA runs at the math floor
+// for every N >= 128 (tools/ts_probe.cu); the third chunk re-streams A for 16 columns and is bound by the L2 round
+// trip of its stages.  Per CTA and hidden layer the L2 traffic is 3 x 270 KB of activations + 608 KB of weights in,
+// 270 KB out; the scratch of all 148 CTAs is 85 MB of the 126 MB L2, and a layer's input image is dropped from L2
+// (discard.global.L2) once the layer's MMAs have completed.  Measurements and what was tried: DESIGN.md section 6.1.
 #pragma once
 #include "flow_tc.cuh"
 #include "gemm_img2.cuh"
