@@ -8,7 +8,7 @@ from .feature_network import (ConcatenateCondition, FeatureNetwork, FeatureNetwo
                               Transformer)
 from .calibration import compute_CDF_residuals, compute_y_hat_ranks  # noqa: F401
 from .resimulation import physics_ODE_simulation_batch, resimulate  # noqa: F401
-from .train import Trainer  # noqa: F401
+from .train import FlatAdam, Trainer, fused_nll  # noqa: F401
 from .utils import ParameterIndexMapping, inn_nll_loss, load_config  # noqa: F401
 
 __version__ = "0.1.0"

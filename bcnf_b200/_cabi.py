@@ -27,7 +27,8 @@ EXPORTS = ["bcnf_abi_version", "bcnf_last_error", "bcnf_flow_create", "bcnf_flow
            "bcnf_flow_info", "bcnf_flow_debug_words", "bcnf_flow_set_params", "bcnf_cond_project", "bcnf_flow_forward",
            "bcnf_flow_inverse", "bcnf_flow_sample", "bcnf_flow_sample_ranks", "bcnf_resimulate", "bcnf_train_gemm", "bcnf_train_colsum", "bcnf_train_dropout_mask",
            "bcnf_train_set_gemm_mode", "bcnf_train_gemm_trace", "bcnf_train_pre", "bcnf_train_post",
-           "bcnf_train_post_bwd", "bcnf_train_pre_bwd", "bcnf_img_pack", "bcnf_gemm_img", "bcnf_gemm_img_gelu", "bcnf_gemm_img_set_trace", "bcnf_lstm_step"]
+           "bcnf_train_post_bwd", "bcnf_train_pre_bwd", "bcnf_img_pack", "bcnf_gemm_img", "bcnf_gemm_img_gelu", "bcnf_gemm_img_set_trace", "bcnf_lstm_step",
+           "bcnf_adam_flat", "bcnf_train_nll"]
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU_DROP, EPI_DGELU_DROP = 0, 1, 2, 3
 
 
@@ -168,6 +169,10 @@ def lib() -> C.CDLL:
     L.bcnf_flow_sample_ranks.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_float, C.c_void_p, C.c_void_p, C.c_int64,
                                          C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.bcnf_train_gemm.argtypes = [C.POINTER(GemmArgs), C.c_int32, C.c_void_p]
+    L.bcnf_adam_flat.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                 C.c_int32, C.c_void_p]
+    L.bcnf_train_nll.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_int32, C.c_void_p]
     L.bcnf_train_set_gemm_mode.argtypes = [C.c_int32]
     L.bcnf_gemm_img.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64,
                                 C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]

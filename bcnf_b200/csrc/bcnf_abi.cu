@@ -1579,6 +1579,35 @@ extern "C" int bcnf_train_colsum(const float* X, int32_t M, int32_t N, int64_t l
   return BCNF_OK;
 }
 
+// Adam over a flat blob (bcnf_b200.h; reference step: torch.optim.Adam in trainer.py:271).
+extern "C" int bcnf_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, const float* step,
+                              int32_t device, void* stream_) {
+  if (!p || !g || !m || !v || !hyper || !step) return fail(BCNF_E_ARG, "bcnf_adam_flat: null argument");
+  if (n < 0 || n % 4) return fail(BCNF_E_ARG, "bcnf_adam_flat: n must be a non-negative multiple of 4");
+  if ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) != 0) return fail(BCNF_E_ARG, "bcnf_adam_flat: 16-byte alignment");
+  if (n == 0) return BCNF_OK;
+  DEVICE_GUARD(device);
+  int n_sm = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+  const long long n4 = n / 4;
+  const long long blocks = std::min<long long>((n4 + 255) / 256, (long long)n_sm * 8);
+  adam_flat_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(p, g, m, v, n4, hyper, step);
+  CUDA_TRY(cudaGetLastError());
+  return BCNF_OK;
+}
+
+// NLL loss of a batch + its gradient seeds (bcnf_b200.h; reference inn_nll_loss, utils.py:49-53).
+extern "C" int bcnf_train_nll(const float* z, const float* logdet, int32_t B, int32_t D, float* loss, float* dz, float* dlogdet,
+                              int32_t device, void* stream_) {
+  if (!z || !logdet || !loss || !dz || !dlogdet) return fail(BCNF_E_ARG, "bcnf_train_nll: null argument");
+  if (B < 1 || D < 1) return fail(BCNF_E_ARG, "bcnf_train_nll: empty batch");
+  DEVICE_GUARD(device);
+  const int threads = B >= 1024 ? 1024 : (B + 31) / 32 * 32;
+  nll_kernel<<<1, threads, 0, (cudaStream_t)stream_>>>(z, logdet, B, D, loss, dz, dlogdet);
+  CUDA_TRY(cudaGetLastError());
+  return BCNF_OK;
+}
+
 extern "C" int bcnf_train_dropout_mask(float* out, int32_t M, int32_t N, uint64_t seed, uint32_t layer_uid, float p_drop,
                                        const uint64_t* seed_ptr, int32_t device, void* stream_) {
   if (!out) return fail(BCNF_E_ARG, "bcnf_train_dropout_mask: null argument");

@@ -233,4 +233,68 @@ __global__ void dropout_mask_kernel(float* __restrict__ out, int M, int N, unsig
   out[e] = (p > 0.f && dropout_uniform(seed, layer_uid, (unsigned long long)e) < p) ? 0.f : scale;
 }
 
+// ---- Trainer step fusion (reference trainer.py:267-277) -----------------------------------
+// Adam over ONE flat parameter / gradient / moment blob (torch.optim.Adam semantics, no amsgrad): a single pass over
+// 4 x n floats instead of one multi-tensor launch per chunk of parameter tensors.  hyper = [lr, beta1, beta2, eps,
+// weight_decay] and step (the 1-based step count, already advanced) live on the device: a captured step replays with
+// the current values.  n is a multiple of 4 (views are 64-element aligned; padding holds zeros and stays zero).
+__global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                        float* __restrict__ m, float* __restrict__ v, long long n4,
+                                                        const float* __restrict__ hyper, const float* __restrict__ step) {
+  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4];
+  const float t = *step;
+  const float bc1 = 1.0f - powf(b1, t), bc2_sqrt = sqrtf(1.0f - powf(b2, t));
+  const float step_size = lr / bc1;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 pp = p4[i], mm = m4[i], vv = v4[i];
+    const float4 gg = g4[i];
+    float* pe = reinterpret_cast<float*>(&pp);
+    float* me = reinterpret_cast<float*>(&mm);
+    float* ve = reinterpret_cast<float*>(&vv);
+    const float* ge = reinterpret_cast<const float*>(&gg);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gk = wd != 0.f ? fmaf(wd, pe[k], ge[k]) : ge[k];
+      me[k] = fmaf(1.0f - b1, gk - me[k], me[k]);                       // exp_avg.lerp_(grad, 1 - beta1)
+      ve[k] = fmaf(1.0f - b2, gk * gk, b2 * ve[k]);                     // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+      const float denom = sqrtf(ve[k]) / bc2_sqrt + eps;
+      pe[k] -= step_size * (me[k] / denom);
+    }
+    p4[i] = pp; m4[i] = mm; v4[i] = vv;
+  }
+}
+
+// NLL of a batch and the gradients it sends back, in one launch (utils.py:49-53): loss = mean_b(0.5 sum_j z^2 - logdet),
+// dz = z / B, dlogdet = -1 / B.  One block, rows strided over its threads, fixed reduction order.
+__global__ void __launch_bounds__(1024) nll_kernel(const float* __restrict__ z, const float* __restrict__ ld, int B, int D,
+                                                   float* __restrict__ loss, float* __restrict__ dz, float* __restrict__ dld) {
+  __shared__ float part[32];
+  const float inv = 1.0f / (float)B;
+  float acc = 0.f;
+  for (int r = threadIdx.x; r < B; r += blockDim.x) {
+    float s = 0.f;
+    for (int j = 0; j < D; ++j) {
+      const float x = z[(long long)r * D + j];
+      s = fmaf(x, x, s);
+      dz[(long long)r * D + j] = x * inv;
+    }
+    acc += 0.5f * s - ld[r];
+    dld[r] = -inv;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float s = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) *loss = s * inv;
+  }
+}
+
 }  // namespace bcnf

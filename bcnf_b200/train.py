@@ -1,17 +1,17 @@
 """Training step of the coupling stack (reference ``Trainer._train_batch``, src/bcnf/train/trainer.py:244-277).
 
-``CondRealNVP_v2.forward`` in training mode routes here: one ``torch.autograd.Function`` for the
-whole stack.  The conditioner's Linear -> GELU -> Dropout chains -- all of the FLOPs -- run forward and
-backward on the fused SGEMM of ``bcnf_b200/csrc/train_ops.cuh`` through the C ABI
-(``bcnf_train_gemm``): bias + GELU + dropout in the forward epilogue, gelu' * mask in the data-gradient
-epilogue, weight gradients accumulated straight into tensors shaped like the parameters.  Dropout
-masks are a counter-based hash of (seed, layer, row, column), regenerated in backward, never stored.
-The D-wide glue between the GEMMs (tanh / exp / affine update, ActNorm, the D x D mixing) is a handful
-of tiny torch ops on (B, D) tensors.
+``CondRealNVP_v2.forward`` in training mode routes here: one ``torch.autograd.Function`` for the whole stack.
+The conditioner's Linear -> GELU -> Dropout chains -- all of the FLOPs -- run forward and backward on the
+tensor-core GEMMs of ``csrc/train_tc.cuh`` through the C ABI (``bcnf_train_gemm`` on bf16 hi / lo operand
+images): bias + GELU + dropout in the forward epilogue, gelu' * mask in the data-gradient epilogue, weight
+gradients written straight into tensors shaped like the parameters (or into the flat gradient buffer of
+``_GradSink``).  Dropout masks are a counter-based hash of (seed, layer, row, column), regenerated in backward,
+never stored.  Everything between the GEMMs of a coupling block is one fused kernel per direction
+(``csrc/train_glue.cuh``).
 
-Because gradients are returned per parameter tensor, ``torch.optim`` and
-``torch.nn.parallel.DistributedDataParallel`` (NCCL all-reduce of the gradients) work
-unchanged on top.
+Gradients are per-parameter tensors (views of one flat buffer when the Trainer owns the step), so ``torch.optim``
+and ``torch.nn.parallel.DistributedDataParallel`` work unchanged on top; ``FlatAdam`` and ``fused_nll`` are the
+fused forms of the optimizer step and the loss.
 """
 from __future__ import annotations
 
@@ -23,7 +23,7 @@ import torch
 
 from . import _cabi
 
-__all__ = ["stack_forward_train", "dropout_mask", "Trainer"]
+__all__ = ["stack_forward_train", "dropout_mask", "Trainer", "FlatAdam", "fused_nll"]
 
 
 def _stream(dev: torch.device) -> int:
@@ -563,19 +563,27 @@ class _GradSink:
     so the SUM all-reduce yields the mean without another pass over the buffer.
     """
 
-    def __init__(self, params: list[torch.Tensor], process_group: Any, n_buckets: int = 4) -> None:
+    def __init__(self, params: list[torch.Tensor], process_group: Any, n_buckets: int = 4,
+                 adopt: "FlatAdam | None" = None) -> None:
         self.group = process_group
         self.n_buckets = n_buckets
         self.params = [t for t in params if t.requires_grad]
         dev = self.params[0].device
-        offs, at = {}, 0
-        for t in self.params:
-            offs[id(t)] = at
-            at += (t.numel() + 63) // 64 * 64              # 256-byte aligned views (vector stores of the GEMM epilogues)
-        self.offs, self.total = offs, at
-        self.flat = torch.zeros(at, device=dev)
-        for t in self.params:
-            t.grad = self.view(t)
+        if adopt is not None:
+            # the optimizer's flat gradient blob IS the sink: its first `stack_end` elements hold the stack's gradients
+            # in this order and with this alignment
+            if [id(t) for t in adopt.params[: len(self.params)]] != [id(t) for t in self.params]:
+                raise ValueError("FlatAdam was built for another model (its parameter order does not start with the stack's)")
+            self.offs, self.total, self.flat = adopt.offs, adopt.stack_end, adopt.flat_g
+        else:
+            offs, at = {}, 0
+            for t in self.params:
+                offs[id(t)] = at
+                at += _align64(t.numel())                   # 256-byte aligned views (vector stores of the GEMM epilogues)
+            self.offs, self.total = offs, at
+            self.flat = torch.zeros(at, device=dev)
+            for t in self.params:
+                t.grad = self.view(t)
         self.comm = torch.cuda.Stream(device=dev)
         self.active = False
         self._pending = False
@@ -585,7 +593,7 @@ class _GradSink:
         return None if o is None else self.flat[o: o + t.numel()].view(t.shape)
 
     def begin(self) -> None:
-        self.flat.zero_()                                   # bias / ActNorm gradients are accumulated with atomics
+        self.flat[: self.total].zero_()                     # bias / ActNorm gradients are accumulated with atomics
         self.active, self._pending = True, False
 
     def bucket_bounds(self, units: list[Any], params: list[torch.Tensor]) -> list[tuple[int, int, int]]:
@@ -615,6 +623,124 @@ class _GradSink:
 
 
 _SINK: _GradSink | None = None      # set by Trainer for the duration of its backward
+
+
+def _align64(n: int) -> int:
+    return (n + 63) // 64 * 64
+
+
+class FlatAdam(torch.optim.Optimizer):
+    """``torch.optim.Adam`` (no amsgrad) over ONE flat blob: SURVEY.md section 8f-3, reference step trainer.py:271.
+
+    Parameters, gradients and both moments of the model live in four flat fp32 buffers of one layout (every tensor
+    a 256-byte-aligned view; the coupling stack's parameters first, in the order the stack's backward produces their
+    gradients, so that the Trainer's gradient sink and its all-reduce buckets are ranges of the same buffer).  A step
+    is one launch (``bcnf_adam_flat``: one pass over 4 x n floats) instead of a multi-tensor launch per chunk of
+    tensors; learning rate, betas, eps, weight decay and the step count live on the device, so a captured step replays
+    with the current values (``sync_hyper`` pushes a changed ``param_groups[0]["lr"]``).
+
+    A ``torch.optim.Optimizer`` (one parameter group; learning-rate schedulers work on it) whose ``state`` is the
+    three flat tensors.  CUDA models without cuDNN RNN modules (their weights must stay in cuDNN's own flat buffer).
+    """
+
+    def __init__(self, model: torch.nn.Module, lr: float = 1e-3, betas: tuple[float, float] = (0.9, 0.999),
+                 eps: float = 1e-8, weight_decay: float = 0.0) -> None:
+        if any(isinstance(m, torch.nn.RNNBase) for m in model.modules()):
+            raise NotImplementedError("FlatAdam: models with cuDNN RNN modules are not supported (use torch.optim.Adam)")
+        stack = [t for t in stack_parameters(model) if t.requires_grad]
+        seen = {id(t) for t in stack}
+        self.params = stack + [t for t in model.parameters() if t.requires_grad and id(t) not in seen]
+        if not self.params or not all(t.is_cuda and t.dtype == torch.float32 for t in self.params):
+            raise ValueError("FlatAdam needs fp32 CUDA parameters")
+        dev = self.params[0].device
+        self.offs, at = {}, 0
+        for i, t in enumerate(self.params):
+            if i == len(stack):
+                self.stack_end = at
+            self.offs[id(t)] = at
+            at += _align64(t.numel())
+        if len(stack) == len(self.params):
+            self.stack_end = at
+        self.total = at
+        self.flat_p = torch.zeros(at, device=dev)
+        self.flat_g = torch.zeros(at, device=dev)
+        self.exp_avg = torch.zeros(at, device=dev)
+        self.exp_avg_sq = torch.zeros(at, device=dev)
+        self.step_t = torch.zeros((), device=dev)
+        with torch.no_grad():
+            for t in self.params:
+                o, n = self.offs[id(t)], t.numel()
+                view = self.flat_p[o: o + n].view(t.shape)
+                view.copy_(t)
+                t.data = view
+                t.grad = self.flat_g[o: o + n].view(t.shape)
+        super().__init__(self.params, {"lr": lr, "betas": tuple(betas), "eps": eps, "weight_decay": weight_decay,
+                                       "capturable": True})
+        self.state["flat"] = {"step": self.step_t, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq}
+        self._hyper_host: tuple | None = None
+        self.hyper = torch.zeros(5, device=dev)
+        self.sync_hyper()
+
+    def sync_hyper(self) -> None:
+        g = self.param_groups[0]
+        host = (float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]))
+        if host != self._hyper_host:
+            self.hyper.copy_(torch.tensor(host, dtype=torch.float32), non_blocking=True)
+            self._hyper_host = host
+
+    def zero_grad(self, set_to_none: bool = True) -> None:      # (the views stay: "none" would detach them from the blob)
+        self.flat_g.zero_()
+
+    @torch.no_grad()
+    def step(self, closure: Any = None) -> None:
+        dev = self.flat_p.device
+        if not torch.cuda.is_current_stream_capturing():
+            self.sync_hyper()
+        self.step_t.add_(1.0)
+        rc = _cabi.lib().bcnf_adam_flat(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.exp_avg.data_ptr(),
+                                        self.exp_avg_sq.data_ptr(), self.total, self.hyper.data_ptr(),
+                                        self.step_t.data_ptr(), dev.index or 0, _stream(dev))
+        _cabi.check(rc, "bcnf_adam_flat")
+
+    def state_dict(self) -> dict:
+        g = {k: v for k, v in self.param_groups[0].items() if k != "params"}
+        return {"flat": {k: v.detach().clone() for k, v in self.state["flat"].items()}, "param_group": g,
+                "layout": [(tuple(t.shape), self.offs[id(t)]) for t in self.params]}
+
+    def load_state_dict(self, sd: dict) -> None:
+        if [(tuple(t.shape), self.offs[id(t)]) for t in self.params] != [(tuple(sh), o) for sh, o in sd["layout"]]:
+            raise ValueError("FlatAdam.load_state_dict: parameter layout differs")
+        with torch.no_grad():
+            for k, v in sd["flat"].items():
+                self.state["flat"][k].copy_(v)
+        self.param_groups[0].update(sd["param_group"])
+        self.sync_hyper()
+
+
+class _NllFn(torch.autograd.Function):
+    """inn_nll_loss(z, logdet) (utils.py:49-53) and the gradients it sends back, one launch (``bcnf_train_nll``)."""
+
+    @staticmethod
+    def forward(ctx, z: torch.Tensor, ld: torch.Tensor):
+        z, ld = z.contiguous(), ld.contiguous()
+        dev = z.device
+        loss = torch.empty((), device=dev)
+        dz, dld = torch.empty_like(z), torch.empty_like(ld)
+        rc = _cabi.lib().bcnf_train_nll(z.data_ptr(), ld.data_ptr(), z.shape[0], z.shape[1], loss.data_ptr(),
+                                        dz.data_ptr(), dld.data_ptr(), dev.index or 0, _stream(dev))
+        _cabi.check(rc, "bcnf_train_nll")
+        ctx.save_for_backward(dz, dld)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g: torch.Tensor):
+        dz, dld = ctx.saved_tensors
+        return dz * g, dld * g
+
+
+def fused_nll(z: torch.Tensor, log_det_J: torch.Tensor) -> torch.Tensor:
+    """``inn_nll_loss(z, log_det_J)`` (mean reduction) as one kernel forward; fp32 CUDA (B, D) / (B,) tensors."""
+    return _NllFn.apply(z, log_det_J)
 
 def stack_parameters(model: Any) -> list[torch.Tensor]:
     """The parameters of ``model.layers`` in the order stack_forward_train hands them to the autograd function."""
@@ -689,9 +815,10 @@ class Trainer:
 
     Data parallel training either wraps the model in ``DistributedDataParallel`` (eager
     steps only), or -- ``process_group=`` given, model NOT wrapped -- keeps the whole step in the graph: the
-    gradients are gathered into one flat buffer, averaged with ONE NCCL all-reduce (195 MB for a *_large config,
-    over NVLink) captured in the same graph, and scattered back before the optimizer step.  Parameters are
-    broadcast from rank 0 when the trainer is built, as DistributedDataParallel does.
+    stack's gradients are views of one flat buffer that the backward writes directly (``_GradSink``), all-reduced
+    bucket by bucket on a communication stream while the backward of the earlier blocks runs.  Parameters are
+    broadcast from rank 0 when the trainer is built, as DistributedDataParallel does.  With ``FlatAdam`` as the
+    optimizer that flat buffer is the optimizer's gradient blob and the step is one launch.
     """
 
     def __init__(self, model: Any, optimizer: torch.optim.Optimizer, hybrid_weight: float = 0.0,
@@ -705,6 +832,16 @@ class Trainer:
         self._graphs: dict[tuple, dict[str, Any]] = {}      # one captured step per batch shape
         self._sink: _GradSink | None = None
         self._other: list[torch.Tensor] = []
+        self._world = 1
+        self._flat_opt = optimizer if isinstance(optimizer, FlatAdam) else None
+        if self._flat_opt is not None:
+            if hasattr(model, "module"):
+                raise ValueError("FlatAdam owns the gradient buffers: pass the bare model (and process_group= for data parallel)")
+            sp = [t for t in stack_parameters(model) if t.requires_grad]
+            if sp and process_group is None:            # single GPU: the stack still writes its gradients into the blob
+                self._sink = _GradSink(sp, None, adopt=self._flat_opt)
+                sunk = {id(t) for t in self._sink.params}
+                self._other = [t for t in model.parameters() if t.requires_grad and id(t) not in sunk]
         if cuda_graph:
             if hasattr(model, "module"):
                 raise NotImplementedError("cuda_graph=True with a DistributedDataParallel wrapper is not supported: pass the "
@@ -721,7 +858,7 @@ class Trainer:
             # one-buffer path of _allreduce_grads after the backward)
             sp = [t for t in stack_parameters(model) if t.requires_grad and t.is_cuda]
             if sp:
-                self._sink = _GradSink(sp, process_group)
+                self._sink = _GradSink(sp, process_group, adopt=self._flat_opt)
                 sunk = {id(t) for t in self._sink.params}
                 self._other = [t for t in model.parameters() if t.requires_grad and id(t) not in sunk]
             with torch.no_grad():
@@ -770,6 +907,9 @@ class Trainer:
         if self._sink is None:
             self.optimizer.zero_grad(set_to_none=True)
             return
+        if self._flat_opt is not None:           # the other parameters' gradients are views of the same blob: one fill
+            self._flat_opt.flat_g[self._flat_opt.stack_end:].zero_()
+            return
         for t in self._other:                    # the stack's .grad views stay: the sink zeroes their buffer in one fill
             t.grad = None
 
@@ -794,6 +934,11 @@ class Trainer:
 
     def _allreduce_other(self) -> None:
         import torch.distributed as dist
+        if self._flat_opt is not None:           # contiguous in the blob: no gather / scatter
+            tail = self._flat_opt.flat_g[self._flat_opt.stack_end:]
+            if tail.numel():
+                dist.all_reduce(tail, group=self.process_group)
+            return
         grads = [p.grad for p in self._other if p.grad is not None]
         if not grads:
             return
@@ -817,7 +962,10 @@ class Trainer:
             mse = self.mse_loss(net.prediction_head(h), y.to(dev))
         else:
             mse = torch.zeros((), device=z.device)
-        nll = self.loss_function(z, net.log_det_J)
+        if z.is_cuda and z.dtype == torch.float32 and z.ndim == 2:
+            nll = fused_nll(z, net.log_det_J)             # the same value and gradients in one launch each way
+        else:
+            nll = self.loss_function(z, net.log_det_J)
         loss = (nll + mse * self.hybrid_weight) / (1 + self.hybrid_weight)
         return loss, nll, mse, z
 
@@ -901,6 +1049,8 @@ class Trainer:
         st["y"].copy_(y, non_blocking=True)
         for d, c in zip(st["c"], conditions):
             d.copy_(c, non_blocking=True)
+        if self._flat_opt is not None:
+            self._flat_opt.sync_hyper()                 # a scheduler may have changed the learning rate since the capture
         st["graph"].replay()
         return st["loss"], st["nll"], st["mse"]
 

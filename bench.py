@@ -308,7 +308,9 @@ def measure_train(args, cfg, cfg_key, batch, rank, world, local_rank, steps, war
     if use_ddp:
         model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank])
     use_graph = not use_ddp and not os.environ.get("BCNF_NO_TRAIN_GRAPH")
-    opt = torch.optim.Adam(model.parameters(), lr=2e-4, capturable=use_graph, fused=True)
+    flat_adam = os.environ.get("BCNF_BENCH_TORCH_ADAM", "0") != "1"
+    opt = (bcnf_b200.FlatAdam(model, lr=2e-4) if flat_adam
+           else torch.optim.Adam(model.parameters(), lr=2e-4, capturable=use_graph, fused=True))
     trainer = bcnf_b200.Trainer(model, opt, cuda_graph=use_graph,
                                 process_group=dist.group.WORLD if world > 1 and not use_ddp else None)
     g = torch.Generator().manual_seed(100 + rank)
@@ -355,7 +357,8 @@ def measure_train(args, cfg, cfg_key, batch, rank, world, local_rank, steps, war
                        "n_blocks": mk["n_blocks"], "n_conditions": mk["n_conditions"],
                        "kernel": "train_tc2_gemm (tcgen05, TMA-fed bf16 hi/lo operand images) + fused pre/post kernels; "
                                  "weight gradients train_tc3_dw (tcgen05, MN-major images)",
-                       "precision": "bf16x3 (3-pass split, fp32 accumulate: fp32-class)", "optimizer": "torch.optim.Adam(fused=True)",
+                       "precision": "bf16x3 (3-pass split, fp32 accumulate: fp32-class)", "optimizer": ("bcnf_b200.FlatAdam (one launch over the flat parameter / gradient / moment blob)" if flat_adam
+                                     else "torch.optim.Adam(fused=True)"),
                        "cuda_graph": use_graph, "l2": "each step touches every parameter, gradient and Adam moment (4 x 195 MB)",
                        "parallelism": f"data parallel over {world} GPU(s), " + ("torch DistributedDataParallel (eager)" if use_ddp else
                                        "one NCCL all-reduce of the flat gradient buffer inside the step's CUDA graph")},

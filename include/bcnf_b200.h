@@ -262,6 +262,17 @@ int bcnf_train_set_gemm_mode(int32_t mode);
 int bcnf_train_gemm_trace(const bcnf_gemm_args_t* args, int32_t device, void* stream, int64_t* out64);
 /* out[j] = sum_i X[i*ldx + j] + beta*out[j]   (bias gradients: the sum(0) of autograd's Linear backward) */
 int bcnf_train_colsum(const float* X, int32_t M, int32_t N, int64_t ldx, float* out, float beta, int32_t device, void* stream);
+/* Trainer step fusion (reference src/bcnf/train/trainer.py:267-277).
+ * bcnf_adam_flat: one torch.optim.Adam update (no amsgrad) of n parameters held in one flat blob, with their gradients
+ * and both moments in blobs of the same layout: p, g, m, v device pointers (16-byte aligned, n a multiple of 4);
+ * hyper = device float[5] {lr, beta1, beta2, eps, weight_decay}; step = device float holding the 1-based step count of
+ * THIS update (the caller advances it).  Replaces optimizer.step() (trainer.py:271).
+ * bcnf_train_nll: loss[0] = mean_b(0.5 sum_j z[b, j]^2 - logdet[b]) (inn_nll_loss, src/bcnf/utils.py:49-53) together
+ * with the gradients it sends back, dz = z / B and dlogdet = -1 / B, in one launch (trainer.py:267). */
+int bcnf_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, const float* step,
+                   int32_t device, void* stream);
+int bcnf_train_nll(const float* z, const float* logdet, int32_t B, int32_t D, float* loss, float* dz, float* dlogdet,
+                   int32_t device, void* stream);
 /* the multiplicative dropout mask (0 or 1/(1-p)) the fused epilogues apply, materialised for tests */
 int bcnf_train_dropout_mask(float* out, int32_t M, int32_t N, uint64_t seed, uint32_t layer_uid, float p_drop,
                             const uint64_t* seed_ptr, int32_t device, void* stream);

@@ -400,3 +400,76 @@ def _units_of(model):
                      "ortho" if isinstance(layer, bcnf_b200.OrthonormalTransformation) else "coupling")
     spec = _Spec(kinds, len(model.nested_sizes) + 1, model.two_way, model.size, model.n_conditions, 0.0, 0, None)
     return _plan(spec)[1], stack_parameters(model)
+
+
+def test_flat_adam_matches_torch_adam():
+    """bcnf_adam_flat = torch.optim.Adam's update (trainer.py:271) on the same gradients, incl. weight decay."""
+    import copy
+    for wd in (0.0, 0.01):
+        a = _model(19, [48, 48], 3, 8, dropout=0.0)
+        b = copy.deepcopy(a)
+        opt_a = bcnf_b200.FlatAdam(a, lr=3e-3, weight_decay=wd)
+        opt_b = torch.optim.Adam([p for p in b.parameters() if p.requires_grad], lr=3e-3, weight_decay=wd)
+        pa = [p for p in a.parameters() if p.requires_grad]
+        pb = [p for p in b.parameters() if p.requires_grad]
+        assert all(p.data_ptr() >= opt_a.flat_p.data_ptr() for p in pa)            # parameters are views of the blob
+        g = torch.Generator().manual_seed(4)
+        for _ in range(6):
+            opt_a.zero_grad()
+            for x, y in zip(pa, pb):
+                gr = torch.randn(x.shape, generator=g).to(DEV) * 0.1
+                x.grad.copy_(gr)                                                  # the views stay attached to the blob
+                y.grad = gr.clone()
+            opt_a.step()
+            opt_b.step()
+        torch.cuda.synchronize()
+        for x, y in zip(pa, pb):
+            assert rel_err(x.detach().cpu().numpy(), y.detach().cpu().numpy()) < 2e-6
+        assert float(opt_a.step_t) == 6.0
+        sd = opt_a.state_dict()
+        opt_a.load_state_dict(sd)
+
+
+def test_fused_nll_matches_inn_nll_loss():
+    g = torch.Generator().manual_seed(5)
+    for B in (1, 77, 256, 3000):
+        z = torch.randn(B, 19, generator=g).to(DEV).requires_grad_()
+        ld = torch.randn(B, generator=g).to(DEV).requires_grad_()
+        z2, ld2 = z.detach().clone().requires_grad_(), ld.detach().clone().requires_grad_()
+        a = bcnf_b200.fused_nll(z, ld)
+        b = bcnf_b200.inn_nll_loss(z2, ld2)
+        (a * 0.5).backward()
+        (b * 0.5).backward()
+        assert abs(a.item() - b.item()) <= 2e-6 * max(1.0, abs(b.item()))
+        assert rel_err(z.grad.cpu().numpy(), z2.grad.cpu().numpy()) < 1e-6
+        assert rel_err(ld.grad.cpu().numpy(), ld2.grad.cpu().numpy()) < 1e-6
+
+
+def test_trainer_with_flat_adam_follows_torch_adam_and_replays_as_a_graph():
+    import copy
+    a = _model(19, [48, 48], 3, 8, dropout=0.0).train()
+    b = copy.deepcopy(a).train()
+    tr_a = bcnf_b200.Trainer(a, bcnf_b200.FlatAdam(a, lr=1e-3))
+    tr_b = bcnf_b200.Trainer(b, torch.optim.Adam(b.parameters(), lr=1e-3))
+    g = torch.Generator().manual_seed(6)
+    y, c = torch.randn(128, 19, generator=g), torch.randn(128, 8, generator=g)
+    la = [tr_a.train_batch(y, c)[0] for _ in range(8)]
+    lb = [tr_b.train_batch(y, c)[0] for _ in range(8)]
+    assert np.allclose(la, lb, rtol=2e-4, atol=2e-4), (la, lb)      # (bias / ActNorm gradients are summed with atomics)
+    assert la[-1] < la[0]
+    # the eval kernels see the parameters that now live in the optimizer's blob
+    a.eval(); b.eval()
+    va, vb = tr_a.validate_batch(y, c)[1], tr_b.validate_batch(y, c)[1]
+    assert abs(va - vb) < 2e-3 * max(1.0, abs(vb))
+    # captured step: learns, and a learning-rate change reaches the replayed kernel
+    m = _model(19, [48, 48], 3, 8, dropout=0.2).train()
+    opt = bcnf_b200.FlatAdam(m, lr=1e-3)
+    tr = bcnf_b200.Trainer(m, opt, cuda_graph=True)
+    losses = [tr.train_batch(y, c)[0] for _ in range(30)]
+    assert all(np.isfinite(losses)) and np.mean(losses[-5:]) < np.mean(losses[:5])
+    assert float(opt.step_t) == 30.0                                   # warm-up steps do not count
+    opt.param_groups[0]["lr"] = 0.0
+    before = opt.flat_p.clone()
+    tr.train_batch(y, c)
+    assert torch.equal(before, opt.flat_p)
+    tr.close()
