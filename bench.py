@@ -41,6 +41,9 @@ WORKLOADS = {
     "fc_large_logprob": ("trajectory_FC_large", 1, 1 << 17, "log_prob"),
     "lstm_large_logprob": ("trajectory_LSTM_large", 1, 1 << 17, "log_prob"),
     "lstm_large_sample": ("trajectory_LSTM_large", 500, 10_000, "sample"),
+    # calibration ranks (compute_y_hat_ranks, M = 10 000 samples per instance) reduced inside the sampler:
+    # the (M, N, D) samples are never written, the output is (N, D) counters
+    "fc_large_ranks": ("trajectory_FC_large", 10_000, 1_000, "ranks"),
     # BASELINE config 4: training step (forward NLL + backward + Adam), batch 256 per GPU, DDP over N GPUs
     "trf_large_train": ("trajectory_TRF_large", 1, 256, "train"),
     "fc_small_train": ("trajectory_FC_small", 1, 256, "train"),
@@ -407,10 +410,11 @@ def main() -> None:
     mk = cfg["model"]["kwargs"]
     if kind == "train":
         return main_train(args, cfg, cfg_key, args.instances_per_step or n_inst_total, rank, world, local_rank)
-    unit = "samples/s" if kind == "sample" else "evals/s"
-    metric = "posterior samples/sec" if kind == "sample" else "log_prob evals/sec"
-    inst_step = args.instances_per_step or (1000 if kind == "sample" else n_inst_total // 8)
-    workload_name = (f"{cfg_key} {'posterior sampling' if kind == 'sample' else 'log_prob'} "
+    unit = "samples/s" if kind in ("sample", "ranks") else "evals/s"
+    metric = "posterior samples/sec" if kind in ("sample", "ranks") else "log_prob evals/sec"
+    inst_step = args.instances_per_step or {"sample": 1000, "ranks": 50}.get(kind, n_inst_total // 8)
+    what = {"sample": "posterior sampling", "ranks": "calibration ranks (samples reduced in the kernel, never written)"}.get(kind, "log_prob")
+    workload_name = (f"{cfg_key} {what} "
                      f"{m_samples} x {n_inst_total} (step = {m_samples} x {inst_step} instances per GPU)")
 
     if args.impl == "reference":
@@ -418,7 +422,7 @@ def main() -> None:
         # the host cores (the Python reference tree does not exist on the GPU box)
         if rank != 0:
             return
-        base = reference_cpu_rate(cfg, kind, m_samples, budget_s=20.0)
+        base = reference_cpu_rate(cfg, "sample" if kind == "ranks" else kind, m_samples, budget_s=20.0)
         rows_step = int(base["sample"].split("=")[1].split()[0])
         line = {"impl": "reference", "metric": metric, "value": base["value"], "unit": unit, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * rows_step / base["value"],
@@ -454,13 +458,26 @@ def main() -> None:
     rows_step = m_samples * inst_step
     launches = [0]
 
+    seed = [1234 + rank]
+    if kind == "sample":
+        out_buf = torch.empty((rows_step, d), device=device)
+    elif kind == "ranks":
+        y_host = torch.randn(inst_step, d, generator=g).pin_memory()
+        y_dev = y_host.to(device)
+        ranks_dev = torch.zeros((inst_step, d), dtype=torch.int32, device=device)
+    else:
+        y_host = torch.randn(rows_step, d, generator=g).pin_memory()
+        y_dev = y_host.to(device)
+
     def step_resident():
         with torch.no_grad():
             h = model.features(cond_dev)
             P = flow.project(h)
-            if kind == "sample":
-                z = torch.randn((rows_step, d), device=device)
-                out, _ = flow.run(True, z, P, inst_period=inst_step, out=z)
+            seed[0] += 1
+            if kind == "sample":          # the latent is drawn inside the kernel (bcnf_flow_sample), as model.sample does
+                out = flow.sample(rows_step, P, seed=seed[0], inst_period=inst_step, out=out_buf)
+            elif kind == "ranks":
+                out = flow.sample_ranks(rows_step, P, y_dev, ranks_dev, seed=seed[0], inst_period=inst_step)
             else:
                 out, _ = flow.run(False, y_dev, P, want_logdet=True)
             launches[0] += 2
@@ -469,12 +486,12 @@ def main() -> None:
     def step_e2e():
         if kind == "sample":
             return model.sample(m_samples, cond_host, outer=True, output_device="cpu")
+        if kind == "ranks":
+            from bcnf_b200 import compute_y_hat_ranks
+            return compute_y_hat_ranks(model, y_host, cond_host, M_samples=m_samples, device=device, output_device="cpu",
+                                       verbose=False)
         lp = model.log_prob(y_host.to(device, non_blocking=True), cond_host.to(device, non_blocking=True))
         return lp.to("cpu")
-
-    if kind != "sample":
-        y_host = torch.randn(rows_step, d, generator=g).pin_memory()
-        y_dev = y_host.to(device)
 
     def barrier():
         if world > 1:
@@ -514,8 +531,12 @@ def main() -> None:
         k_steps = max(3, min(args.steps, 10))
 
         def kernel_only():
-            flow.run(kind == "sample", zbuf, P, inst_period=inst_step if kind == "sample" else 0,
-                     want_logdet=(kind != "sample"))
+            if kind == "sample":
+                flow.sample(rows_step, P, seed=7, inst_period=inst_step, out=zbuf)
+            elif kind == "ranks":
+                flow.sample_ranks(rows_step, P, y_dev, ranks_dev, seed=7, inst_period=inst_step)
+            else:
+                flow.run(False, zbuf, P, want_logdet=True)
         kernel_only()
         ms_kernel = timed(kernel_only, k_steps) / k_steps
     peaks, peak_src = measured_peaks()
@@ -534,15 +555,15 @@ def main() -> None:
                 "peak_source": f"{peak_src} bf16 dense",
                 "kernel": f"flow_{flow.kernel}", "kernel_ms": ms_kernel,
                 "fp32_fma_peak_tflops": fma_peak_tf, "fp32_fma_frac": achieved_tf / fma_peak_tf,
-                "algorithmic_bytes_per_row": 4 * d * 2 + 4, "flops_per_row": 2 * int(flow.info.macs_per_row)}
+                "algorithmic_bytes_per_row": {"sample": 4 * d, "ranks": 0}.get(kind, 4 * d * 2 + 4), "flops_per_row": 2 * int(flow.info.macs_per_row)}
 
     # end to end through the public API with host buffers
     e2e_steps = max(1, min(args.steps, 5))
     step_e2e()
     ms_e2e = timed(step_e2e, e2e_steps)
     e2e_value = world * rows_step * e2e_steps / (ms_e2e * 1e-3)
-    h2d = cond_host.numel() * 4 + (0 if kind == "sample" else rows_step * d * 4)
-    d2h = rows_step * d * 4 if kind == "sample" else rows_step * 4
+    h2d = cond_host.numel() * 4 + {"sample": 0, "ranks": inst_step * d * 4}.get(kind, rows_step * d * 4)
+    d2h = {"sample": rows_step * d * 4, "ranks": inst_step * d * 4}.get(kind, rows_step * 4)
 
     # auxiliary measurements carried by the default line (not the headline; each names its own workload):
     #   train_*     BASELINE config 4, trajectory_TRF_large training step, batch 256 per GPU -- the one multi-GPU
@@ -602,7 +623,7 @@ def main() -> None:
         if aux is not None:
             line["aux"] = aux
         if not args.no_cpu_baseline:
-            line["cpu_baseline"] = reference_cpu_rate(cfg, kind, m_samples)
+            line["cpu_baseline"] = reference_cpu_rate(cfg, "sample" if kind == "ranks" else kind, m_samples)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
