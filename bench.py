@@ -480,7 +480,9 @@ def main() -> None:
                 out = flow.sample_ranks(rows_step, P, y_dev, ranks_dev, seed=seed[0], inst_period=inst_step)
             else:
                 out, _ = flow.run(False, y_dev, P, want_logdet=True)
-            launches[0] += 2
+            # own kernels per step: the fused stack + the projection (tensor-core handles: img_pack of h + the CTA-pair
+            # GEMM; fp32 handles: one SGEMM); the feature network below 2 048 instances is PyTorch and not counted
+            launches[0] += 3 if flow.kernel == "tcgen05" else 2
             return out
 
     def step_e2e():

@@ -41,6 +41,21 @@ def test_abi_validation_errors_without_gpu():
     assert lib.bcnf_flow_create(ctypes.byref(desc), arr, ctypes.byref(h)) == -1     # unknown layer type
     assert lib.bcnf_flow_forward(None, None, None, None, 0, 0, None, None, None) == -1
     assert lib.bcnf_flow_destroy(None) == 0
+    # trainer-step fusion entry points validate before they touch the device
+    assert lib.bcnf_adam_flat(None, None, None, None, 0, None, None, 0, None) == -1
+    assert lib.bcnf_adam_flat(16, 16, 16, 16, 6, 16, 16, 0, None) == -1          # n not a multiple of 4
+    assert lib.bcnf_train_nll(None, None, 4, 19, None, None, None, 0, None) == -1
+    assert lib.bcnf_train_nll(16, 16, 0, 19, 16, 16, 16, 0, None) == -1           # empty batch
+
+
+def test_flat_adam_refuses_what_it_cannot_hold():
+    import torch
+    import bcnf_b200
+    lstm = torch.nn.LSTM(3, 4)
+    with pytest.raises(NotImplementedError):
+        bcnf_b200.FlatAdam(lstm)                      # cuDNN keeps RNN weights in its own flat buffer
+    with pytest.raises(ValueError):
+        bcnf_b200.FlatAdam(torch.nn.Linear(3, 4))     # CPU parameters: the step is a CUDA kernel, no fallback
 
 
 @pytest.mark.parametrize("name", ["trajectory_FC_small", "trajectory_FC_large", "trajectory_LSTM_large",
