@@ -214,6 +214,18 @@ class _Spec:
 # chain room.  BCNF_TRAIN_SIDE_STREAMS=0 puts everything on the caller's stream (isolated kernel timings).
 _N_SIDE = int(os.environ.get("BCNF_TRAIN_SIDE_STREAMS", "2"))
 _SIDE: dict[int, list[Any]] = {}
+# Operand images of a network's parameters are packed this many networks ahead of the chain (forward orientation in the
+# forward pass, data-gradient orientation in the backward pass), so that the GEMMs find them in L2: packed all at once
+# at the start of the step (0 = the previous behaviour) the 260 MB of images evict each other before they are read.
+_PACK_AHEAD = int(os.environ.get("BCNF_TRAIN_PACK_AHEAD", "2"))
+_PACK: dict[int, Any] = {}
+
+
+def _pack_stream(dev: torch.device) -> torch.cuda.Stream:
+    key = dev.index or 0
+    if key not in _PACK:
+        _PACK[key] = torch.cuda.Stream(device=dev)
+    return _PACK[key]
 
 
 def _side_streams(dev: torch.device) -> list[Any]:
@@ -286,6 +298,13 @@ def _pitch(n: int) -> int:
     return (n + 3) // 4 * 4
 
 
+def _bwd_descs(u: Any, ws: Sequence[torch.Tensor], L: int, Cn: int, bwd: list[_Img]) -> list[tuple]:
+    """img_pack descriptors of a network's weights in the data-gradient orientation (rows = input index)."""
+    w1 = ws[0]
+    return [(w1, u.din, 1, w1.stride(0), Cn, w1.shape[0], bwd[0])] + \
+           [(ws[l], 0, 1, ws[l].stride(0), ws[l].shape[1], ws[l].shape[0], bwd[l]) for l in range(1, L)]
+
+
 class _StackFn(torch.autograd.Function):
     """z, log|det J| = stack(y, h; parameters) with a hand-written backward.
 
@@ -310,13 +329,24 @@ class _StackFn(torch.autograd.Function):
         # off the chain, per network: operand images of its parameters (they changed in the last optimizer step), in
         # the forward (rows = out) and the data-gradient (rows = in) orientation, then the condition projection P
         side.wait_stream(main)
-        P, p_ready, wimg = [], [], []
+        n_units = len(units)
+        ahead = _PACK_AHEAD if _PACK_AHEAD > 0 else n_units
+        P: list[Any] = [None] * n_units
+        p_ready: list[Any] = [None] * n_units
+        wimg: list[Any] = [None] * n_units
         with torch.cuda.stream(side):
             # images this call saves for its backward: h (d W1h) and every hidden activation but the last of each network
             lease = _PoolLease(dev, [(B, Cn)] + [(B, params[u.w0 + l].shape[0]) for u in units for l in range(L - 1)])
             h_img, act_pool = lease.images[0], lease.images[1:]
             _pack_images([(h, 0, h.stride(0), 1, B, Cn, h_img)], dev)
-            for u in units:
+
+        def prepare(idx: int, gate: Any) -> None:
+            """Side stream: the forward-orientation images of network idx (all its images when nothing is deferred) and
+            its condition projection, once the chain has reached the network `gate` was recorded at."""
+            u = units[idx]
+            with torch.cuda.stream(side):
+                if gate is not None:
+                    side.wait_event(gate)
                 ws = params[u.w0: u.w0 + spec.n_lin]
                 w1, b1 = ws[0], params[u.w0 + spec.n_lin]
                 H1, pitch1 = w1.shape[0], w1.stride(0)
@@ -324,18 +354,19 @@ class _StackFn(torch.autograd.Function):
                       [_img(dev, ("wf", w.data_ptr()), *w.shape, owner=w) for w in ws[1:L]]
                 bwd = [_img(dev, ("wb", w1.data_ptr()), Cn, H1, owner=w1)] + \
                       [_img(dev, ("wb", w.data_ptr()), w.shape[1], w.shape[0], owner=w) for w in ws[1:L]]
-                descs = [(w1, u.din, pitch1, 1, H1, Cn, fwd[0]), (w1, u.din, 1, pitch1, Cn, H1, bwd[0])]
-                for l in range(1, L):
-                    w = ws[l]
-                    descs += [(w, 0, w.stride(0), 1, w.shape[0], w.shape[1], fwd[l]), (w, 0, 1, w.stride(0), w.shape[1], w.shape[0], bwd[l])]
+                descs = [(w1, u.din, pitch1, 1, H1, Cn, fwd[0])] + \
+                        [(ws[l], 0, ws[l].stride(0), 1, ws[l].shape[0], ws[l].shape[1], fwd[l]) for l in range(1, L)]
+                if _PACK_AHEAD <= 0:                   # the data-gradient orientation too (else: packed by the backward)
+                    descs += _bwd_descs(u, ws, L, Cn, bwd)
                 _pack_images(descs, dev)
                 Pu = new(B, _pitch(H1))
                 _gemm(None, None, None, None, Pu, B, H1, Cn, epi=_cabi.EPI_BIAS, bias=b1, split_k=1, a_img=h_img, b_img=fwd[0])
                 ev = torch.cuda.Event()
                 ev.record(side)
-                P.append(Pu)
-                p_ready.append(ev)
-                wimg.append((fwd, bwd))
+                P[idx], p_ready[idx], wimg[idx] = Pu, ev, (fwd, bwd)
+
+        for idx in range(min(ahead, n_units)):
+            prepare(idx, None)
 
         def glue_only(y_in, ops):
             a = _cabi.TrainPostArgs()
@@ -351,6 +382,10 @@ class _StackFn(torch.autograd.Function):
             y, lead_saves = glue_only(y, lead)
         saved_units = []
         for ui, u in enumerate(units):
+            if ui + ahead < n_units:
+                gate = torch.cuda.Event()
+                gate.record(main)
+                prepare(ui + ahead, gate)
             ws = params[u.w0: u.w0 + spec.n_lin]
             bs = params[u.w0 + spec.n_lin: u.w0 + 2 * spec.n_lin]
             widths = [w.shape[0] for w in ws[:-1]]
@@ -458,10 +493,36 @@ class _StackFn(torch.autograd.Function):
         keep: list[Any] = [grad_lease]                                 # everything the side streams read stays alive until the join
         for sd in sides:
             sd.wait_stream(main)
+        # data-gradient orientation of the parameter images, packed _PACK_AHEAD networks ahead of the chain on a stream
+        # of their own (the side streams carry the weight-gradient GEMMs of earlier networks)
+        n_units = len(units)
+        bwd_ready: list[Any] = [None] * n_units
+        pk = _pack_stream(dev) if _PACK_AHEAD > 0 else None
+
+        def pack_bwd(idx: int, gate: Any) -> None:
+            uu = units[idx]
+            with torch.cuda.stream(pk):
+                if gate is not None:
+                    pk.wait_event(gate)
+                _pack_images(_bwd_descs(uu, params[uu.w0: uu.w0 + spec.n_lin], L, Cn, ctx.wimg[idx][1]), dev)
+                ev = torch.cuda.Event()
+                ev.record(pk)
+                bwd_ready[idx] = ev
+
+        if pk is not None:
+            pk.wait_stream(main)
+            for idx in range(n_units - 1, max(n_units - 1 - _PACK_AHEAD, -1), -1):
+                pack_bwd(idx, None)
         first_dh = True
         rr = 0
         for ui in range(len(units) - 1, -1, -1):
             u = units[ui]
+            if pk is not None:
+                if ui - _PACK_AHEAD >= 0:
+                    gate = torch.cuda.Event()
+                    gate.record(main)
+                    pack_bwd(ui - _PACK_AHEAD, gate)
+                main.wait_event(bwd_ready[ui])
             y_in, pre, act, ls, ydst, op_saves, aimg = saved_units[ui]
             ws = params[u.w0: u.w0 + spec.n_lin]
             widths = [w.shape[0] for w in ws[:-1]]
@@ -540,6 +601,8 @@ class _StackFn(torch.autograd.Function):
             dz = dz_new
         for sd in sides:
             main.wait_stream(sd)
+        if pk is not None:
+            main.wait_stream(pk)
         if sink is not None:
             sink.reduce_range(*buckets[0], [main])          # the first bucket (incl. the leading ActNorm) closes the backward
         del keep
