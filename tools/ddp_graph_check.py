@@ -15,7 +15,10 @@ torch.manual_seed(rank)          # different initial weights per rank: the train
 n_blocks = int(os.environ.get("BCNF_CHECK_BLOCKS", "3"))
 model = bcnf_b200.CondRealNVP_v2(size=19, nested_sizes=[64, 64], n_blocks=n_blocks, n_conditions=32,
                                  feature_networks=[bcnf_b200.ConcatenateCondition(None, 32)], dropout=0.1, act_norm=True).to(dev).train()
-opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True, fused=True)
+if os.environ.get("BCNF_CHECK_FLAT_ADAM"):     # the optimizer's gradient blob is the sink the buckets are cut from
+    opt = bcnf_b200.FlatAdam(model, lr=1e-3)
+else:
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True, fused=True)
 tr = bcnf_b200.Trainer(model, opt, cuda_graph=True, process_group=dist.group.WORLD)
 g = torch.Generator().manual_seed(100 + rank)
 y, c = torch.randn(128, 19, generator=g), torch.randn(128, 32, generator=g)
