@@ -364,7 +364,7 @@ def measure_train(args, cfg, cfg_key, batch, rank, world, local_rank, steps, war
                                      else "torch.optim.Adam(fused=True)"),
                        "cuda_graph": use_graph, "l2": "each step touches every parameter, gradient and Adam moment (4 x 195 MB)",
                        "parallelism": f"data parallel over {world} GPU(s), " + ("torch DistributedDataParallel (eager)" if use_ddp else
-                                       "one NCCL all-reduce of the flat gradient buffer inside the step's CUDA graph")},
+                                       "gradients written into one flat buffer and all-reduced (NCCL) in buckets underneath the backward, inside the step's CUDA graph")},
             # per conditioner network: pre, hidden GEMMs, post; post_bwd, data-gradient GEMMs, pre_bwd; weight-gradient
             # GEMMs, P and d h GEMMs, two column sums, the operand-image pack (bcnf_b200/train.py)
             "gpu_launches": steps * (n_coupling * (4 * (n_lin - 2) + 8) + 3),
@@ -581,7 +581,7 @@ def main() -> None:
             tcfg = load_run_config("trajectory_TRF_large")
             tl = measure_train(args, tcfg, "trajectory_TRF_large", 256, rank, world, local_rank, steps=20, warmup=5, e2e=False)
             aux.update({"train_workload": "trajectory_TRF_large training step (forward NLL + backward + Adam), batch 256 per GPU, "
-                                          "dropout on; gradients averaged by one NCCL all-reduce inside the step's CUDA graph",
+                                          "dropout on; gradients all-reduced (NCCL) in buckets underneath the backward, inside the step's CUDA graph",
                         "train_ms_per_step": tl["ms_per_step"], "train_samples_per_s": tl["value"], "train_n_gpus": world})
         except Exception as e:  # noqa: BLE001   (the headline must not depend on the auxiliary run)
             aux["train_error"] = repr(e)[:300]
