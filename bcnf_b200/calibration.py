@@ -56,7 +56,7 @@ def compute_y_hat_ranks(model: Any, y: torch.Tensor, *conditions: torch.Tensor, 
         for b in range(0, n, chunk):
             cs = [c[b: b + chunk] for c in conditions]
             nb = cs[0].shape[0]
-            P = flow.project(model.features(*cs))
+            P = model._projection(*cs)
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
             flow.sample_ranks(M_samples * nb, P, yd[b: b + nb], ranks[b: b + nb], seed=seed, sigma=1.0, inst_period=nb)
     return ranks.to(device=output_device, dtype=torch.int64)

@@ -580,11 +580,33 @@ class CondRealNVP_v2(ConditionalInvertibleLayer):
         dev = _as_device(self.device)
         if dev.type == "cuda" and not self.training:
             flow = self._flow()
-            passes = {"bf16x3": 3, "bf16": 1}.get(flow.precision, 0) if flow.kernel == "tcgen05" else 0
-            for fn in self.feature_network_stack.feature_networks:
-                if hasattr(fn, "tc_passes"):
-                    fn.tc_passes = passes
+            self._tc_passes(flow)
         return self.feature_network_stack(*[c.to(dev) for c in conditions])
+
+    def _tc_passes(self, flow: PackedFlow) -> int:
+        """Arithmetic mode of the handle (3 = bf16x3, 1 = bf16, 0 = no tensor-core path), handed on to the encoders."""
+        passes = {"bf16x3": 3, "bf16": 1}.get(flow.precision, 0) if flow.kernel == "tcgen05" else 0
+        for fn in self.feature_network_stack.feature_networks:
+            if hasattr(fn, "tc_passes"):
+                fn.tc_passes = passes
+        return passes
+
+    def _projection(self, *conditions: torch.Tensor) -> torch.Tensor:
+        """Raw conditions -> P (n_inst, proj_width), the hoisted condition terms of every conditioner's first Linear.
+
+        Eval mode on a tensor-core handle: the last feature network's affine output layer and the projection are ONE GEMM
+        (feature_tc.fused_projection; h is never materialised); otherwise features() followed by bcnf_cond_project."""
+        flow = self._flow()
+        dev = _as_device(self.device)
+        if not self.training and not self.feature_network_stack.training:
+            passes = self._tc_passes(flow)
+            if passes:
+                from . import feature_tc
+                P = feature_tc.fused_projection(self, flow, tuple(c.to(dev) for c in conditions), passes)
+                if P is not None:
+                    return P
+        with torch.no_grad():
+            return flow.project(self.features(*conditions))      # tensor-core handles: img_pack + GEMM; fp32: one SGEMM
 
     # -- reference API ------------------------------------------------------------------
     def forward(self, y: torch.Tensor, *conditions: torch.Tensor, log_det_J: bool = False,
@@ -595,6 +617,17 @@ class CondRealNVP_v2(ConditionalInvertibleLayer):
         ``bcnf_b200/train.py`` (conditioner dropout active, autograd history on z and ``log_det_J``); in
         eval mode through the fused inference kernels, without autograd history.
         """
+        if not self.training and not return_features and not deterministic_features:
+            # eval mode, h not asked for: features and projection fused (the log-prob / NLL evaluation path)
+            P = self._projection(*conditions)
+            if P.shape[0] != y.shape[0]:
+                raise ValueError(f"got {y.shape[0]} rows but {P.shape[0]} condition rows")
+            flow = self._flow()
+            with torch.no_grad():
+                z, ld = flow.run(False, y, P, want_logdet=log_det_J)
+            if log_det_J:
+                self.log_det_J = ld
+            return z
         if deterministic_features:
             self.feature_network_stack.eval()
             condition = self.features(*conditions).detach()
@@ -620,12 +653,12 @@ class CondRealNVP_v2(ConditionalInvertibleLayer):
     def inverse(self, z: torch.Tensor, *conditions: torch.Tensor) -> torch.Tensor:
         """cnf.py:495-508."""
         self._check_mode("inverse")
-        condition = self.features(*conditions)
-        if condition.shape[0] != z.shape[0]:
-            raise ValueError(f"got {z.shape[0]} rows but {condition.shape[0]} condition rows")
+        P = self._projection(*conditions)
+        if P.shape[0] != z.shape[0]:
+            raise ValueError(f"got {z.shape[0]} rows but {P.shape[0]} condition rows")
         flow = self._flow()
         with torch.no_grad():
-            return flow.run(True, z, flow.project(condition))[0]
+            return flow.run(True, z, P)[0]
 
     def log_prob(self, y: torch.Tensor, *conditions: torch.Tensor, reference_scale: bool = False) -> torch.Tensor:
         """New convenience (the reference has no log_prob).
@@ -718,8 +751,7 @@ class CondRealNVP_v2(ConditionalInvertibleLayer):
             for b in range(0, n_inst, chunk):
                 cs = [c[b: b + chunk] for c in conditions]
                 nb = cs[0].shape[0]
-                h = self.features(*cs)
-                P = flow.project(h)
+                P = self._projection(*cs)
                 # z = sigma * N(0, 1) is drawn inside the kernel (Philox keyed by one seed per chunk, taken from the
                 # generator like a torch.randn call would advance it): no z tensor, no torch.randn launch
                 seed = int(torch.randint(0, 2 ** 62, (1,), generator=generator, device=generator.device).item()) \

@@ -23,6 +23,7 @@
 #include "gemm_img2.cuh"
 #include "flow_tc2.cuh"
 #include "resim.cuh"
+#include "trf.cuh"
 
 using namespace bcnf;
 
@@ -1045,6 +1046,86 @@ extern "C" int bcnf_lstm_step(const bcnf_lstm_step_t* a, int32_t device, void* s
   g.lstm = 1; g.cell = a->cell; g.hsum = a->hsum; g.state_rows = a->state_rows;
   for (int t = 0; t < 4; ++t) { g.h_hi[t] = (unsigned char*)a->h_hi[t]; g.h_lo[t] = (unsigned char*)a->h_lo[t]; }
   return a->passes == 3 ? launch_gemm_img2<3>(g, n_sm, (cudaStream_t)stream) : launch_gemm_img2<1>(g, n_sm, (cudaStream_t)stream);
+}
+
+// ---- Transformer condition encoder: the kernels between its Linears (trf.cuh) ------------------------------------------
+static int trf_img_check(const char* who, const void* img, int64_t plane, int32_t rpad, int64_t rows, int32_t E) {
+  if (!img) return fail(BCNF_E_ARG, "%s: null image", who);
+  if (E < 8 || E % 8 || E > 1024) return fail(BCNF_E_ARG, "%s: E=%d must be a multiple of 8 in [8, 1024]", who, E);
+  if (rows < 0 || rows > 0x7fffff00LL) return fail(BCNF_E_ARG, "%s: rows=%lld", who, (long long)rows);
+  if (rpad % 32 || rpad < rows || plane < (long long)((E + 63) / 64) * rpad * 128)
+    return fail(BCNF_E_ARG, "%s: image too small (rpad=%d plane=%lld for %lld rows x %d)", who, rpad, (long long)plane, (long long)rows, E);
+  return BCNF_OK;
+}
+
+extern "C" int bcnf_trf_embed(const float* tokens, const float* Wf, const float* bf, const float* pos, int64_t rows, int32_t T,
+                              int32_t F, int32_t E, float* x, void* x_img, int64_t plane, int32_t rpad, int32_t device, void* stream) {
+  NVTX_RANGE("bcnf_trf_embed");
+  if (!tokens || !Wf || !bf || !x || T < 1 || F < 1) return fail(BCNF_E_ARG, "bcnf_trf_embed: bad argument");
+  if (int rc = trf_img_check("bcnf_trf_embed", x_img, plane, rpad, rows, E)) return rc;
+  if (rows == 0) return BCNF_OK;
+  DEVICE_GUARD(device);
+  TrfEmbedArgs a;
+  a.tokens = tokens; a.Wf = Wf; a.bf = bf; a.pos = pos; a.x = x;
+  a.x_img = (unsigned char*)x_img; a.plane = plane; a.rpad = rpad; a.rows = rows; a.T = T; a.F = F; a.E = E;
+  const long long threads = rows * (E / 8);
+  trf_embed_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  return BCNF_OK;
+}
+
+extern "C" int bcnf_trf_attention(const float* qkv, int64_t n_inst, int32_t T, int32_t E, int32_t heads, void* ctx_img,
+                                  int64_t plane, int32_t rpad, int32_t device, void* stream) {
+  NVTX_RANGE("bcnf_trf_attention");
+  if (!qkv || n_inst < 0 || T < 1 || T > kTrfMaxT || heads < 1 || E % heads)
+    return fail(BCNF_E_ARG, "bcnf_trf_attention: bad argument (T=%d must be in [1, %d], E=%d divisible by heads=%d)", T, kTrfMaxT, E, heads);
+  if (int rc = trf_img_check("bcnf_trf_attention", ctx_img, plane, rpad, n_inst * T, E)) return rc;
+  if (n_inst == 0) return BCNF_OK;
+  DEVICE_GUARD(device);
+  const int hd = E / heads;
+  if (hd != 8 && hd != 16 && hd != 32 && hd != 64)
+    return fail(BCNF_E_UNSUPPORTED, "bcnf_trf_attention: head width %d (supported: 8, 16, 32, 64)", hd);
+  const size_t smem = sizeof(float) * (size_t)T * 2 * E;
+  if (smem > 200 * 1024) return fail(BCNF_E_UNSUPPORTED, "bcnf_trf_attention: T=%d x E=%d does not fit shared memory", T, E);
+  void (*kern)(const TrfAttnArgs) = nullptr;
+  const bool small = T <= 32;
+  int slot = 0;
+  switch (hd) {
+    case 8: kern = small ? trf_attn_kernel<8, 32> : trf_attn_kernel<8, 64>; slot = 0; break;
+    case 16: kern = small ? trf_attn_kernel<16, 32> : trf_attn_kernel<16, 64>; slot = 1; break;
+    case 32: kern = small ? trf_attn_kernel<32, 32> : trf_attn_kernel<32, 64>; slot = 2; break;
+    default: kern = small ? trf_attn_kernel<64, 32> : trf_attn_kernel<64, 64>; slot = 3; break;
+  }
+  slot = 2 * slot + (small ? 0 : 1);
+  static size_t configured[64][8] = {};
+  if (smem > 48 * 1024 && (device >= 64 || configured[device][slot] < smem)) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (device < 64) configured[device][slot] = smem;
+  }
+  int n_sm = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+  TrfAttnArgs a;
+  a.qkv = qkv; a.ctx_img = (unsigned char*)ctx_img; a.plane = plane; a.rpad = rpad;
+  a.n_inst = n_inst; a.T = T; a.E = E; a.heads = heads; a.scale = 1.0f / sqrtf((float)hd);
+  const long long grid = std::min<long long>(n_inst, (long long)n_sm * 32);
+  kern<<<(unsigned)grid, kTrfAttnThreads, smem, (cudaStream_t)stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  return BCNF_OK;
+}
+
+extern "C" int bcnf_trf_add_layernorm(float* x, const float* y, const float* gamma, const float* beta, float eps, int64_t rows,
+                                      int32_t E, void* x_img, int64_t plane, int32_t rpad, int32_t device, void* stream) {
+  NVTX_RANGE("bcnf_trf_add_layernorm");
+  if (!x || !y || !gamma || !beta) return fail(BCNF_E_ARG, "bcnf_trf_add_layernorm: null argument");
+  if (int rc = trf_img_check("bcnf_trf_add_layernorm", x_img, plane, rpad, rows, E)) return rc;
+  if (rows == 0) return BCNF_OK;
+  DEVICE_GUARD(device);
+  TrfAddLnArgs a;
+  a.x = x; a.y = y; a.gamma = gamma; a.beta = beta; a.x_img = (unsigned char*)x_img; a.plane = plane; a.rpad = rpad;
+  a.rows = rows; a.E = E; a.eps = eps;
+  trf_add_ln_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  return BCNF_OK;
 }
 
 static void* g_g2_trace = nullptr;

@@ -352,6 +352,66 @@ gemm_img2_kernel(const G2Args g) {
           }
         }
         (void)i;
+      } else if ((g.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(g.C) & 15) == 0 && !(g.debug & 2)) {
+        // ---- fp32 tile, stores coalesced through a per-warp transpose ----
+        // A lane owns a row of the accumulator, so direct stores touch 32 lines per warp instruction, half a sector
+        // each (the fallback below: ~10 us per tile, which bounds every GEMM with K < ~600).  Instead each warp parks
+        // 32 rows x 32 columns in its own 4 KB of the staging area (16-byte units XOR-swizzled by row & 7: conflict-free
+        // both ways) and writes them back with 8 lanes per row: every store instruction covers four whole 128-byte lines.
+        unsigned char* wst = smem_g2 + Cfg::stg_off + (warp - 4) * 4096;
+        const long long row_w0 = (long long)tm * 256 + (long long)cta * 128 + q * 32;     // first row of this warp
+        const int rr0 = lane >> 3, uu = lane & 7;
+#pragma unroll 1
+        for (int c = 0; c < 128; c += 32) {
+          if (n_base + c >= g.N) break;
+          uint32_t r[4][8];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) tmem_ld8_issue(taddr + c + u * 8, r[u]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int n = n_base + c + u * 8;
+            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+            if (g.bias) {
+              if (n + 8 <= g.N) {
+                b0 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+                b1 = __ldg(reinterpret_cast<const float4*>(g.bias + n + 4));
+              } else {
+                float bb[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) bb[e] = n + e < g.N ? __ldg(g.bias + n + e) : 0.f;
+                b0 = make_float4(bb[0], bb[1], bb[2], bb[3]);
+                b1 = make_float4(bb[4], bb[5], bb[6], bb[7]);
+              }
+            }
+            *reinterpret_cast<float4*>(wst + lane * 128 + (((2 * u) ^ (lane & 7)) << 4)) =
+                make_float4(__uint_as_float(r[u][0]) + b0.x, __uint_as_float(r[u][1]) + b0.y,
+                            __uint_as_float(r[u][2]) + b0.z, __uint_as_float(r[u][3]) + b0.w);
+            *reinterpret_cast<float4*>(wst + lane * 128 + (((2 * u + 1) ^ (lane & 7)) << 4)) =
+                make_float4(__uint_as_float(r[u][4]) + b1.x, __uint_as_float(r[u][5]) + b1.y,
+                            __uint_as_float(r[u][6]) + b1.z, __uint_as_float(r[u][7]) + b1.w);
+          }
+          __syncwarp();
+          const int n = n_base + c + uu * 4;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + rr0;
+            const float4 v = *reinterpret_cast<const float4*>(wst + rr * 128 + ((uu ^ (rr & 7)) << 4));
+            const long long gi = row_w0 + rr;
+            if (gi < g.M) {
+              float* dst = g.C + gi * g.ldc + n;
+              if (n + 4 <= g.N) {
+                *reinterpret_cast<float4*>(dst) = v;
+              } else {
+                if (n < g.N) dst[0] = v.x;
+                if (n + 1 < g.N) dst[1] = v.y;
+                if (n + 2 < g.N) dst[2] = v.z;
+              }
+            }
+          }
+          __syncwarp();
+        }
+        (void)i;
       } else {
       float* crow = g.C + i * g.ldc;
 #pragma unroll 1

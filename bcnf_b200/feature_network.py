@@ -1,4 +1,5 @@
-"""Condition encoders (adjacent to the hot path; they stay plain PyTorch modules).
+"""Condition encoders (adjacent to the hot path; plain PyTorch modules whose eval-mode forward on a tensor-core handle
+is routed to bcnf_b200/feature_tc.py).
 
 Same class names, constructor arguments and parameter names as the reference's
 ``src/bcnf/models/feature_network.py`` so that ``state_dict`` keys under
@@ -66,12 +67,15 @@ class FeatureNetworkStack(FeatureNetwork):
         self.input_size = getattr(nets[0], "input_size", None)
         self.output_size = getattr(nets[-1], "output_size", None)
 
-    def forward(self, *conditions: torch.Tensor) -> torch.Tensor:
+    def forward(self, *conditions: torch.Tensor, skip_last: bool = False) -> torch.Tensor:
+        """``skip_last`` (bcnf_b200 only): stop in front of the last network and return its input -- the caller fuses
+        that network's affine output layer with the condition projection (feature_tc.fused_projection)."""
         if len(conditions) != self.n_distinct_conditions:
             raise ValueError(f"Expected {self.n_distinct_conditions} conditions, but got {len(conditions)}.")
         taken = 0
         feats: torch.Tensor | None = None
-        for fn in self.feature_networks:
+        nets = list(self.feature_networks)
+        for fn in nets[:-1] if skip_last else nets:
             if isinstance(fn, ConcatenateCondition):
                 raw = conditions[taken]
                 taken += 1
@@ -235,7 +239,13 @@ class Transformer(FeatureNetwork):
         pe[:, : self.input_size] = vals.to(torch.float32).to(device)
         return pe
 
+    tc_passes: int = 0      # set by CondRealNVP_v2 on tensor-core handles: 3 = bf16x3 (fp32-class), 1 = bf16, 0 = PyTorch
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.tc_passes and x.is_cuda and x.ndim == 3 and not self.training and _inference_call(x):
+            from . import feature_tc
+            if x.size(0) >= feature_tc.MIN_ROWS_TRF and x.size(1) <= 64 and feature_tc.transformer_supported(self):
+                return feature_tc.transformer_forward(self, x, self.tc_passes)
         x = self.dropout(self.features(x))
         if self.add_positional_embeddings:
             x = x + self._positional(x.size(1), x.device)

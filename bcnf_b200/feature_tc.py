@@ -26,6 +26,10 @@ MIN_ROWS_LSTM = int(os.environ.get("BCNF_FEATURE_TC_MIN_ROWS", "512"))   # measu
 _LSTM_TWO_STREAMS = os.environ.get("BCNF_LSTM_ONE_STREAM", "0") != "1"
 
 
+# kernels of libbcnf_b200.so launched by this module since import (bench.py reports the per-step count as gpu_launches)
+N_LAUNCH = [0]
+
+
 def supported(net: Any) -> bool:
     mods = list(net.nn)
     if not mods or not isinstance(mods[-1], nn.Linear):
@@ -57,8 +61,9 @@ def _weight_image(net: Any, lin: nn.Linear) -> _Img:
     return im
 
 
-def forward(net: Any, x: torch.Tensor, passes: int) -> torch.Tensor:
-    """x (rows, features) on a CUDA device -> h (rows, output_size), fp32."""
+def forward(net: Any, x: torch.Tensor, passes: int, stop_before_last: bool = False) -> Any:
+    """x (rows, features) on a CUDA device -> h (rows, output_size), fp32.  ``stop_before_last``: the operand image of
+    the last hidden activation instead (the A operand of the fused output-Linear + projection GEMM, fused_projection)."""
     dev = x.device
     x = x.reshape(x.size(0), -1).contiguous().float()
     rows = x.shape[0]
@@ -66,7 +71,11 @@ def forward(net: Any, x: torch.Tensor, passes: int) -> torch.Tensor:
     linears = [m for m in net.nn if isinstance(m, nn.Linear)]
     a = _img(dev, ("fc_in", id(net)), rows, x.shape[1], align=256)
     _pack_images([(x, 0, x.stride(0), 1, rows, x.shape[1], a)], dev)
+    N_LAUNCH[0] += 1
     for li, lin in enumerate(linears):
+        if stop_before_last and li == len(linears) - 1:
+            return a
+        N_LAUNCH[0] += 1
         wimg = _weight_image(net, lin)
         n_out, n_in = lin.weight.shape
         bias = lin.bias.detach() if lin.bias is not None else torch.zeros(n_out, device=dev)
@@ -142,7 +151,7 @@ def _lstm_weights(net: Any, layer: int, d: int, dev: torch.device) -> tuple[_Img
     return im, bias
 
 
-def lstm_forward(net: Any, x: torch.Tensor, passes: int) -> torch.Tensor:
+def lstm_forward(net: Any, x: torch.Tensor, passes: int, pooled_only: bool = False) -> torch.Tensor:
     """x (B, T, input_size) -> features (B, output_size).  One CTA-pair GEMM launch per layer, direction and time step
     (csrc/gemm_img2.cuh, LSTM-cell epilogue); the mean over time is accumulated by the last layer's epilogues and the
     output Linear runs once per pooled row."""
@@ -160,6 +169,7 @@ def lstm_forward(net: Any, x: torch.Tensor, passes: int) -> torch.Tensor:
     # x_t images
     ximg = [_img(dev, (tag, "x", t), B, F, align=256) for t in range(T)]
     _pack_images([(x, t * F, T * F, 1, B, F, ximg[t]) for t in range(T)], dev)
+    N_LAUNCH[0] += 1 + L * dirs * T
     zero_h = _img(dev, (tag, "h0"), B, hc * 64, align=256)              # h_(-1) = 0 (never written)
     state = net.__dict__.setdefault("_tc_lstm_state", {})
     if state.get("tag") != tag:
@@ -232,4 +242,219 @@ def lstm_forward(net: Any, x: torch.Tensor, passes: int) -> torch.Tensor:
         if two:
             cur.wait_stream(side)
     pooled = hsum[:, :, :B, :].permute(2, 0, 1, 3).reshape(B, dirs * H) * (1.0 / T)
+    if pooled_only:                     # fused_projection: the output Linear is folded into the projection GEMM
+        return pooled
     return torch.nn.functional.linear(pooled, net.linear.weight, net.linear.bias)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Transformer (reference feature_network.py:183-307): embedding -> post-norm blocks -> Linear on token 0
+# ------------------------------------------------------------------------------------------------------------------
+MIN_ROWS_TRF = int(os.environ.get("BCNF_FEATURE_TC_MIN_ROWS", "256"))
+_TRF_SLICE_ROWS = 1 << 19          # token rows per pass (scratch: ~2 GB at E = 128)
+
+
+def transformer_supported(net: Any) -> bool:
+    E = net.trf_size
+    if E % 8 or E > 1024 or len(net.layers) == 0 or any(p.dtype != torch.float32 for p in net.parameters()):
+        return False
+    for blk in net.layers:
+        att, ffn = blk.attention, list(blk.ffn)
+        if att.d_model != E or E % att.n_heads or att.n_heads * att.head_dim != E or att.head_dim not in (8, 16, 32, 64):
+            return False
+        if len(ffn) != 3 or not isinstance(ffn[0], nn.Linear) or not isinstance(ffn[2], nn.Linear) \
+                or not isinstance(ffn[1], nn.GELU) or ffn[1].approximate != "none" or ffn[0].out_features > 1024:
+            return False
+    return True
+
+
+def _matrix_image(w: torch.Tensor) -> _Img:
+    im = _Img(w.device, w.shape[0], w.shape[1], align=256)
+    wc = w.detach().contiguous()
+    _pack_images([(wc, 0, wc.stride(0), 1, wc.shape[0], wc.shape[1], im)], w.device)
+    return im
+
+
+def _trf_weights(net: Any) -> dict:
+    """Operand images of the encoder's matrices (q / k / v merged into one (3E, E) operand), per parameter version."""
+    key = tuple((p.data_ptr(), p._version) for p in net.parameters())
+    hit = net.__dict__.get("_tc_trf")
+    if hit is not None and hit["key"] == key:
+        return hit
+    blocks = []
+    with torch.no_grad():
+        for blk in net.layers:
+            att = blk.attention
+            wqkv = torch.cat([att.q_linear.weight, att.k_linear.weight, att.v_linear.weight], dim=0)
+            blocks.append({
+                "wqkv": _matrix_image(wqkv),
+                "bqkv": torch.cat([att.q_linear.bias, att.k_linear.bias, att.v_linear.bias]).contiguous(),
+                "wo": _matrix_image(att.fc_out.weight), "bo": att.fc_out.bias.detach().contiguous(),
+                "w1": _matrix_image(blk.ffn[0].weight), "b1": blk.ffn[0].bias.detach().contiguous(),
+                "w2": _matrix_image(blk.ffn[2].weight), "b2": blk.ffn[2].bias.detach().contiguous(),
+            })
+    hit = {"key": key, "blocks": blocks}
+    net.__dict__["_tc_trf"] = hit
+    return hit
+
+
+def transformer_token0(net: Any, x: torch.Tensor, passes: int) -> torch.Tensor:
+    """x (B, T, input_size) -> the encoder's state of token 0 after the last block, (B, trf_size) fp32 (eval mode: the
+    two nn.Dropout of feature_network.py:288,304 are identities).  Per block: one GEMM for q | k | v, the attention
+    kernel, fc_out, add + LayerNorm, FFN (GELU fused into the first GEMM's epilogue), add + LayerNorm."""
+    dev = x.device
+    x = x.contiguous().float()
+    B, T, F = x.shape
+    E = net.trf_size
+    lib, di = _cabi.lib(), dev.index or 0
+    W = _trf_weights(net)
+    pos = net._positional(T, dev).contiguous() if net.add_positional_embeddings else None
+    fw, fb = net.features.weight.detach().contiguous(), net.features.bias.detach().contiguous()
+    out = torch.empty(B, E, device=dev)
+    per = max(1, _TRF_SLICE_ROWS // T)
+    for b0 in range(0, B, per):
+        nb = min(per, B - b0)
+        rows = nb * T
+        tag = ("trf", id(net), rows)
+        xs = torch.empty(rows, E, device=dev)
+        ys = torch.empty(rows, E, device=dev)
+        qkv = torch.empty(rows, 3 * E, device=dev)
+        x_img = _img(dev, (tag, "x"), rows, E, align=256)
+        c_img = _img(dev, (tag, "ctx"), rows, E, align=256)
+        st = _stream(dev)
+        tok = x[b0: b0 + nb]
+        _cabi.check(lib.bcnf_trf_embed(tok.data_ptr(), fw.data_ptr(), fb.data_ptr(), pos.data_ptr() if pos is not None else None,
+                                       rows, T, F, E, xs.data_ptr(), x_img.ptr, x_img.plane, x_img.rpad, di, st), "bcnf_trf_embed")
+        N_LAUNCH[0] += 1 + 7 * len(net.layers)
+        for blk, w in zip(net.layers, W["blocks"]):
+            heads, ff = blk.attention.n_heads, blk.ffn[0].out_features
+            f_img = _img(dev, (tag, "ffn", ff), rows, ff, align=256)
+            _cabi.check(lib.bcnf_gemm_img(x_img.ptr, x_img.plane, x_img.rpad, w["wqkv"].ptr, w["wqkv"].plane, w["wqkv"].rpad,
+                                          qkv.data_ptr(), 3 * E, w["bqkv"].data_ptr(), rows, 3 * E, E, passes, di, st), "bcnf_gemm_img")
+            _cabi.check(lib.bcnf_trf_attention(qkv.data_ptr(), nb, T, E, heads, c_img.ptr, c_img.plane, c_img.rpad, di, st),
+                        "bcnf_trf_attention")
+            _cabi.check(lib.bcnf_gemm_img(c_img.ptr, c_img.plane, c_img.rpad, w["wo"].ptr, w["wo"].plane, w["wo"].rpad,
+                                          ys.data_ptr(), E, w["bo"].data_ptr(), rows, E, E, passes, di, st), "bcnf_gemm_img")
+            n1, n2 = blk.norm1, blk.norm2
+            _cabi.check(lib.bcnf_trf_add_layernorm(xs.data_ptr(), ys.data_ptr(), n1.weight.data_ptr(), n1.bias.data_ptr(), n1.eps,
+                                                   rows, E, x_img.ptr, x_img.plane, x_img.rpad, di, st), "bcnf_trf_add_layernorm")
+            _cabi.check(lib.bcnf_gemm_img_gelu(x_img.ptr, x_img.plane, x_img.rpad, w["w1"].ptr, w["w1"].plane, w["w1"].rpad,
+                                               w["b1"].data_ptr(), f_img.ptr, f_img.plane, f_img.rpad, rows, ff, E, passes, di, st),
+                        "bcnf_gemm_img_gelu")
+            _cabi.check(lib.bcnf_gemm_img(f_img.ptr, f_img.plane, f_img.rpad, w["w2"].ptr, w["w2"].plane, w["w2"].rpad,
+                                          ys.data_ptr(), E, w["b2"].data_ptr(), rows, E, ff, passes, di, st), "bcnf_gemm_img")
+            _cabi.check(lib.bcnf_trf_add_layernorm(xs.data_ptr(), ys.data_ptr(), n2.weight.data_ptr(), n2.bias.data_ptr(), n2.eps,
+                                                   rows, E, x_img.ptr, x_img.plane, x_img.rpad, di, st), "bcnf_trf_add_layernorm")
+        out[b0: b0 + nb] = xs.view(nb, T, E)[:, 0, :]
+    return out
+
+
+def transformer_forward(net: Any, x: torch.Tensor, passes: int) -> torch.Tensor:
+    """x (B, T, input_size) -> features (B, output_size): transformer_token0 + the output Linear on the same GEMM."""
+    u = transformer_token0(net, x, passes)
+    return _linear_tc(net, net.output, u, passes)
+
+
+def _linear_tc(owner: Any, lin: nn.Linear, u: torch.Tensor, passes: int) -> torch.Tensor:
+    """lin(u) for a fp32 matrix u (rows, in) on the CTA-pair GEMM."""
+    dev = u.device
+    rows, n_in = u.shape
+    a = _img(dev, ("lin_in", id(lin)), rows, n_in, align=256)
+    _pack_images([(u, 0, u.stride(0), 1, rows, n_in, a)], dev)
+    N_LAUNCH[0] += 2
+    wimg = _weight_image(owner, lin)
+    n_out = lin.weight.shape[0]
+    bias = lin.bias.detach() if lin.bias is not None else torch.zeros(n_out, device=dev)
+    h = torch.empty(rows, n_out, device=dev)
+    _cabi.check(_cabi.lib().bcnf_gemm_img(a.ptr, a.plane, a.rpad, wimg.ptr, wimg.plane, wimg.rpad, h.data_ptr(), n_out,
+                                          bias.data_ptr(), rows, n_out, n_in, passes, dev.index or 0, _stream(dev)), "bcnf_gemm_img")
+    return h
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Feature network fused with the condition projection (SURVEY.md section 8f-1)
+#
+# Every encoder of the reference ends in an affine layer (FullyConnected: the last nn.Linear, feature_network.py:141;
+# LSTM: self.linear, :158; Transformer: self.output, :282), and the only consumer of its output h inside the stack is
+# the h-part of each conditioner's first Linear (cnf.py:100-103), hoisted here into P = h . Wproj^T + bproj
+# (bcnf_cond_project).  Two affine maps compose:  P = u . (Wproj W_out)^T + (Wproj b_out + bproj)  with u the encoder's
+# last hidden state, so in eval mode ONE GEMM with K = width of u (310 / 280 / 128 for the BASELINE configs) replaces
+# the output Linear (K = width of u, N = 1360) AND the projection (K = 1360, N = proj_width): h is never materialised.
+# ------------------------------------------------------------------------------------------------------------------
+FUSE_PROJECTION = os.environ.get("BCNF_FUSE_PROJECTION", "1") != "0"
+
+
+def _composite(flow: Any, lin: nn.Linear) -> tuple[_Img, torch.Tensor]:
+    """Image of Wc = Wproj . W_out (proj_width x in_features) and bc = Wproj . b_out + bproj, per parameter version.
+
+    Wproj / bproj live packed inside the handle; they are read back through the projection itself, which is affine:
+    project(rows of W_out^T) - project(0) are the rows of Wc^T and project(b_out) is bc.  In the handle's own arithmetic
+    (bf16x3: fp32-class) -- a one-off (in_features + 2)-row projection per parameter update."""
+    flow.sync_params()
+    w, b = lin.weight, lin.bias
+    key = (flow._sig, w.data_ptr(), w._version, None if b is None else (b.data_ptr(), b._version))
+    hit = getattr(flow, "_composite", None)
+    if hit is not None and hit[0] == key:
+        return hit[1], hit[2]
+    with torch.no_grad():
+        n_out, n_in = w.shape
+        probe = torch.zeros(n_in + 2, n_out, device=w.device)
+        probe[:n_in] = w.detach().t()
+        if b is not None:
+            probe[n_in] = b.detach()
+        Pm = flow.project(probe)                         # (n_in + 2, proj_width)
+        wct = (Pm[:n_in] - Pm[n_in + 1]).contiguous()    # Wc^T
+        bc = Pm[n_in].contiguous()
+        im = _Img(w.device, flow.proj_width, n_in, align=256)
+        _pack_images([(wct, 0, 1, wct.stride(0), flow.proj_width, n_in, im)], w.device)
+    flow._composite = (key, im, bc)
+    return im, bc
+
+
+def fused_projection(model: Any, flow: Any, conditions: tuple, passes: int) -> torch.Tensor | None:
+    """P (n_inst, proj_width) straight from the raw conditions, or None when this stack / batch takes the two-step path."""
+    if not FUSE_PROJECTION or passes == 0 or flow.proj_width <= 0:
+        return None
+    from . import feature_network as fnm
+    stack = model.feature_network_stack
+    last = stack.feature_networks[-1]
+    dev = flow.device
+    with torch.no_grad():
+        feats = stack(*conditions, skip_last=True)
+        if feats is None or not feats.is_cuda or feats.dtype != torch.float32:
+            return None
+        rows = feats.shape[0]
+        if isinstance(last, fnm.FullyConnectedFeatureNetwork):
+            if rows < MIN_ROWS or not supported(last):
+                return None
+            lin = [m for m in last.nn if isinstance(m, nn.Linear)][-1]
+            a = forward(last, feats, passes, stop_before_last=True)
+        elif isinstance(last, fnm.LSTMFeatureNetwork):
+            if feats.ndim != 3 or rows < MIN_ROWS_LSTM or not lstm_supported(last):
+                return None
+            lin = last.linear
+            a = _as_image(lstm_forward(last, feats, passes, pooled_only=True), ("fuse_in", id(last)))
+        elif isinstance(last, fnm.Transformer):
+            if feats.ndim != 3 or rows < MIN_ROWS_TRF or feats.shape[1] > 64 or not transformer_supported(last):
+                return None
+            lin = last.output
+            a = _as_image(transformer_token0(last, feats, passes), ("fuse_in", id(last)))
+        else:
+            return None
+        if lin.weight.shape[0] != model.n_conditions:
+            return None
+        wc, bc = _composite(flow, lin)
+        N_LAUNCH[0] += 1
+        P = torch.empty(rows, flow.proj_width, device=dev)
+        _cabi.check(_cabi.lib().bcnf_gemm_img(a.ptr, a.plane, a.rpad, wc.ptr, wc.plane, wc.rpad, P.data_ptr(), flow.proj_width,
+                                              bc.data_ptr(), rows, flow.proj_width, lin.weight.shape[1], passes,
+                                              dev.index or 0, _stream(dev)), "bcnf_gemm_img")
+    return P
+
+
+def _as_image(u: torch.Tensor, tag: Any) -> _Img:
+    rows, k = u.shape
+    a = _img(u.device, tag, rows, k, align=256)
+    _pack_images([(u, 0, u.stride(0), 1, rows, k, a)], u.device)
+    N_LAUNCH[0] += 1
+    return a

@@ -40,6 +40,7 @@ WORKLOADS = {
     "fc_small_logprob": ("trajectory_FC_small", 1, 1 << 22, "log_prob"),
     "fc_large_logprob": ("trajectory_FC_large", 1, 1 << 17, "log_prob"),
     "lstm_large_logprob": ("trajectory_LSTM_large", 1, 1 << 17, "log_prob"),
+    "trf_large_logprob": ("trajectory_TRF_large", 1, 1 << 17, "log_prob"),
     "lstm_large_sample": ("trajectory_LSTM_large", 500, 10_000, "sample"),
     # calibration ranks (compute_y_hat_ranks, M = 10 000 samples per instance) reduced inside the sampler:
     # the (M, N, D) samples are never written, the output is (N, D) counters
@@ -469,10 +470,14 @@ def main() -> None:
         y_host = torch.randn(rows_step, d, generator=g).pin_memory()
         y_dev = y_host.to(device)
 
+    from bcnf_b200 import feature_tc
+
     def step_resident():
         with torch.no_grad():
-            h = model.features(cond_dev)
-            P = flow.project(h)
+            # features + projection as the model does it: one fused GEMM chain from 2 048 instances up (log-prob workloads),
+            # PyTorch feature network + bcnf_cond_project below (the 500-instance sampling steps)
+            n0 = feature_tc.N_LAUNCH[0]
+            P = model._projection(cond_dev)
             seed[0] += 1
             if kind == "sample":          # the latent is drawn inside the kernel (bcnf_flow_sample), as model.sample does
                 out = flow.sample(rows_step, P, seed=seed[0], inst_period=inst_step, out=out_buf)
@@ -480,9 +485,11 @@ def main() -> None:
                 out = flow.sample_ranks(rows_step, P, y_dev, ranks_dev, seed=seed[0], inst_period=inst_step)
             else:
                 out, _ = flow.run(False, y_dev, P, want_logdet=True)
-            # own kernels per step: the fused stack + the projection (tensor-core handles: img_pack of h + the CTA-pair
-            # GEMM; fp32 handles: one SGEMM); the feature network below 2 048 instances is PyTorch and not counted
-            launches[0] += 3 if flow.kernel == "tcgen05" else 2
+            # own kernels per step: the fused stack + either the feature-network / projection GEMM chain (counted by
+            # feature_tc where it runs) or bcnf_cond_project behind a PyTorch feature network (tensor-core handles:
+            # img_pack of h + the CTA-pair GEMM; fp32 handles: one SGEMM)
+            own = feature_tc.N_LAUNCH[0] - n0
+            launches[0] += 1 + (own if own else (2 if flow.kernel == "tcgen05" else 1))
             return out
 
     def step_e2e():
@@ -528,7 +535,7 @@ def main() -> None:
 
     # the fused stack kernel alone (roofline numerator/denominator)
     with torch.no_grad():
-        P = flow.project(model.features(cond_dev))
+        P = model._projection(cond_dev)
         zbuf = torch.randn((rows_step, d), device=device)
         k_steps = max(3, min(args.steps, 10))
 

@@ -250,6 +250,21 @@ typedef struct {
   int32_t N, passes, pad0, pad1;
 } bcnf_lstm_step_t;
 int bcnf_lstm_step(const bcnf_lstm_step_t* args, int32_t device, void* stream);
+/* Transformer condition encoder (reference src/bcnf/models/feature_network.py:183-307), inference: the pieces between
+ * its Linears, each leaving the operand image the next bcnf_gemm_img / bcnf_gemm_img_gelu reads (driver:
+ * bcnf_b200/feature_tc.py: transformer_forward).  rows = instances * T tokens; E = trf_size (multiple of 8, <= 1024);
+ * images as above with rpad a multiple of 256 covering rows.
+ *   bcnf_trf_embed:         x = tokens . Wf^T + bf (+ pos[t], the (T, E) positional table or NULL)  (:287-301) -> x fp32 + image
+ *   bcnf_trf_attention:     per instance and head softmax(q k^T / sqrt(E / heads)) v from qkv (rows, 3E) = q | k | v
+ *                           (:207-226, no mask) -> image of the concatenated heads; T <= 64, E / heads in {8, 16, 32, 64}
+ *   bcnf_trf_add_layernorm: x <- LayerNorm(x + y) * gamma + beta (post-norm block, :255-259; eps as nn.LayerNorm) -> x fp32
+ *                           in place + image */
+int bcnf_trf_embed(const float* tokens, const float* Wf, const float* bf, const float* pos, int64_t rows, int32_t T, int32_t F,
+                   int32_t E, float* x, void* x_img, int64_t plane, int32_t rpad, int32_t device, void* stream);
+int bcnf_trf_attention(const float* qkv, int64_t n_inst, int32_t T, int32_t E, int32_t heads, void* ctx_img, int64_t plane,
+                       int32_t rpad, int32_t device, void* stream);
+int bcnf_trf_add_layernorm(float* x, const float* y, const float* gamma, const float* beta, float eps, int64_t rows, int32_t E,
+                           void* x_img, int64_t plane, int32_t rpad, int32_t device, void* stream);
 /* Debug aid (tools/gemm_img_check.py --trace): device buffer of 74 x 16 x 4 uint64 for the per-tile globaltimer stamps
  * of the following bcnf_gemm_img launches; NULL switches it off. */
 int bcnf_gemm_img_set_trace(void* device_buffer);

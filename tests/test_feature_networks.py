@@ -3,8 +3,8 @@
 The reference's state_dicts load unchanged into bcnf_b200's modules (same parameter names) and the features h must
 match: FullyConnectedFeatureNetwork (feature_network.py:114-145), LSTMFeatureNetwork (:148-178; the reference pools
 over the batch axis, reproduced by pool_axis="reference"), Transformer (:263-307).  CPU: plain PyTorch path, 1e-6.
-GPU: the same modules on the device, and the tensor-core implementations of the FullyConnected / LSTM encoders
-(bcnf_b200/feature_tc.py) on a tiled batch large enough to take that path.
+GPU: the same modules on the device, and the tensor-core implementations of the FullyConnected / LSTM / Transformer
+encoders (bcnf_b200/feature_tc.py) on a tiled batch large enough to take that path.
 """
 import json
 import os
@@ -67,9 +67,10 @@ def test_features_match_the_reference_on_the_device(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["fc", "lstm_mean"])
+@pytest.mark.parametrize("name", ["fc", "lstm_mean", "transformer", "transformer_pos"])
 def test_tensor_core_feature_networks_match_the_reference(name):
-    """feature_tc.py (CTA-pair GEMM chain / LSTM-cell epilogue) on the fixture's instances tiled to 4096 rows."""
+    """feature_tc.py (CTA-pair GEMM chain / LSTM-cell epilogue / Transformer encoder kernels) on the fixture's instances
+    tiled to 4096 rows."""
     net = _build(name).to("cuda:0")
     x0 = torch.from_numpy(DATA[name + "/x"])
     reps = 4096 // x0.shape[0] + 1
@@ -81,6 +82,7 @@ def test_tensor_core_feature_networks_match_the_reference(name):
         h_ref = net(x)
     assert h.shape == h_ref.shape
     assert rel_err(h.cpu().numpy(), h_ref.cpu().numpy()) < 1e-4
-    if name == "fc":                      # row i of the tiled batch is instance i % B of the fixture
-        ref = np.tile(DATA["fc/h"], (reps, 1))[:4096]
+    assert not torch.equal(h, h_ref)      # (the tensor-core path did run)
+    if not name.startswith("lstm"):       # row i of the tiled batch is instance i % B of the fixture
+        ref = np.tile(DATA[name + "/h"], (reps, 1))[:4096]
         assert rel_err(h.cpu().numpy(), ref) < 1e-5

@@ -166,6 +166,104 @@ def test_lstm_feature_network_on_tensor_cores_matches_pytorch():
     assert e(h3, ref) < 5e-5
 
 
+def test_transformer_feature_network_on_tensor_cores_matches_pytorch():
+    """Transformer encoder of trajectory_TRF_large (8 post-norm blocks, d_model 128, 8 heads, 30 tokens; reference
+    feature_network.py:183-307): Linears on the CTA-pair GEMM, attention / add + LayerNorm / embedding as image-producing
+    kernels (csrc/trf.cuh), against the PyTorch module in fp64: stated tolerance 2e-5 of max|ref| for the 3-pass split."""
+    from bcnf_b200 import feature_tc
+    from bcnf_b200.feature_network import Transformer
+    torch.manual_seed(8)
+    net = Transformer(input_size=3, trf_size=128, n_heads=8, ff_size=128, n_blocks=8, output_size=1360, trf_dropout=0.1,
+                      dropout=0.5).to(DEV).eval()
+    assert feature_tc.transformer_supported(net)
+    with torch.no_grad():                 # LayerNorm gains / shifts away from their (1, 0) initialisation
+        for blk in net.layers:
+            for ln in (blk.norm1, blk.norm2):
+                ln.weight.uniform_(0.5, 1.5)
+                ln.bias.uniform_(-0.3, 0.3)
+    x = torch.randn(700, 30, 3, device=DEV)
+    with torch.no_grad():
+        ref = net.double()(x.double())
+        net.float()
+        h_torch = net(x)
+        net.tc_passes = 3
+        h3 = net(x)
+        h3_again = net(x)
+        net.tc_passes = 1
+        h1 = net(x)
+        # the image cache follows in-place parameter updates
+        net.layers[3].attention.k_linear.weight.mul_(1.25)
+        net.tc_passes = 0
+        ref2 = net.double()(x.double())
+        net.float()
+        net.tc_passes = 3
+        h3b = net(x)
+    e = lambda a, b: rel_err(a.double().cpu().numpy(), b.cpu().numpy())
+    print("transformer features: torch fp32", e(h_torch, ref), "bf16x3", e(h3, ref), "bf16", e(h1, ref))
+    assert not torch.equal(h3, h_torch)
+    assert torch.equal(h3, h3_again)
+    assert e(h3, ref) < 2e-5 and e(h3b, ref2) < 2e-5
+    assert e(h1, ref) < 3e-2
+
+
+def _encoder(kind):
+    if kind == "fc":
+        return bcnf_b200.FullyConnectedFeatureNetwork([90, 310, 310, 200], dropout=0.1), (30, 3)
+    if kind == "fc_single":
+        return bcnf_b200.FullyConnectedFeatureNetwork([90, 200]), (30, 3)
+    if kind == "lstm":
+        return bcnf_b200.LSTMFeatureNetwork(input_size=3, hidden_size=70, output_size=200, num_layers=2, dropout=0.1,
+                                            bidirectional=True, pooling="mean"), (30, 3)
+    return bcnf_b200.Transformer(input_size=3, trf_size=64, n_heads=4, ff_size=96, n_blocks=2, output_size=200), (30, 3)
+
+
+@pytest.mark.parametrize("kind", ["fc", "fc_single", "lstm", "transformer"])
+def test_feature_network_fused_with_the_projection(kind, monkeypatch):
+    """the encoder's affine output layer and the condition projection as ONE GEMM (P = u (Wproj W_out)^T +
+    Wproj b_out + bproj, feature_tc.fused_projection) against the two-step path (h = output layer, then bcnf_cond_project):
+    P within 1e-5 of max|P|, z / log-det of the stack within the 1e-5 / 2e-5 gates; follows in-place parameter updates."""
+    from bcnf_b200 import feature_tc
+    torch.manual_seed(11)
+    enc, cshape = _encoder(kind)
+    fnets = [bcnf_b200.ConcatenateCondition(None, 90 if kind.startswith("fc") else 3), enc]
+    model = CondRealNVP_v2(size=19, nested_sizes=[128] * 3, n_blocks=4, n_conditions=200, feature_networks=fnets,
+                           dropout=0.2, act_norm=True, precision="bf16x3").to(DEV).eval()
+    g = torch.Generator().manual_seed(12)
+    rows = 4200
+    y, c = torch.randn(rows, 19, generator=g), torch.randn(rows, *cshape, generator=g)
+    e = lambda a, b: rel_err(a.cpu().numpy(), b.cpu().numpy())
+
+    def both():
+        with torch.no_grad():
+            n0 = feature_tc.N_LAUNCH[0]
+            P_f = model._projection(c)
+            assert feature_tc.N_LAUNCH[0] > n0
+            z_f = model(y, c, log_det_J=True)
+            ld_f = model.log_det_J
+            monkeypatch.setattr(feature_tc, "FUSE_PROJECTION", False)
+            P_2 = model._projection(c)
+            z_2, h = model(y, c, log_det_J=True, return_features=True)
+            ld_2 = model.log_det_J
+            monkeypatch.setattr(feature_tc, "FUSE_PROJECTION", True)
+        assert h.shape == (rows, 200) and P_f.shape == P_2.shape and not torch.equal(P_f, P_2)
+        print(kind, "fused vs two-step: P", e(P_f, P_2), "z", e(z_f, z_2), "logdet", e(ld_f, ld_2))
+        assert e(P_f, P_2) < 1e-5 and e(z_f, z_2) < 1e-5 and e(ld_f, ld_2) < 2e-5
+
+    both()
+    with torch.no_grad():                 # the composite matrix is rebuilt after an update of either factor
+        last = model.feature_network_stack.feature_networks[-1]
+        out_lin = last.nn[-1] if kind.startswith("fc") else (last.linear if kind == "lstm" else last.output)
+        out_lin.weight.mul_(0.8)
+        coupling = next(l for l in model.layers if isinstance(l, bcnf_b200.ConditionalAffineCouplingLayer))
+        coupling.nn_a.linears()[0].weight.mul_(1.1)
+    both()
+    # below the row threshold the two-step path runs (PyTorch encoder + bcnf_cond_project)
+    with torch.no_grad():
+        n0 = feature_tc.N_LAUNCH[0]
+        model._projection(c[:16])
+        assert feature_tc.N_LAUNCH[0] == n0
+
+
 def test_tensorcore_agrees_with_fp32_kernels_on_golden_large_batch():
     # same weights through the FMA kernel and the 3-pass tensor-core kernel, many tiles per CTA pair
     m32 = _model(19, [128] * 3, 4, 32, "fp32")
