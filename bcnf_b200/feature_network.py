@@ -32,6 +32,68 @@ def _inference_call(x: torch.Tensor) -> bool:
     return not (torch.is_grad_enabled() and x.requires_grad)
 
 
+# ---- training: parameter gradients of the encoder's Linears off the dependency chain ------------------------------------
+# Set by bcnf_b200.train.Trainer for the duration of a step's forward pass (None otherwise: plain nn.Linear autograd).
+# At batch 256 the encoder's backward is a chain of ~500 launch-bound kernels; a Linear's weight gradient g^T x and bias
+# gradient sum(g) feed nothing but the optimizer, so they do not have to sit on that chain: the Function below returns
+# only dx and leaves the parameter gradients to a side stream (OffChain.defer), which the Trainer joins before the
+# gradient all-reduce / optimizer step.
+_OFF_CHAIN: Any = None
+
+
+class OffChain:
+    """Side streams for the deferred parameter gradients of one training step."""
+
+    def __init__(self, streams: list) -> None:
+        self.streams, self.keep, self.n = streams, [], 0
+
+    def defer(self, x: torch.Tensor, g: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None) -> None:
+        main = torch.cuda.current_stream(g.device)
+        st = self.streams[self.n % len(self.streams)]
+        self.n += 1
+        g2, x2 = g.reshape(-1, g.shape[-1]), x.reshape(-1, x.shape[-1])
+        st.wait_stream(main)
+        with torch.cuda.stream(st):
+            for p, d in ((weight, g2.t().mm(x2)), (bias, g2.sum(0) if bias is not None else None)):
+                if p is None or not p.requires_grad:
+                    continue
+                if p.grad is None:
+                    p.grad = d
+                else:
+                    p.grad.add_(d)
+        self.keep.append((g2, x2))          # alive until the join: the caching allocator must not hand them out earlier
+
+    def join(self, main: Any) -> None:
+        if self.n:
+            for st in self.streams:
+                main.wait_stream(st)
+        self.keep.clear()
+        self.n = 0
+
+
+class _OffChainLinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None, oc: OffChain):
+        ctx.save_for_backward(x, weight)
+        ctx.bias, ctx.oc = bias, oc
+        return F.linear(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, g: torch.Tensor):
+        x, weight = ctx.saved_tensors
+        dx = g.matmul(weight) if ctx.needs_input_grad[0] else None
+        ctx.oc.defer(x, g, weight, ctx.bias)
+        return dx, None, None, None
+
+
+def _linear(lin: nn.Linear, x: torch.Tensor) -> torch.Tensor:
+    """lin(x); inside a Trainer step on a CUDA device with the parameter gradients deferred to a side stream."""
+    oc = _OFF_CHAIN
+    if oc is not None and x.is_cuda and torch.is_grad_enabled() and lin.weight.requires_grad:
+        return _OffChainLinearFn.apply(x, lin.weight, lin.bias, oc)
+    return lin(x)
+
+
 class FeatureNetwork(nn.Module):
     """Base class: records ``input_size`` / ``output_size`` (reference feature_network.py:10-25)."""
     input_size: int
@@ -189,14 +251,14 @@ class MultiHeadAttention(nn.Module):
         b = query.size(0)
 
         def heads(t: torch.Tensor, lin: nn.Linear) -> torch.Tensor:
-            return lin(t).view(b, -1, self.n_heads, self.head_dim).transpose(1, 2)
+            return _linear(lin, t).view(b, -1, self.n_heads, self.head_dim).transpose(1, 2)
 
         q, k, v = heads(query, self.q_linear), heads(key, self.k_linear), heads(value, self.v_linear)
         scores = q @ k.transpose(-2, -1) / math.sqrt(self.head_dim)
         if mask is not None:
             scores = scores.masked_fill(mask == 0, -1e9)
         ctx = F.softmax(scores, dim=-1) @ v
-        return self.fc_out(ctx.transpose(1, 2).contiguous().view(b, -1, self.d_model))
+        return _linear(self.fc_out, ctx.transpose(1, 2).contiguous().view(b, -1, self.d_model))
 
 
 class TransformerBlock(nn.Module):
@@ -212,7 +274,11 @@ class TransformerBlock(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         x = self.norm1(x + self.dropout(self.attention(x, x, x)))
-        return self.norm2(x + self.dropout(self.ffn(x)))
+        if _OFF_CHAIN is not None and len(self.ffn) == 3:
+            f = _linear(self.ffn[2], self.ffn[1](_linear(self.ffn[0], x)))
+        else:
+            f = self.ffn(x)
+        return self.norm2(x + self.dropout(f))
 
 
 class Transformer(FeatureNetwork):
@@ -246,10 +312,10 @@ class Transformer(FeatureNetwork):
             from . import feature_tc
             if x.size(0) >= feature_tc.MIN_ROWS_TRF and x.size(1) <= 64 and feature_tc.transformer_supported(self):
                 return feature_tc.transformer_forward(self, x, self.tc_passes)
-        x = self.dropout(self.features(x))
+        x = self.dropout(_linear(self.features, x))
         if self.add_positional_embeddings:
             x = x + self._positional(x.size(1), x.device)
         for layer in self.layers:
             x = layer(x)
         x = self.dropout(x)
-        return self.output(x[:, 0, :])
+        return _linear(self.output, x[:, 0, :])

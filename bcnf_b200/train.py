@@ -219,6 +219,9 @@ _SIDE: dict[int, list[Any]] = {}
 # at the start of the step (0 = the previous behaviour) the 260 MB of images evict each other before they are read.
 _PACK_AHEAD = int(os.environ.get("BCNF_TRAIN_PACK_AHEAD", "2"))
 _PACK: dict[int, Any] = {}
+# Weight / bias gradients of the Transformer encoder's Linears on the side streams instead of the backward chain
+# (feature_network.OffChain; BCNF_TRAIN_ENC_OFF_CHAIN=0: plain nn.Linear autograd)
+_ENC_OFF_CHAIN = os.environ.get("BCNF_TRAIN_ENC_OFF_CHAIN", "1") != "0"
 
 
 def _pack_stream(dev: torch.device) -> torch.cuda.Stream:
@@ -979,8 +982,11 @@ class Trainer:
     def _backward(self, loss: torch.Tensor) -> None:
         """loss.backward(), with the stack's gradients written into the sink and all-reduced underneath the backward."""
         global _SINK
+        oc = getattr(self, "_oc", None)
         if self._sink is None:
             loss.backward()
+            if oc is not None:
+                oc.join(torch.cuda.current_stream(loss.device))
             if self.process_group is not None:
                 self._allreduce_grads()
             return
@@ -992,6 +998,8 @@ class Trainer:
         finally:
             _SINK = None
         self._sink.end(torch.cuda.current_stream(dev))
+        if oc is not None:                       # the encoder's deferred weight / bias gradients (feature_network.OffChain)
+            oc.join(torch.cuda.current_stream(dev))
         if self._world > 1:
             self._allreduce_other()
 
@@ -1017,10 +1025,26 @@ class Trainer:
         dist.all_reduce(flat, group=self.process_group)      # (already scaled by 1 / world through the loss)
         torch._foreach_copy_(grads, views)
 
+    def _off_chain(self, dev: torch.device) -> Any:
+        """Side streams for the encoder's deferred parameter gradients (feature_network.OffChain), or None."""
+        # (a torch DistributedDataParallel wrapper needs every gradient to pass its autograd hooks: plain path there)
+        if not _ENC_OFF_CHAIN or torch.device(dev).type != "cuda" or not self.model.training or hasattr(self.model, "module"):
+            return None
+        oc = getattr(self, "_oc", None)
+        if oc is None:
+            from .feature_network import OffChain
+            oc = self._oc = OffChain(_side_streams(torch.device(dev)))
+        return oc
+
     def _losses(self, y: torch.Tensor, *conditions: torch.Tensor):
+        from . import feature_network as _fn
         net = self._net()
         dev = net.device
-        z, h = self.model(y.to(dev), *[c.to(dev) for c in conditions], log_det_J=True, return_features=True)
+        _fn._OFF_CHAIN = self._off_chain(dev)
+        try:
+            z, h = self.model(y.to(dev), *[c.to(dev) for c in conditions], log_det_J=True, return_features=True)
+        finally:
+            _fn._OFF_CHAIN = None
         if self.hybrid_weight > 0:
             mse = self.mse_loss(net.prediction_head(h), y.to(dev))
         else:

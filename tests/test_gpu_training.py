@@ -473,3 +473,58 @@ def test_trainer_with_flat_adam_follows_torch_adam_and_replays_as_a_graph():
     tr.train_batch(y, c)
     assert torch.equal(before, opt.flat_p)
     tr.close()
+
+
+def test_encoder_parameter_gradients_off_the_backward_chain(monkeypatch):
+    """Trainer steps defer the weight / bias gradients of the Transformer encoder's Linears to side streams
+    (feature_network.OffChain: the backward chain only carries dx).  Same gradients as plain nn.Linear autograd
+    (dropout off: identical arithmetic up to the summation order of the bias sums), gradient accumulation over two
+    backward passes, and the captured step trains."""
+    from bcnf_b200 import feature_network as fnm
+
+    def make():
+        torch.manual_seed(21)
+        m = CondRealNVP_v2(size=19, nested_sizes=[64, 64], n_blocks=3, n_conditions=24,
+                           feature_networks=[bcnf_b200.ConcatenateCondition(None, 3),
+                                             bcnf_b200.Transformer(input_size=3, trf_size=32, n_heads=4, ff_size=48, n_blocks=2,
+                                                                   output_size=24, dropout=0.0, trf_dropout=0.0)],
+                           dropout=0.0, act_norm=True)
+        return m.to(DEV).train()
+    g = torch.Generator().manual_seed(22)
+    y, c = torch.randn(64, 19, generator=g), torch.randn(64, 30, 3, generator=g)
+    a, b = make(), make()
+    monkeypatch.setattr(train, "_ENC_OFF_CHAIN", False)
+    ta = bcnf_b200.Trainer(a, torch.optim.SGD(a.parameters(), lr=0.0))
+    loss_a, _, _, _ = ta._losses(y, c)
+    ta._backward(loss_a)
+    assert getattr(ta, "_oc", None) is None
+    monkeypatch.setattr(train, "_ENC_OFF_CHAIN", True)
+    tb = bcnf_b200.Trainer(b, torch.optim.SGD(b.parameters(), lr=0.0))
+    calls = []
+    orig = fnm.OffChain.defer
+    monkeypatch.setattr(fnm.OffChain, "defer", lambda self, *args: (calls.append(1), orig(self, *args))[1])
+    loss_b, _, _, _ = tb._losses(y, c)
+    assert fnm._OFF_CHAIN is None                           # only set while the forward pass runs
+    tb._backward(loss_b)
+    torch.cuda.synchronize()
+    assert len(calls) == 2 + 2 * 6                          # features, output, and six Linears per block
+    assert torch.equal(loss_a, loss_b)
+    for (n, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+        assert (pa.grad is None) == (pb.grad is None), n
+        if pa.grad is not None:
+            assert rel_err(pb.grad.cpu().numpy(), pa.grad.cpu().numpy()) < 2e-6, n
+    # a second backward accumulates into the existing .grad tensors
+    loss_b2, _, _, _ = tb._losses(y, c)
+    tb._backward(loss_b2)
+    torch.cuda.synchronize()
+    wa, wb = a.feature_network_stack.feature_networks[1].output.weight, b.feature_network_stack.feature_networks[1].output.weight
+    assert rel_err(wb.grad.cpu().numpy(), 2.0 * wa.grad.cpu().numpy()) < 2e-6
+    # the captured step (forward, backward with the side-stream gradients, Adam) replays and trains
+    m = make()
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3, capturable=True)
+    tr = bcnf_b200.Trainer(m, opt, cuda_graph=True)
+    first = tr.train_batch(y, c)[0]
+    for _ in range(20):
+        last = tr.train_batch(y, c)[0]
+    assert np.isfinite(last) and last < first
+    tr.close()
