@@ -28,7 +28,8 @@ EXPORTS = ["bcnf_abi_version", "bcnf_last_error", "bcnf_flow_create", "bcnf_flow
            "bcnf_flow_inverse", "bcnf_flow_sample", "bcnf_flow_sample_ranks", "bcnf_resimulate", "bcnf_train_gemm", "bcnf_train_colsum", "bcnf_train_dropout_mask",
            "bcnf_train_set_gemm_mode", "bcnf_train_gemm_trace", "bcnf_train_pre", "bcnf_train_post",
            "bcnf_train_post_bwd", "bcnf_train_pre_bwd", "bcnf_img_pack", "bcnf_gemm_img", "bcnf_gemm_img_gelu", "bcnf_gemm_img_set_trace", "bcnf_lstm_step",
-           "bcnf_adam_flat", "bcnf_train_nll", "bcnf_trf_embed", "bcnf_trf_attention", "bcnf_trf_add_layernorm"]
+           "bcnf_adam_flat", "bcnf_train_nll", "bcnf_trf_embed", "bcnf_trf_attention", "bcnf_trf_add_layernorm",
+           "bcnf_trf_attention_bwd", "bcnf_trf_gelu", "bcnf_trf_ln_param_grad"]
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU_DROP, EPI_DGELU_DROP = 0, 1, 2, 3
 
 
@@ -180,12 +181,19 @@ def lib() -> C.CDLL:
     L.bcnf_lstm_step.argtypes = [C.POINTER(LstmStep), C.c_int32, C.c_void_p]
     L.bcnf_gemm_img_gelu.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                      C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
-    L.bcnf_trf_embed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
-                                 C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
-    L.bcnf_trf_attention.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32,
-                                     C.c_int32, C.c_void_p]
-    L.bcnf_trf_add_layernorm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int64, C.c_int32,
-                                         C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
+    L.bcnf_trf_embed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                 C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
+    L.bcnf_trf_attention.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
+                                     C.c_int32, C.c_int32, C.c_void_p]
+    L.bcnf_trf_attention_bwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                         C.c_int32, C.c_void_p]
+    L.bcnf_trf_add_layernorm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int64,
+                                         C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                         C.c_int32, C.c_int32, C.c_void_p]
+    L.bcnf_trf_ln_param_grad.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
+                                         C.c_void_p, C.c_int32, C.c_void_p]
+    L.bcnf_trf_gelu.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                C.c_void_p]
     L.bcnf_img_pack.argtypes = [C.POINTER(ImgPackDesc), C.c_int32, C.c_int32, C.c_void_p]
     L.bcnf_train_pre.argtypes = [C.POINTER(TrainPreArgs), C.c_int32, C.c_void_p]
     L.bcnf_train_post.argtypes = [C.POINTER(TrainPostArgs), C.c_int32, C.c_void_p]

@@ -41,27 +41,54 @@ def _inference_call(x: torch.Tensor) -> bool:
 _OFF_CHAIN: Any = None
 
 
+def _wgrad(g2: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
+    """g2^T x2 for tall operands (rows >> columns).  cuBLAS runs the plain product as a handful of CTAs over the whole row
+    count (42-114 us for 7680 x 128: measured, profiles/r02b_train_step_kernels_cupti.txt); cut into row slabs it is one
+    batched GEMM that fills the GPU plus a small sum."""
+    rows = g2.shape[0]
+    for slabs in (32, 16, 8, 4):
+        if rows % slabs == 0 and rows // slabs >= 128 and g2.is_contiguous() and x2.is_contiguous():
+            r = rows // slabs
+            return torch.bmm(g2.view(slabs, r, -1).transpose(1, 2), x2.view(slabs, r, -1)).sum(0)
+    return g2.t().mm(x2)
+
+
 class OffChain:
     """Side streams for the deferred parameter gradients of one training step."""
 
     def __init__(self, streams: list) -> None:
         self.streams, self.keep, self.n = streams, [], 0
 
-    def defer(self, x: torch.Tensor, g: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None) -> None:
-        main = torch.cuda.current_stream(g.device)
+    @staticmethod
+    def accumulate(p: torch.Tensor | None, d: torch.Tensor) -> None:
+        """p.grad += d, as autograd's AccumulateGrad would (called on the side stream that computed d)."""
+        if p is None or not p.requires_grad:
+            return
+        if p.grad is None:
+            p.grad = d
+        else:
+            p.grad.add_(d)
+
+    def run(self, fn: Any, *keep: Any) -> None:
+        """fn() on the next side stream, after everything enqueued so far on the current stream.  ``keep``: the tensors fn
+        reads -- held until join(), so that the caching allocator cannot hand their memory out while fn is pending."""
         st = self.streams[self.n % len(self.streams)]
+        main = torch.cuda.current_stream(st.device)
         self.n += 1
-        g2, x2 = g.reshape(-1, g.shape[-1]), x.reshape(-1, x.shape[-1])
         st.wait_stream(main)
         with torch.cuda.stream(st):
-            for p, d in ((weight, g2.t().mm(x2)), (bias, g2.sum(0) if bias is not None else None)):
-                if p is None or not p.requires_grad:
-                    continue
-                if p.grad is None:
-                    p.grad = d
-                else:
-                    p.grad.add_(d)
-        self.keep.append((g2, x2))          # alive until the join: the caching allocator must not hand them out earlier
+            fn()
+        self.keep.append(keep)
+
+    def defer(self, x: torch.Tensor, g: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None) -> None:
+        """Parameter gradients of y = x W^T + b given g = dL/dy: dW = g^T x, db = sum over rows of g."""
+        g2, x2 = g.reshape(-1, g.shape[-1]), x.reshape(-1, x.shape[-1])
+
+        def grads():
+            self.accumulate(weight, _wgrad(g2, x2))
+            if bias is not None:
+                self.accumulate(bias, g2.sum(0))
+        self.run(grads, g2, x2)
 
     def join(self, main: Any) -> None:
         if self.n:
@@ -84,6 +111,41 @@ class _OffChainLinearFn(torch.autograd.Function):
         dx = g.matmul(weight) if ctx.needs_input_grad[0] else None
         ctx.oc.defer(x, g, weight, ctx.bias)
         return dx, None, None, None
+
+
+class _OffChainLayerNormFn(torch.autograd.Function):
+    """nn.LayerNorm whose backward computes dx on the chain and d gamma / d beta (a column reduction over all token rows
+    that only the optimizer reads) on a side stream: the same ATen kernels, selected through their output mask."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float, oc: OffChain):
+        out, mean, rstd = torch.ops.aten.native_layer_norm(x, [x.shape[-1]], weight, bias, eps)
+        ctx.save_for_backward(x, mean, rstd, weight)
+        ctx.bias, ctx.oc = bias, oc
+        return out
+
+    @staticmethod
+    def backward(ctx, g: torch.Tensor):
+        x, mean, rstd, weight = ctx.saved_tensors
+        g = g.contiguous()
+        shape = [x.shape[-1]]
+        dx = torch.ops.aten.native_layer_norm_backward(g, x, shape, mean, rstd, weight, ctx.bias, [True, False, False])[0]
+        oc, bias = ctx.oc, ctx.bias
+
+        def params_grad():
+            _, dw, db = torch.ops.aten.native_layer_norm_backward(g, x, shape, mean, rstd, weight, bias, [False, True, True])
+            oc.accumulate(weight, dw)
+            oc.accumulate(bias, db)
+        oc.run(params_grad, g, x, mean, rstd)
+        return dx, None, None, None, None
+
+
+def _layer_norm(ln: nn.LayerNorm, x: torch.Tensor) -> torch.Tensor:
+    oc = _OFF_CHAIN
+    if oc is not None and x.is_cuda and torch.is_grad_enabled() and ln.elementwise_affine and ln.bias is not None \
+            and ln.weight.requires_grad and len(ln.normalized_shape) == 1:
+        return _OffChainLayerNormFn.apply(x, ln.weight, ln.bias, ln.eps, oc)
+    return ln(x)
 
 
 def _linear(lin: nn.Linear, x: torch.Tensor) -> torch.Tensor:
@@ -273,12 +335,12 @@ class TransformerBlock(nn.Module):
         self.dropout = nn.Dropout(dropout)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        x = self.norm1(x + self.dropout(self.attention(x, x, x)))
+        x = _layer_norm(self.norm1, x + self.dropout(self.attention(x, x, x)))
         if _OFF_CHAIN is not None and len(self.ffn) == 3:
             f = _linear(self.ffn[2], self.ffn[1](_linear(self.ffn[0], x)))
         else:
             f = self.ffn(x)
-        return self.norm2(x + self.dropout(f))
+        return _layer_norm(self.norm2, x + self.dropout(f))
 
 
 class Transformer(FeatureNetwork):
@@ -312,6 +374,10 @@ class Transformer(FeatureNetwork):
             from . import feature_tc
             if x.size(0) >= feature_tc.MIN_ROWS_TRF and x.size(1) <= 64 and feature_tc.transformer_supported(self):
                 return feature_tc.transformer_forward(self, x, self.tc_passes)
+        if _OFF_CHAIN is not None and self.training and x.is_cuda and torch.is_grad_enabled():
+            from . import trf_train            # inside a Trainer step: own kernels forward, hand-written backward
+            if trf_train.usable(self, x):
+                return trf_train.forward(self, x, _OFF_CHAIN)
         x = self.dropout(_linear(self.features, x))
         if self.add_positional_embeddings:
             x = x + self._positional(x.size(1), x.device)

@@ -324,27 +324,29 @@ def transformer_token0(net: Any, x: torch.Tensor, passes: int) -> torch.Tensor:
         st = _stream(dev)
         tok = x[b0: b0 + nb]
         _cabi.check(lib.bcnf_trf_embed(tok.data_ptr(), fw.data_ptr(), fb.data_ptr(), pos.data_ptr() if pos is not None else None,
-                                       rows, T, F, E, xs.data_ptr(), x_img.ptr, x_img.plane, x_img.rpad, di, st), "bcnf_trf_embed")
+                                       None, rows, T, F, E, xs.data_ptr(), x_img.ptr, x_img.plane, x_img.rpad, di, st), "bcnf_trf_embed")
         N_LAUNCH[0] += 1 + 7 * len(net.layers)
         for blk, w in zip(net.layers, W["blocks"]):
             heads, ff = blk.attention.n_heads, blk.ffn[0].out_features
             f_img = _img(dev, (tag, "ffn", ff), rows, ff, align=256)
             _cabi.check(lib.bcnf_gemm_img(x_img.ptr, x_img.plane, x_img.rpad, w["wqkv"].ptr, w["wqkv"].plane, w["wqkv"].rpad,
                                           qkv.data_ptr(), 3 * E, w["bqkv"].data_ptr(), rows, 3 * E, E, passes, di, st), "bcnf_gemm_img")
-            _cabi.check(lib.bcnf_trf_attention(qkv.data_ptr(), nb, T, E, heads, c_img.ptr, c_img.plane, c_img.rpad, di, st),
+            _cabi.check(lib.bcnf_trf_attention(qkv.data_ptr(), nb, T, E, heads, None, c_img.ptr, c_img.plane, c_img.rpad, di, st),
                         "bcnf_trf_attention")
             _cabi.check(lib.bcnf_gemm_img(c_img.ptr, c_img.plane, c_img.rpad, w["wo"].ptr, w["wo"].plane, w["wo"].rpad,
                                           ys.data_ptr(), E, w["bo"].data_ptr(), rows, E, E, passes, di, st), "bcnf_gemm_img")
             n1, n2 = blk.norm1, blk.norm2
-            _cabi.check(lib.bcnf_trf_add_layernorm(xs.data_ptr(), ys.data_ptr(), n1.weight.data_ptr(), n1.bias.data_ptr(), n1.eps,
-                                                   rows, E, x_img.ptr, x_img.plane, x_img.rpad, di, st), "bcnf_trf_add_layernorm")
+            _cabi.check(lib.bcnf_trf_add_layernorm(xs.data_ptr(), ys.data_ptr(), None, n1.weight.data_ptr(), n1.bias.data_ptr(), n1.eps,
+                                                   rows, E, None, None, None, xs.data_ptr(), x_img.ptr, x_img.plane, x_img.rpad, di, st),
+                        "bcnf_trf_add_layernorm")
             _cabi.check(lib.bcnf_gemm_img_gelu(x_img.ptr, x_img.plane, x_img.rpad, w["w1"].ptr, w["w1"].plane, w["w1"].rpad,
                                                w["b1"].data_ptr(), f_img.ptr, f_img.plane, f_img.rpad, rows, ff, E, passes, di, st),
                         "bcnf_gemm_img_gelu")
             _cabi.check(lib.bcnf_gemm_img(f_img.ptr, f_img.plane, f_img.rpad, w["w2"].ptr, w["w2"].plane, w["w2"].rpad,
                                           ys.data_ptr(), E, w["b2"].data_ptr(), rows, E, ff, passes, di, st), "bcnf_gemm_img")
-            _cabi.check(lib.bcnf_trf_add_layernorm(xs.data_ptr(), ys.data_ptr(), n2.weight.data_ptr(), n2.bias.data_ptr(), n2.eps,
-                                                   rows, E, x_img.ptr, x_img.plane, x_img.rpad, di, st), "bcnf_trf_add_layernorm")
+            _cabi.check(lib.bcnf_trf_add_layernorm(xs.data_ptr(), ys.data_ptr(), None, n2.weight.data_ptr(), n2.bias.data_ptr(), n2.eps,
+                                                   rows, E, None, None, None, xs.data_ptr(), x_img.ptr, x_img.plane, x_img.rpad, di, st),
+                        "bcnf_trf_add_layernorm")
         out[b0: b0 + nb] = xs.view(nb, T, E)[:, 0, :]
     return out
 

@@ -250,21 +250,36 @@ typedef struct {
   int32_t N, passes, pad0, pad1;
 } bcnf_lstm_step_t;
 int bcnf_lstm_step(const bcnf_lstm_step_t* args, int32_t device, void* stream);
-/* Transformer condition encoder (reference src/bcnf/models/feature_network.py:183-307), inference: the pieces between
- * its Linears, each leaving the operand image the next bcnf_gemm_img / bcnf_gemm_img_gelu reads (driver:
- * bcnf_b200/feature_tc.py: transformer_forward).  rows = instances * T tokens; E = trf_size (multiple of 8, <= 1024);
- * images as above with rpad a multiple of 256 covering rows.
- *   bcnf_trf_embed:         x = tokens . Wf^T + bf (+ pos[t], the (T, E) positional table or NULL)  (:287-301) -> x fp32 + image
+/* Transformer condition encoder (reference src/bcnf/models/feature_network.py:183-307): the pieces between its Linears,
+ * each leaving the operand image the next bcnf_gemm_img / bcnf_gemm_img_gelu reads (drivers: bcnf_b200/feature_tc.py:
+ * transformer_token0 for inference, bcnf_b200/trf_train.py for the Trainer's step).  rows = instances * T tokens;
+ * E = trf_size (multiple of 8, <= 1024); images as above with rpad a multiple of 256 covering rows.  Pointers marked
+ * "opt" may be NULL; they are the training-mode extras (dropout multipliers in, tensors saved for the backward out).
+ *   bcnf_trf_embed:         x = (tokens . Wf^T + bf) * mask[opt] (+ pos[t], the (T, E) positional table, opt)  (:287-301)
+ *                           -> x fp32 + image
  *   bcnf_trf_attention:     per instance and head softmax(q k^T / sqrt(E / heads)) v from qkv (rows, 3E) = q | k | v
- *                           (:207-226, no mask) -> image of the concatenated heads; T <= 64, E / heads in {8, 16, 32, 64}
- *   bcnf_trf_add_layernorm: x <- LayerNorm(x + y) * gamma + beta (post-norm block, :255-259; eps as nn.LayerNorm) -> x fp32
- *                           in place + image */
-int bcnf_trf_embed(const float* tokens, const float* Wf, const float* bf, const float* pos, int64_t rows, int32_t T, int32_t F,
-                   int32_t E, float* x, void* x_img, int64_t plane, int32_t rpad, int32_t device, void* stream);
-int bcnf_trf_attention(const float* qkv, int64_t n_inst, int32_t T, int32_t E, int32_t heads, void* ctx_img, int64_t plane,
-                       int32_t rpad, int32_t device, void* stream);
-int bcnf_trf_add_layernorm(float* x, const float* y, const float* gamma, const float* beta, float eps, int64_t rows, int32_t E,
-                           void* x_img, int64_t plane, int32_t rpad, int32_t device, void* stream);
+ *                           (:207-226, no mask) -> image of the concatenated heads (+ fp32 ctx, opt); T <= 64,
+ *                           E / heads in {8, 16, 32, 64}
+ *   bcnf_trf_attention_bwd: its backward, d ctx (rows, E) -> d qkv (rows, 3E), probabilities recomputed from qkv; T <= 32
+ *   bcnf_trf_add_layernorm: x_out = LayerNorm(x + mask[opt] * y) * gamma + beta (post-norm block, :255-259; eps as
+ *                           nn.LayerNorm) -> x_out fp32 (may alias x) + image; s = x + mask * y, mean, rstd (rows) opt
+ *   bcnf_trf_gelu:          a = gelu(u) (nn.GELU, erf) for u (rows, N), N a multiple of 8 -> image (+ fp32 a, opt)
+ *   bcnf_trf_ln_param_grad: dgamma[c] += sum_rows g * (s - mean) * rstd, dbeta[c] += sum_rows g  (nn.LayerNorm's parameter
+ *                           gradients from the s / mean / rstd bcnf_trf_add_layernorm saved; the caller zeroes the outputs) */
+int bcnf_trf_embed(const float* tokens, const float* Wf, const float* bf, const float* pos, const float* mask, int64_t rows,
+                   int32_t T, int32_t F, int32_t E, float* x, void* x_img, int64_t plane, int32_t rpad, int32_t device,
+                   void* stream);
+int bcnf_trf_attention(const float* qkv, int64_t n_inst, int32_t T, int32_t E, int32_t heads, float* ctx, void* ctx_img,
+                       int64_t plane, int32_t rpad, int32_t device, void* stream);
+int bcnf_trf_attention_bwd(const float* qkv, const float* dctx, int64_t n_inst, int32_t T, int32_t E, int32_t heads,
+                           float* dqkv, int32_t device, void* stream);
+int bcnf_trf_add_layernorm(const float* x, const float* y, const float* mask, const float* gamma, const float* beta, float eps,
+                           int64_t rows, int32_t E, float* s, float* mean, float* rstd, float* x_out, void* x_img,
+                           int64_t plane, int32_t rpad, int32_t device, void* stream);
+int bcnf_trf_gelu(const float* u, int64_t rows, int32_t N, float* a, void* a_img, int64_t plane, int32_t rpad, int32_t device,
+                  void* stream);
+int bcnf_trf_ln_param_grad(const float* g, const float* s, const float* mean, const float* rstd, int64_t rows, int32_t E,
+                           float* dgamma, float* dbeta, int32_t device, void* stream);
 /* Debug aid (tools/gemm_img_check.py --trace): device buffer of 74 x 16 x 4 uint64 for the per-tile globaltimer stamps
  * of the following bcnf_gemm_img launches; NULL switches it off. */
 int bcnf_gemm_img_set_trace(void* device_buffer);

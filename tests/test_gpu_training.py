@@ -475,12 +475,27 @@ def test_trainer_with_flat_adam_follows_torch_adam_and_replays_as_a_graph():
     tr.close()
 
 
-def test_encoder_parameter_gradients_off_the_backward_chain(monkeypatch):
-    """Trainer steps defer the weight / bias gradients of the Transformer encoder's Linears to side streams
-    (feature_network.OffChain: the backward chain only carries dx).  Same gradients as plain nn.Linear autograd
-    (dropout off: identical arithmetic up to the summation order of the bias sums), gradient accumulation over two
-    backward passes, and the captured step trains."""
-    from bcnf_b200 import feature_network as fnm
+def _grad_close(got, ref, tol, name):
+    """Relative to max|ref|; a gradient that is identically zero in exact arithmetic (the key bias of an attention layer:
+    softmax is invariant to a shift of all scores of a query) is rounding noise on both sides."""
+    got, ref = got.detach().cpu().numpy(), ref.detach().cpu().numpy()
+    if name.endswith("k_linear.bias"):
+        assert np.abs(ref).max() < 1e-5 and np.abs(got).max() < 1e-5, (name, np.abs(ref).max(), np.abs(got).max())
+        return
+    assert rel_err(got, ref) < tol, (name, rel_err(got, ref))
+
+
+@pytest.mark.parametrize("kernels", [False, True], ids=["torch_modules", "own_kernels"])
+def test_encoder_parameter_gradients_off_the_backward_chain(kernels, monkeypatch):
+    """Trainer steps defer the weight / bias / LayerNorm gradients of the Transformer encoder to side streams
+    (feature_network.OffChain: the backward chain only carries dx), either around the PyTorch modules
+    (BCNF_TRAIN_TRF_KERNELS=0) or around the package's own forward kernels + hand-written backward (bcnf_b200/trf_train.py).
+    Same gradients as plain autograd through the modules (dropout off; PyTorch modules: identical arithmetic up to the
+    summation order of the bias sums; own kernels: 3-pass bf16 split GEMMs in the forward, stated tolerance 2e-5 of
+    max|ref grad|), gradient accumulation over two backward passes, and the captured step trains."""
+    from bcnf_b200 import feature_network as fnm, trf_train
+    monkeypatch.setattr(trf_train, "ENABLED", kernels)
+    tol = 2e-5 if kernels else 2e-6
 
     def make():
         torch.manual_seed(21)
@@ -489,6 +504,11 @@ def test_encoder_parameter_gradients_off_the_backward_chain(monkeypatch):
                                              bcnf_b200.Transformer(input_size=3, trf_size=32, n_heads=4, ff_size=48, n_blocks=2,
                                                                    output_size=24, dropout=0.0, trf_dropout=0.0)],
                            dropout=0.0, act_norm=True)
+        with torch.no_grad():
+            for blk in m.feature_network_stack.feature_networks[1].layers:
+                for ln in (blk.norm1, blk.norm2):
+                    ln.weight.uniform_(0.5, 1.5)
+                    ln.bias.uniform_(-0.3, 0.3)
         return m.to(DEV).train()
     g = torch.Generator().manual_seed(22)
     y, c = torch.randn(64, 19, generator=g), torch.randn(64, 30, 3, generator=g)
@@ -501,24 +521,30 @@ def test_encoder_parameter_gradients_off_the_backward_chain(monkeypatch):
     monkeypatch.setattr(train, "_ENC_OFF_CHAIN", True)
     tb = bcnf_b200.Trainer(b, torch.optim.SGD(b.parameters(), lr=0.0))
     calls = []
-    orig = fnm.OffChain.defer
-    monkeypatch.setattr(fnm.OffChain, "defer", lambda self, *args: (calls.append(1), orig(self, *args))[1])
+    orig = fnm.OffChain.run
+    monkeypatch.setattr(fnm.OffChain, "run", lambda self, fn, *keep: (calls.append(1), orig(self, fn, *keep))[1])
     loss_b, _, _, _ = tb._losses(y, c)
     assert fnm._OFF_CHAIN is None                           # only set while the forward pass runs
     tb._backward(loss_b)
     torch.cuda.synchronize()
-    assert len(calls) == 2 + 2 * 6                          # features, output, and six Linears per block
-    assert torch.equal(loss_a, loss_b)
+    # features, output, and per block: four LayerNorm / Linear groups + (q, k, v as one group | separately) + 2 LayerNorms
+    assert len(calls) == (2 + 2 * (4 + 2) if kernels else 2 + 2 * (6 + 2))
+    if kernels:
+        assert abs(float(loss_a.detach()) - float(loss_b.detach())) < 1e-4 * abs(float(loss_a.detach()))
+    else:
+        assert torch.equal(loss_a, loss_b)
     for (n, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
         assert (pa.grad is None) == (pb.grad is None), n
         if pa.grad is not None:
-            assert rel_err(pb.grad.cpu().numpy(), pa.grad.cpu().numpy()) < 2e-6, n
+            _grad_close(pb.grad, pa.grad, tol, n)
     # a second backward accumulates into the existing .grad tensors
     loss_b2, _, _, _ = tb._losses(y, c)
     tb._backward(loss_b2)
     torch.cuda.synchronize()
-    wa, wb = a.feature_network_stack.feature_networks[1].output.weight, b.feature_network_stack.feature_networks[1].output.weight
-    assert rel_err(wb.grad.cpu().numpy(), 2.0 * wa.grad.cpu().numpy()) < 2e-6
+    enc_a, enc_b = a.feature_network_stack.feature_networks[1], b.feature_network_stack.feature_networks[1]
+    for pa, pb in ((enc_a.output.weight, enc_b.output.weight), (enc_a.layers[0].attention.v_linear.bias, enc_b.layers[0].attention.v_linear.bias),
+                   (enc_a.layers[1].norm1.weight, enc_b.layers[1].norm1.weight)):
+        assert rel_err(pb.grad.cpu().numpy(), 2.0 * pa.grad.cpu().numpy()) < tol
     # the captured step (forward, backward with the side-stream gradients, Adam) replays and trains
     m = make()
     opt = torch.optim.Adam(m.parameters(), lr=1e-3, capturable=True)
@@ -528,3 +554,52 @@ def test_encoder_parameter_gradients_off_the_backward_chain(monkeypatch):
         last = tr.train_batch(y, c)[0]
     assert np.isfinite(last) and last < first
     tr.close()
+
+
+@pytest.mark.parametrize("pos", [False, True], ids=["plain", "positional"])
+def test_transformer_training_kernels_with_dropout_match_autograd(pos, monkeypatch):
+    """bcnf_b200/trf_train.py alone, dropout ON: the multiplier tensors it draws are recorded and fed to a functional
+    restatement of the module (feature_network.py:183-307) under plain autograd; features and every parameter gradient
+    must agree (2e-5 of max|ref|: the forward GEMMs are 3-pass bf16 splits)."""
+    import torch.nn.functional as F
+    from bcnf_b200 import feature_network as fnm, trf_train
+    torch.manual_seed(31)
+    net = bcnf_b200.Transformer(input_size=3, trf_size=64, n_heads=4, ff_size=96, n_blocks=3, output_size=40, dropout=0.5,
+                                trf_dropout=0.1, add_positional_embeddings=pos).to(DEV).train()
+    with torch.no_grad():
+        for blk in net.layers:
+            for ln in (blk.norm1, blk.norm2):
+                ln.weight.uniform_(0.5, 1.5)
+                ln.bias.uniform_(-0.3, 0.3)
+    B, T, E = 48, 30, 64
+    x = torch.randn(B, T, 3, device=DEV)
+    w = torch.randn(B, 40, device=DEV)
+    masks = []
+    orig = trf_train._mask
+    monkeypatch.setattr(trf_train, "_mask", lambda shape, p, dev: (masks.append(orig(shape, p, dev)), masks[-1])[1])
+    assert trf_train.usable(net, x)
+    oc = fnm.OffChain([torch.cuda.Stream(device=DEV), torch.cuda.Stream(device=DEV)])
+    h = trf_train.forward(net, x, oc)
+    (h * w).sum().backward()
+    oc.join(torch.cuda.current_stream(torch.device(DEV)))
+    torch.cuda.synchronize()
+    got = {n: p.grad.clone() for n, p in net.named_parameters()}
+    assert len(masks) == 3 and all(m is not None for m in masks)        # embedding, final state, all blocks at once
+    assert abs(float((masks[0] == 0).float().mean()) - 0.5) < 0.02 and abs(float((masks[2] == 0).float().mean()) - 0.1) < 0.02
+    masks = masks[:2] + list(masks[2])
+    net.zero_grad(set_to_none=True)
+    # functional restatement with the same multipliers
+    it = iter(masks)
+    m_in, m_out = next(it), next(it)
+    z = net.features(x) * m_in.view(B, T, E)
+    if pos:
+        z = z + net._positional(T, z.device)
+    for blk in net.layers:
+        m1, m2 = next(it), next(it)
+        z = blk.norm1(z + blk.attention(z, z, z) * m1.view(B, T, E))
+        z = blk.norm2(z + blk.ffn(z) * m2.view(B, T, E))
+    h_ref = net.output(z[:, 0, :] * m_out)
+    (h_ref * w).sum().backward()
+    assert rel_err(h.detach().cpu().numpy(), h_ref.detach().cpu().numpy()) < 2e-5
+    for n, p in net.named_parameters():
+        _grad_close(got[n], p.grad, 2e-5, n)
