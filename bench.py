@@ -345,11 +345,17 @@ def measure_train(args, cfg, cfg_key, batch, rank, world, local_rank, steps, war
         sampler.start()
     for _ in range(max(warmup, 3)):
         trainer.train_batch(y_dev, c_dev)
-    ms_total = timed(lambda: trainer.train_batch(y_dev, c_dev), steps)
+    # device-timed value: steps enqueued back to back (train_batch_async: the losses stay on the device, one synchronisation
+    # when the timed region closes); the e2e figure below goes through train_batch with host batches and reads the losses
+    # back every step, as the reference's loop does (trainer.py:271-277)
+    ms_total = timed(lambda: trainer.train_batch_async(y_dev, c_dev), steps)
     clocks = sampler.stop() if rank == 0 else {}
     e2e_steps = max(1, min(steps, 5))
     ms_e2e = timed(lambda: trainer.train_batch(y_host, c_host), e2e_steps) if e2e else None
     value = world * batch * steps / (ms_total * 1e-3)
+    enc = [fn for fn in (model.module if hasattr(model, "module") else model).feature_network_stack.feature_networks
+           if isinstance(fn, bcnf_b200.Transformer)]
+    n_enc_launches = sum(2 + 11 * len(fn.layers) for fn in enc)
     n_lin = len(mk["nested_sizes"]) + 1
     n_coupling = mk["n_blocks"] * (2 if mk.get("two_way") else 1)
     from oracle.flow_oracle import macs_per_row
@@ -368,13 +374,17 @@ def measure_train(args, cfg, cfg_key, batch, rank, world, local_rank, steps, war
                                        "gradients written into one flat buffer and all-reduced (NCCL) in buckets underneath the backward, inside the step's CUDA graph")},
             # per conditioner network: pre, hidden GEMMs, post; post_bwd, data-gradient GEMMs, pre_bwd; weight-gradient
             # GEMMs, P and d h GEMMs, two column sums, the operand-image pack (bcnf_b200/train.py)
-            "gpu_launches": steps * (n_coupling * (4 * (n_lin - 2) + 8) + 3),
+            # + the Transformer encoder on its own kernels (bcnf_b200/trf_train.py): weight-image pack, embedding, per block
+            # four GEMMs + attention + GELU + two add-LayerNorm forward, attention backward + two LayerNorm parameter
+            # gradients backward; + the optimizer launches of FlatAdam (one per gradient bucket + the remainder)
+            "gpu_launches": steps * (n_coupling * (4 * (n_lin - 2) + 8) + 3 + n_enc_launches + (5 if flat_adam else 0)),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": float(peaks["bf16_tflops"]), "unit": "TFLOP/s",
                          "frac": achieved / float(peaks["bf16_tflops"]), "traffic": None,
                          "peak_source": f"{peak_src} bf16 dense", "kernel": "train_tc2_gemm_kernel / train_tc3_dw_kernel (all launches of the step)",
                          "note": "algorithmic FLOPs (3 x forward) of the step / step time; at batch 256 the step is a chain of ~310 "
-                                 "dependent launches of ~10 us each plus the PyTorch feature network and Adam (SURVEY 8d: latency-, not "
-                                 "throughput-bound); --instances-per-step 4096 / 32768 shows the tensor-core rate"},
+                                 "dependent launches of ~10 us each for the stack plus ~150 for the Transformer encoder (own forward "
+                                 "kernels, hand-written backward; parameter gradients and the optimizer off the chain) (SURVEY 8d: "
+                                 "latency-, not throughput-bound); --instances-per-step 4096 / 32768 shows the tensor-core rate"},
             "clocks": clocks}
     if e2e:
         line["e2e"] = {"value": world * batch * e2e_steps / (ms_e2e * 1e-3), "unit": unit,
