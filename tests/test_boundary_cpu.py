@@ -278,3 +278,58 @@ def test_image_pool_leases_are_recycled_but_never_shared():
     assert c.images[0].buf.data_ptr() == ptr
     d = train._PoolLease(dev, [(8, 70)])                    # other shapes: other pool
     assert d.images[0].buf.data_ptr() not in (ptr, b.images[0].buf.data_ptr())
+
+
+def test_transformer_entry_points_validate_before_they_touch_the_device():
+    """bcnf_trf_* (include/bcnf_b200.h): argument checks run without a GPU."""
+    lib = _cabi.lib()
+    assert lib.bcnf_trf_embed(None, None, None, None, None, 8, 30, 3, 128, None, None, 0, 0, 0, None) == -1
+    assert lib.bcnf_trf_embed(16, 16, 16, None, None, 30, 30, 3, 100, 16, 16, 1 << 20, 256, 0, None) == -1     # E % 8
+    assert b"multiple of 8" in lib.bcnf_last_error()
+    assert lib.bcnf_trf_embed(16, 16, 16, None, None, 300, 30, 3, 128, 16, 16, 1 << 20, 256, 0, None) == -1    # image rows < rows
+    assert lib.bcnf_trf_attention(16, 4, 65, 128, 8, None, 16, 1 << 24, 512, 0, None) == -1                    # T > 64
+    assert lib.bcnf_trf_attention(16, 4, 30, 128, 5, None, 16, 1 << 24, 512, 0, None) == -1                    # E % heads
+    assert lib.bcnf_trf_attention(16, 4, 30, 96, 8, None, 16, 1 << 24, 512, 0, None) == -2                     # head width 12
+    assert lib.bcnf_trf_attention_bwd(16, 16, 4, 40, 128, 8, 16, 0, None) == -1                                # T > 32
+    assert lib.bcnf_trf_attention_bwd(None, 16, 4, 30, 128, 8, 16, 0, None) == -1
+    assert lib.bcnf_trf_add_layernorm(16, 16, None, 16, 16, 1e-5, 30, 128, None, 16, None, 16, 16, 1 << 20, 256, 0, None) == -1   # mean without rstd
+    assert lib.bcnf_trf_gelu(None, 30, 128, None, 16, 1 << 20, 256, 0, None) == -1
+    assert lib.bcnf_trf_ln_param_grad(16, 16, 16, 16, 30, 128, None, 16, 0, None) == -1
+    # empty problems are accepted without a launch
+    assert lib.bcnf_trf_gelu(16, 0, 128, None, 16, 1 << 20, 256, 0, None) == 0
+    assert lib.bcnf_trf_ln_param_grad(16, 16, 16, 16, 0, 128, 16, 16, 0, None) == 0
+
+
+def test_transformer_paths_only_take_what_they_reproduce_and_slab_weight_gradient():
+    """Host logic of the Transformer paths (feature_tc.transformer_supported, trf_train.usable) and of the slab-batched
+    weight gradient the side streams compute (feature_network._wgrad)."""
+    import torch
+    from torch import nn
+    from bcnf_b200 import feature_tc, trf_train
+    from bcnf_b200.feature_network import Transformer, _wgrad, OffChain
+    ok = Transformer(input_size=3, trf_size=128, n_heads=8, ff_size=128, n_blocks=8, output_size=1360)
+    assert feature_tc.transformer_supported(ok)
+    assert not feature_tc.transformer_supported(Transformer(3, 100, 4, 64, 1, 8))            # d_model % 8
+    assert not feature_tc.transformer_supported(Transformer(3, 96, 8, 64, 1, 8))             # head width 12
+    assert not feature_tc.transformer_supported(Transformer(3, 64, 4, 64, 1, 8).double())
+    tanh = Transformer(3, 64, 4, 64, 1, 8)
+    tanh.layers[0].ffn[1] = nn.GELU(approximate="tanh")
+    assert not feature_tc.transformer_supported(tanh)
+    assert not trf_train.usable(ok, torch.randn(4, 30, 3))                                    # CPU tensors: PyTorch modules
+    # eval mode on the CPU, and training mode outside a Trainer step, run the plain modules
+    ok.tc_passes = 3
+    with torch.no_grad():
+        assert ok.eval()(torch.randn(4, 30, 3)).shape == (4, 1360)
+    g = torch.Generator().manual_seed(0)
+    for rows in (7680, 4096, 96):          # 32 slabs of 240 / 32 slabs of 128 / too few rows: plain product
+        gg, xx = torch.randn(rows, 24, generator=g), torch.randn(rows, 40, generator=g)
+        ref = gg.double().t() @ xx.double()
+        assert torch.allclose(_wgrad(gg, xx).double(), ref, rtol=1e-5, atol=1e-4)
+    # OffChain.accumulate: the first gradient becomes .grad, later ones add to it; frozen parameters are skipped
+    p = nn.Parameter(torch.zeros(3))
+    OffChain.accumulate(p, torch.ones(3))
+    OffChain.accumulate(p, torch.ones(3))
+    assert torch.equal(p.grad, torch.full((3,), 2.0))
+    frozen = nn.Parameter(torch.zeros(3), requires_grad=False)
+    OffChain.accumulate(frozen, torch.ones(3))
+    assert frozen.grad is None
