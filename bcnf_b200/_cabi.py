@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(HERE)
 # BCNF_B200_LIB: load another build of the library (A/B timing of two kernel versions on the same box)
 LIB_PATH = os.environ.get("BCNF_B200_LIB") or os.path.join(HERE, "libbcnf_b200.so")
-SOURCES = [os.path.join(HERE, "csrc", "bcnf_abi.cu")]
+SOURCES = [os.path.join(HERE, "csrc", "bcnf_abi.cu"), os.path.join(HERE, "csrc", "trf_abi.cu")]
 HEADERS = sorted(os.path.join(HERE, "csrc", n) for n in os.listdir(os.path.join(HERE, "csrc"))
                  if n.endswith((".cuh", ".h"))) + [os.path.join(REPO, "include", "bcnf_b200.h")]
 
@@ -117,7 +117,8 @@ class LstmStep(C.Structure):
 
 def nvcc_command(out_path: str = LIB_PATH) -> list[str]:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    # (--threads: the two translation units compile side by side)
+    return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--threads", "2",
             "-shared", "-Xcompiler", "-fPIC", "-o", out_path] + SOURCES + ["-ldl"]
 
 

@@ -32,6 +32,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "img_store.cuh"   // pack_bf16x2
 #include "flow_rowthread.cuh"   // mbarrier / bulk-copy helpers
 
 namespace bcnf {
@@ -168,10 +169,6 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&p);
-}
 
 // store 8 consecutive activations (columns n0..n0+7 of `row`) as bf16 hi (and lo) into the tiles
 template <int NPASS>

@@ -343,11 +343,6 @@ train_tc_gemm_kernel(const GemmArgs g, const TgExtra x) {
 // Three warps issue the MMAs, one per pass of the 3-term split, each into its own accumulator; the epilogue adds them.
 // =====================================================================================================
 
-__device__ __forceinline__ float warp_sum_tc(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
 
 struct ImgArgs {
   const unsigned char* a_img; long long a_plane; int a_rpad;   // A(i, r): rows i (M), chunks over r (K)
@@ -369,26 +364,7 @@ struct T2Cfg {
   static constexpr int tmem_cols = 3 * BN <= 128 ? 128 : (3 * BN <= 256 ? 256 : 512);
 };
 
-// write 8 consecutive columns (n0 .. n0+7, n0 % 8 == 0) of `row` into an image
-__device__ __forceinline__ void img_store8(unsigned char* img, long long plane, int rpad, int row, int n0, const float (&v)[8]) {
-  const long long off = ((long long)(n0 >> 6) * rpad + row) * 128 + ((((n0 & 63) >> 3) ^ (row & 7)) << 4);
-  uint32_t hi[4], lo[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    hi[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-    const float h0 = __uint_as_float(hi[i] << 16), h1 = __uint_as_float(hi[i] & 0xffff0000u);
-    lo[i] = pack_bf16x2(v[2 * i] - h0, v[2 * i + 1] - h1);
-  }
-  *reinterpret_cast<uint4*>(img + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-  *reinterpret_cast<uint4*>(img + plane + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-}
-// single element (kernels whose threads own one column each)
-__device__ __forceinline__ void img_store1(unsigned char* img, long long plane, int rpad, int row, int n, float v) {
-  const long long off = ((long long)(n >> 6) * rpad + row) * 128 + ((((n & 63) >> 3) ^ (row & 7)) << 4) + ((n & 7) << 1);
-  const __nv_bfloat16 h = __float2bfloat16_rn(v);
-  *reinterpret_cast<__nv_bfloat16*>(img + off) = h;
-  *reinterpret_cast<__nv_bfloat16*>(img + plane + off) = __float2bfloat16_rn(v - __bfloat162float(h));
-}
+// (img_store8 / img_store1, the writers of the image format: img_store.cuh)
 
 template <int BN>
 __global__ void __launch_bounds__(kT2Threads, 1)

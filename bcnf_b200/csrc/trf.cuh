@@ -6,11 +6,11 @@
 //   trf_attn_kernel    q | k | v (rows, 3E) fp32 -> softmax(q k^T / sqrt(hd)) v per instance, head : image of the context
 //   trf_add_ln_kernel  x <- LayerNorm(x + y) * gamma + beta  (post-norm block, :255-259)      : fp32 x + image of x
 //
-// All arithmetic is fp32; an image is the bf16 hi / lo split of the fp32 value (train_tc.cuh: img_store8), so the GEMM
+// All arithmetic is fp32; an image is the bf16 hi / lo split of the fp32 value (img_store.cuh: img_store8), so the GEMM
 // that reads it sees the value to 2^-17.  HBM-bound kernels: every element is read once and written once (+ its image).
 #pragma once
 #include "common.cuh"
-#include "train_tc.cuh"
+#include "img_store.cuh"
 
 namespace bcnf {
 

@@ -372,7 +372,7 @@ class Transformer(FeatureNetwork):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if self.tc_passes and x.is_cuda and x.ndim == 3 and not self.training and _inference_call(x):
             from . import feature_tc
-            if x.size(0) >= feature_tc.MIN_ROWS_TRF and x.size(1) <= 64 and feature_tc.transformer_supported(self):
+            if x.size(0) >= feature_tc.MIN_ROWS_TRF and feature_tc.transformer_supported(self, x.size(1)):
                 return feature_tc.transformer_forward(self, x, self.tc_passes)
         if _OFF_CHAIN is not None and self.training and x.is_cuda and torch.is_grad_enabled():
             from . import trf_train            # inside a Trainer step: own kernels forward, hand-written backward

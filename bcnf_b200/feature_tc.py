@@ -254,8 +254,12 @@ MIN_ROWS_TRF = int(os.environ.get("BCNF_FEATURE_TC_MIN_ROWS", "256"))
 _TRF_SLICE_ROWS = 1 << 19          # token rows per pass (scratch: ~2 GB at E = 128)
 
 
-def transformer_supported(net: Any) -> bool:
+def transformer_supported(net: Any, n_tokens: int = 0) -> bool:
+    """Module shapes the kernels of csrc/trf.cuh reproduce; ``n_tokens``: the sequence length of the call (up to 32 tokens
+    for every head width in {8, 16, 32, 64}, up to 64 for head widths 8 and 16)."""
     E = net.trf_size
+    if n_tokens > 64 or (n_tokens > 32 and any(blk.attention.head_dim > 16 for blk in net.layers)):
+        return False
     if E % 8 or E > 1024 or len(net.layers) == 0 or any(p.dtype != torch.float32 for p in net.parameters()):
         return False
     for blk in net.layers:
@@ -437,7 +441,7 @@ def fused_projection(model: Any, flow: Any, conditions: tuple, passes: int) -> t
             lin = last.linear
             a = _as_image(lstm_forward(last, feats, passes, pooled_only=True), ("fuse_in", id(last)))
         elif isinstance(last, fnm.Transformer):
-            if feats.ndim != 3 or rows < MIN_ROWS_TRF or feats.shape[1] > 64 or not transformer_supported(last):
+            if feats.ndim != 3 or rows < MIN_ROWS_TRF or not transformer_supported(last, feats.shape[1]):
                 return None
             lin = last.output
             a = _as_image(transformer_token0(last, feats, passes), ("fuse_in", id(last)))

@@ -258,8 +258,8 @@ int bcnf_lstm_step(const bcnf_lstm_step_t* args, int32_t device, void* stream);
  *   bcnf_trf_embed:         x = (tokens . Wf^T + bf) * mask[opt] (+ pos[t], the (T, E) positional table, opt)  (:287-301)
  *                           -> x fp32 + image
  *   bcnf_trf_attention:     per instance and head softmax(q k^T / sqrt(E / heads)) v from qkv (rows, 3E) = q | k | v
- *                           (:207-226, no mask) -> image of the concatenated heads (+ fp32 ctx, opt); T <= 64,
- *                           E / heads in {8, 16, 32, 64}
+ *                           (:207-226, no mask) -> image of the concatenated heads (+ fp32 ctx, opt); E / heads in
+ *                           {8, 16, 32, 64} for T <= 32, in {8, 16} for T <= 64
  *   bcnf_trf_attention_bwd: its backward, d ctx (rows, E) -> d qkv (rows, 3E), probabilities recomputed from qkv; T <= 32
  *   bcnf_trf_add_layernorm: x_out = LayerNorm(x + mask[opt] * y) * gamma + beta (post-norm block, :255-259; eps as
  *                           nn.LayerNorm) -> x_out fp32 (may alias x) + image; s = x + mask * y, mean, rstd (rows) opt
