@@ -86,3 +86,28 @@ def test_tensor_core_feature_networks_match_the_reference(name):
     if not name.startswith("lstm"):       # row i of the tiled batch is instance i % B of the fixture
         ref = np.tile(DATA[name + "/h"], (reps, 1))[:4096]
         assert rel_err(h.cpu().numpy(), ref) < 1e-5
+
+
+def test_transformer_gradients_match_the_reference_cpu():
+    """Backward of the Transformer encoder against gradients recorded from the live reference
+    (tests/golden/make_transformer_grad_golden.py: training mode, dropouts at zero, scalar sum(h * w)).  The module here is
+    the autograd reference the GPU tests hold the Trainer's hand-written encoder backward against
+    (tests/test_gpu_training.py), so this pins that backward to the reference as well."""
+    data = np.load(os.path.join(GOLDEN_DIR, "transformer_grads.npz"))
+    meta = json.loads(str(data["meta"]))
+    net = fn.Transformer(**meta["kwargs"])
+    missing, unexpected = net.load_state_dict({k[3:]: torch.from_numpy(data[k]) for k in data.files if k.startswith("sd/")},
+                                              strict=True)
+    assert not missing and not unexpected
+    net.train()
+    h = net(torch.from_numpy(data["x"]))
+    (h * torch.from_numpy(data["w"])).sum().backward()
+    assert rel_err(h.detach().numpy(), data["h"]) < 1e-6
+    names = [k[5:] for k in data.files if k.startswith("grad/")]
+    assert sorted(names) == sorted(n for n, _ in net.named_parameters())
+    for n, p in net.named_parameters():
+        ref = data["grad/" + n]
+        if n.endswith("k_linear.bias"):          # identically zero in exact arithmetic (softmax shift invariance): noise
+            assert np.abs(ref).max() < 1e-5 and np.abs(p.grad.numpy()).max() < 1e-5
+            continue
+        assert rel_err(p.grad.numpy(), ref) < 1e-5, (n, rel_err(p.grad.numpy(), ref))
