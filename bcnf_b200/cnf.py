@@ -15,7 +15,6 @@ import ctypes as C
 import math
 from typing import Any, Sequence
 
-import numpy as np
 import torch
 import torch.nn as nn
 

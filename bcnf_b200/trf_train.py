@@ -19,7 +19,6 @@ import os
 from typing import Any
 
 import torch
-from torch import nn
 
 from . import _cabi
 from .feature_network import _wgrad
