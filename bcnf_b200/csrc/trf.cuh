@@ -1,13 +1,19 @@
-// Transformer condition encoder (reference src/bcnf/models/feature_network.py:183-307), inference: everything that is
-// not a Linear.  The Linears (q/k/v merged, fc_out, the two FFN layers, the output layer) run on the CTA-pair GEMM on
-// operand images (gemm_img2.cuh); the three kernels here produce those images:
+// Transformer condition encoder (reference src/bcnf/models/feature_network.py:183-307): everything that is not a Linear.
+// The Linears (q/k/v merged, fc_out, the two FFN layers, the output layer) run on the CTA-pair GEMM on operand images
+// (gemm_img2.cuh); the kernels here produce those images.  Inference (feature_tc.py) and the Trainer's step (trf_train.py):
 //
-//   trf_embed_kernel   tokens (B, T, F) -> x = tokens . Wf^T + bf (+ positional table)        : fp32 x + image of x
-//   trf_attn_kernel    q | k | v (rows, 3E) fp32 -> softmax(q k^T / sqrt(hd)) v per instance, head : image of the context
-//   trf_add_ln_kernel  x <- LayerNorm(x + y) * gamma + beta  (post-norm block, :255-259)      : fp32 x + image of x
+//   trf_embed_kernel    tokens (B, T, F) -> x = (tokens . Wf^T + bf) * mask (+ positional table)   : fp32 x + image of x
+//   trf_attn_kernel     q | k | v (rows, 3E) fp32 -> softmax(q k^T / sqrt(hd)) v per instance, head : image of the context
+//                                                                                                     (+ fp32 copy)
+//   trf_add_ln_kernel   x_out = LayerNorm(x + mask * y) * gamma + beta  (post-norm block, :255-259) : fp32 x_out + image
+//                                                                                   (+ LayerNorm input and statistics)
+//   trf_gelu_kernel     a = gelu(u)                                              (training)        : fp32 a + image of a
+//   trf_attn_bwd_kernel d ctx -> d q | d k | d v, probabilities recomputed       (training)        : fp32
+//   trf_ln_param_grad_kernel  d gamma, d beta of nn.LayerNorm                    (training)        : fp32, atomics
 //
-// All arithmetic is fp32; an image is the bf16 hi / lo split of the fp32 value (img_store.cuh: img_store8), so the GEMM
-// that reads it sees the value to 2^-17.  HBM-bound kernels: every element is read once and written once (+ its image).
+// `mask` = dropout multipliers (training; null in inference).  All arithmetic is fp32; an image is the bf16 hi / lo split
+// of the fp32 value (img_store.cuh: img_store8), so the GEMM that reads it sees the value to 2^-17.  In inference these are
+// HBM-bound kernels: every element is read once and written once (+ its image).
 #pragma once
 #include "common.cuh"
 #include "img_store.cuh"
