@@ -4,10 +4,12 @@ CPU only.  Tolerance: 1e-5 of max|ref| for the fp32 oracle (north_star: "within 
 relative (fp32)"; the reference's own fp32 result is only reproducible to ~1e-6 of scale
 across BLAS back ends), and 1e-12 for the fp64 oracle vs the fp64 reference.
 """
+import os
+
 import numpy as np
 import pytest
 
-from conftest import assert_parity, rel_err
+from conftest import GOLDEN_DIR, assert_parity, rel_err
 from oracle import flow_oracle as fo
 
 TOL32 = 1e-5
@@ -129,3 +131,28 @@ def test_macs_per_row_match_survey():
 def test_outer_row_map():
     m = fo.sample_outer_rows(3, 4)
     assert m.tolist() == [0, 1, 2, 3] * 3
+
+
+@pytest.mark.parametrize("name", ["transformer", "transformer_pos"])
+def test_transformer_oracle_matches_the_reference(name):
+    """oracle/transformer_oracle.py (numpy restatement of feature_network.py:183-307, eval mode) against the features the
+    live reference produced (tests/golden/feature_networks.npz): fp64 evaluation within 1e-6 of the fp32 reference."""
+    import json
+    from oracle import transformer_oracle as to
+    data = np.load(os.path.join(GOLDEN_DIR, "feature_networks.npz"))
+    kw = json.loads(str(data["meta"]))["cases"][name]["kwargs"]
+    sd = {k[len(name) + 4:]: data[k] for k in data.files if k.startswith(name + "/sd/")}
+    h = to.transformer_forward(sd, data[name + "/x"], n_heads=kw["n_heads"], n_blocks=kw["n_blocks"], input_size=kw["input_size"],
+                               add_positional_embeddings=kw.get("add_positional_embeddings", False))
+    assert h.shape == data[name + "/h"].shape
+    assert rel_err(h, data[name + "/h"]) < 1e-6
+
+
+def test_transformer_oracle_matches_the_training_mode_reference_with_dropout_off():
+    import json
+    from oracle import transformer_oracle as to
+    data = np.load(os.path.join(GOLDEN_DIR, "transformer_grads.npz"))
+    kw = json.loads(str(data["meta"]))["kwargs"]
+    sd = {k[3:]: data[k] for k in data.files if k.startswith("sd/")}
+    h = to.transformer_forward(sd, data["x"], n_heads=kw["n_heads"], n_blocks=kw["n_blocks"], input_size=kw["input_size"])
+    assert rel_err(h, data["h"]) < 1e-6
