@@ -3,7 +3,7 @@ SURVEY.md section 8f-1 / 8a12): forward on the package's own kernels, backward w
 
 At batch 256 the PyTorch module is a dependency chain of ~250 launch-bound kernels forward (a Linear alone is three:
 split-K SGEMM, reduction, bias epilogue) and ~300 backward: 2.6 + 2.3 ms of an 11 ms step.  Here the forward is the
-inference path of feature_tc.transformer_token0 -- seven launches per block: q | k | v GEMM, attention, fc_out GEMM,
+inference path of feature_tc.transformer_token0 -- eight launches per block: q | k | v GEMM, attention, fc_out GEMM,
 dropout + add + LayerNorm, FFN GEMM, GELU, FFN GEMM, dropout + add + LayerNorm -- with the tensors the backward needs
 written out by the same kernels, and the backward is eleven launches per block on the chain (LayerNorm and GELU through
 ATen's backward kernels, the attention core through bcnf_trf_attention_bwd, data gradients as cuBLAS GEMMs); every
